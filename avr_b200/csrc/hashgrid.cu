@@ -1,0 +1,432 @@
+// Ray generation + sampling + multiresolution hash-grid encode, forward and deterministic backward.
+//
+// Replaces: renderer.py:54-62,86-87 (ray points, normalisation, tx delays) and the tiny-cuda-nn
+// `kernel_grid` / `kernel_grid_backward` launched from model.py:191,219-220.
+//
+// Layout: a CTA owns 128 consecutive sample points n=(b,r,s) and all levels; threadIdx.y strides the
+// levels so 4 x 8 gathers are in flight per point.  Encoded rows are staged in shared memory and
+// written as contiguous rows.  The backward recomputes the sample positions (nothing is saved) and
+// accumulates 2^e-scaled int64 contributions with red.global.add.u64 -- integer addition is
+// associative, so the result is bit-identical from run to run regardless of scheduling.
+#include <math.h>
+#include "common.cuh"
+
+namespace avr {
+
+struct GridDev {
+    int n_levels;
+    float scale[AVR_MAX_LEVELS];
+    uint32_t res[AVR_MAX_LEVELS];
+    uint32_t size[AVR_MAX_LEVELS];
+    uint32_t offset[AVR_MAX_LEVELS];
+};
+
+static GridDev make_grid(const avr_grid_meta* g) {
+    GridDev d;
+    d.n_levels = g->n_levels;
+    for (int l = 0; l < AVR_MAX_LEVELS; ++l) {
+        d.scale[l] = g->scale[l]; d.res[l] = g->res[l]; d.size[l] = g->size[l]; d.offset[l] = g->offset[l];
+    }
+    return d;
+}
+
+constexpr int ENC_PTS = 128;   // points per CTA
+constexpr int ENC_LG = 4;      // level groups (threadIdx.y)
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t res, uint32_t size) {
+    uint64_t stride = 1;
+    uint32_t index = cx;                          // stride 1 <= size always
+    stride *= res;
+    if (stride <= size) {
+        index += cy * (uint32_t)stride;
+        stride *= res;
+        if (stride <= size) {
+            index += cz * (uint32_t)stride;
+            stride *= res;
+        }
+    }
+    if (size < stride) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+    return index % size;
+}
+
+struct Cell {
+    uint32_t gx, gy, gz;
+    float wx, wy, wz;
+};
+
+__device__ __forceinline__ Cell locate(float scale, float ux, float uy, float uz) {
+    Cell c;
+    float px = __fmaf_rn(scale, ux, 0.5f), py = __fmaf_rn(scale, uy, 0.5f), pz = __fmaf_rn(scale, uz, 0.5f);
+    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    c.gx = (uint32_t)(int)fx; c.gy = (uint32_t)(int)fy; c.gz = (uint32_t)(int)fz;
+    c.wx = px - fx; c.wy = py - fy; c.wz = pz - fz;
+    return c;
+}
+
+__device__ __forceinline__ float corner_weight(const Cell& c, int corner) {
+    float w = (corner & 1) ? c.wx : (1.0f - c.wx);
+    w = __fmul_rn(w, (corner & 2) ? c.wy : (1.0f - c.wy));
+    w = __fmul_rn(w, (corner & 4) ? c.wz : (1.0f - c.wz));
+    return w;
+}
+
+__device__ __forceinline__ float2 encode_level(const GridDev& g, int l, const float2* __restrict__ table,
+                                               float ux, float uy, float uz) {
+    const Cell c = locate(g.scale[l], ux, uy, uz);
+    const uint32_t res = g.res[l], size = g.size[l];
+    const float2* base = table + g.offset[l];
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t idx = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
+        v[k] = __ldg(base + idx);
+    }
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = corner_weight(c, k);
+        r0 = fmaf(w, v[k].x, r0);
+        r1 = fmaf(w, v[k].y, r1);
+    }
+    return make_float2(r0, r1);
+}
+
+// exponent e of the fixed-point scale 2^e: gmax * 2^e < 2^(62 - headroom).  ok=false -> skip.
+__device__ __forceinline__ int fixed_exponent(uint32_t gmax_bits, int headroom, bool& ok, bool& poisoned) {
+    float gmax = __uint_as_float(gmax_bits);
+    poisoned = !(gmax <= 3.0e38f);                 // inf or nan reached the gradient
+    ok = (gmax > 0.f) && !poisoned;
+    int ex = 0;
+    if (ok) frexpf(gmax, &ex);                     // gmax = m * 2^ex, m in [0.5, 1)
+    int e = (62 - headroom) - ex;
+    return max(-120, min(120, e));
+}
+
+__device__ __forceinline__ void scatter_level(const GridDev& g, int l, float ux, float uy, float uz, float g0,
+                                              float g1, float sc, unsigned long long* __restrict__ acc) {
+    const Cell c = locate(g.scale[l], ux, uy, uz);
+    const uint32_t res = g.res[l], size = g.size[l];
+    unsigned long long* base = acc + 2ull * g.offset[l];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t idx = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
+        float w = corner_weight(c, k);
+        long long q0 = __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc));
+        long long q1 = __float2ll_rn(__fmul_rn(__fmul_rn(w, g1), sc));
+        if (q0 != 0) atomicAdd(base + 2ull * idx, (unsigned long long)q0);
+        if (q1 != 0) atomicAdd(base + 2ull * idx + 1, (unsigned long long)q1);
+    }
+}
+
+// unit-cube position of sample n=(b,r,s); optionally its tx delay
+__device__ __forceinline__ void sample_unit(const Geom& geo, int64_t n, const float* __restrict__ rays_o,
+                                            const float* __restrict__ dirs, const float* __restrict__ d_vals,
+                                            float& ux, float& uy, float& uz, float& nx, float& ny, float& nz, int& b) {
+    const int64_t P = (int64_t)geo.R * geo.S;
+    b = (int)(n / P);
+    const int rem = (int)(n - (int64_t)b * P);
+    const int r = rem / geo.S, s = rem - r * geo.S;
+    const float d = __ldg(d_vals + s);
+    nx = to_unit(ray_point(__ldg(rays_o + 3 * b + 0), __ldg(dirs + 3 * r + 0), d), geo.lo, geo.span);
+    ny = to_unit(ray_point(__ldg(rays_o + 3 * b + 1), __ldg(dirs + 3 * r + 1), d), geo.lo, geo.span);
+    nz = to_unit(ray_point(__ldg(rays_o + 3 * b + 2), __ldg(dirs + 3 * r + 2), d), geo.lo, geo.span);
+    ux = to_cube(nx); uy = to_cube(ny); uz = to_cube(nz);
+}
+
+template <bool RAYGEN>
+__global__ void __launch_bounds__(ENC_PTS* ENC_LG)
+encode_fwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t n_pts, const float* __restrict__ rays_o,
+                  const float* __restrict__ pos_tx, const float* __restrict__ dirs, const float* __restrict__ d_vals,
+                  const float* __restrict__ u_in, const float2* __restrict__ table, float* __restrict__ out,
+                  int64_t ld_out, int col0, int n_ones, int* __restrict__ delay) {
+    extern __shared__ float tile[];
+    const int W = 2 * grid.n_levels + n_ones;
+    const int Wp = W | 1;                                   // odd stride: conflict-free column writes
+    const int p = threadIdx.x, lg = threadIdx.y;
+    const int64_t n = (int64_t)blockIdx.x * ENC_PTS + p;
+    if (n < n_pts) {
+        float ux, uy, uz;
+        if (RAYGEN) {
+            float nx, ny, nz;
+            int b;
+            sample_unit(geo, n, rays_o, dirs, d_vals, ux, uy, uz, nx, ny, nz, b);
+            if (lg == 0 && delay != nullptr) {
+                float tx0 = to_unit(__ldg(pos_tx + 3 * b + 0), geo.lo, geo.span);
+                float tx1 = to_unit(__ldg(pos_tx + 3 * b + 1), geo.lo, geo.span);
+                float tx2 = to_unit(__ldg(pos_tx + 3 * b + 2), geo.lo, geo.span);
+                delay[n] = source_delay(tx0, tx1, tx2, nx, ny, nz, geo);
+            }
+        } else {
+            ux = __ldg(u_in + 3 * n + 0); uy = __ldg(u_in + 3 * n + 1); uz = __ldg(u_in + 3 * n + 2);
+        }
+        for (int l = lg; l < grid.n_levels; l += ENC_LG) {
+            float2 v = encode_level(grid, l, table, ux, uy, uz);
+            tile[p * Wp + 2 * l] = v.x;
+            tile[p * Wp + 2 * l + 1] = v.y;
+        }
+        if (lg == 0)
+            for (int c = 0; c < n_ones; ++c) tile[p * Wp + 2 * grid.n_levels + c] = 1.0f;
+    }
+    __syncthreads();
+    const int tid = lg * ENC_PTS + p;
+    const int64_t n0 = (int64_t)blockIdx.x * ENC_PTS;
+    for (int idx = tid; idx < ENC_PTS * W; idx += ENC_PTS * ENC_LG) {
+        const int pp = idx / W, c = idx - pp * W;
+        if (n0 + pp < n_pts) out[(n0 + pp) * ld_out + col0 + c] = tile[pp * Wp + c];
+    }
+}
+
+template <bool RAYGEN>
+__global__ void __launch_bounds__(ENC_PTS* ENC_LG)
+encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t n_pts, const float* __restrict__ rays_o,
+                  const float* __restrict__ dirs, const float* __restrict__ d_vals, const float* __restrict__ u_in,
+                  const float* __restrict__ d_out, int64_t ld_out, int col0, const uint32_t* __restrict__ gmax_bits,
+                  int headroom, unsigned long long* __restrict__ acc) {
+    extern __shared__ float tile[];
+    bool ok, poisoned;
+    const int e = fixed_exponent(__ldg(gmax_bits), headroom, ok, poisoned);
+    if (!ok) return;                                        // zero (or poisoned) gradient: nothing to add
+    const float sc = ldexpf(1.0f, e);
+    const int W = 2 * grid.n_levels;
+    const int Wp = W | 1;
+    const int p = threadIdx.x, lg = threadIdx.y;
+    const int tid = lg * ENC_PTS + p;
+    const int64_t n0 = (int64_t)blockIdx.x * ENC_PTS;
+    for (int idx = tid; idx < ENC_PTS * W; idx += ENC_PTS * ENC_LG) {
+        const int pp = idx / W, c = idx - pp * W;
+        tile[pp * Wp + c] = (n0 + pp < n_pts) ? __ldg(d_out + (n0 + pp) * ld_out + col0 + c) : 0.f;
+    }
+    __syncthreads();
+    const int64_t n = n0 + p;
+    if (n >= n_pts) return;
+    float ux, uy, uz;
+    if (RAYGEN) {
+        float nx, ny, nz;
+        int b;
+        sample_unit(geo, n, rays_o, dirs, d_vals, ux, uy, uz, nx, ny, nz, b);
+    } else {
+        ux = __ldg(u_in + 3 * n + 0); uy = __ldg(u_in + 3 * n + 1); uz = __ldg(u_in + 3 * n + 2);
+    }
+    for (int l = lg; l < grid.n_levels; l += ENC_LG) {
+        const float g0 = tile[p * Wp + 2 * l], g1 = tile[p * Wp + 2 * l + 1];
+        if (g0 != 0.f || g1 != 0.f) scatter_level(grid, l, ux, uy, uz, g0, g1, sc, acc);
+    }
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t rows, int64_t ld, int col0, int ncols,
+                              uint32_t* __restrict__ gmax_bits) {
+    uint32_t m = 0;
+    const int64_t total = rows * ncols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ncols;
+        const int c = (int)(i - r * ncols);
+        m = max(m, __float_as_uint(fabsf(__ldg(x + r * ld + col0 + c))));   // |x| bit patterns order like values; NaN sorts last
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(gmax_bits, m);
+}
+
+__global__ void grad_finalize_kernel(const long long* __restrict__ acc, int64_t n, const uint32_t* __restrict__ gmax_bits,
+                                     int headroom, float* __restrict__ grad, int accumulate) {
+    bool ok, poisoned;
+    const int e = fixed_exponent(__ldg(gmax_bits), headroom, ok, poisoned);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (poisoned) v = __uint_as_float(0x7fc00000u);
+        else if (ok) v = (float)ldexp((double)acc[i], -e);
+        grad[i] = accumulate ? grad[i] + v : v;
+    }
+}
+
+__global__ void sample_points_kernel(const Geom geo, const float* __restrict__ rays_o, const float* __restrict__ pos_tx,
+                                     const float* __restrict__ dirs, const float* __restrict__ d_vals,
+                                     float* __restrict__ pts_n, float* __restrict__ view, float* __restrict__ tx_n,
+                                     int* __restrict__ delay) {
+    const int64_t n_pts = (int64_t)geo.bs * geo.R * geo.S;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_pts) return;
+    float ux, uy, uz, nx, ny, nz;
+    int b;
+    sample_unit(geo, n, rays_o, dirs, d_vals, ux, uy, uz, nx, ny, nz, b);
+    const float tx0 = to_unit(__ldg(pos_tx + 3 * b + 0), geo.lo, geo.span);
+    const float tx1 = to_unit(__ldg(pos_tx + 3 * b + 1), geo.lo, geo.span);
+    const float tx2 = to_unit(__ldg(pos_tx + 3 * b + 2), geo.lo, geo.span);
+    if (pts_n) { pts_n[3 * n] = nx; pts_n[3 * n + 1] = ny; pts_n[3 * n + 2] = nz; }
+    if (tx_n) { tx_n[3 * n] = tx0; tx_n[3 * n + 1] = tx1; tx_n[3 * n + 2] = tx2; }
+    if (view) {
+        const int r = (int)((n / geo.S) % geo.R);
+        view[3 * n] = -__ldg(dirs + 3 * r); view[3 * n + 1] = -__ldg(dirs + 3 * r + 1); view[3 * n + 2] = -__ldg(dirs + 3 * r + 2);
+    }
+    if (delay) delay[n] = source_delay(tx0, tx1, tx2, nx, ny, nz, geo);
+}
+
+// unit-cube inputs of the per-ray / per-receiver encodings: (-dir+1)/2 and (normalize(x)+1)/2
+__global__ void aux_inputs_kernel(const Geom geo, const float* __restrict__ pos_tx, const float* __restrict__ dirs,
+                                  const float* __restrict__ dir_tx, float* __restrict__ u_view, float* __restrict__ u_tx,
+                                  float* __restrict__ u_dir_tx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u_view && i < geo.R * 3) u_view[i] = to_cube(-__ldg(dirs + i));
+    if (u_tx && i < geo.bs * 3) u_tx[i] = to_cube(to_unit(__ldg(pos_tx + i), geo.lo, geo.span));
+    if (u_dir_tx && dir_tx && i < geo.bs * 3) u_dir_tx[i] = to_cube(__ldg(dir_tx + i));
+}
+
+static int check_grid(const avr_grid_meta* g) {
+    if (!g) return fail(AVR_ERR_INVALID, "grid meta is null");
+    if (g->n_feat != 2) return fail(AVR_ERR_UNSUPPORTED, "n_features_per_level=%d (only 2 is built)", g->n_feat);
+    if (g->n_levels < 1 || g->n_levels > AVR_MAX_LEVELS) return fail(AVR_ERR_INVALID, "n_levels=%d out of range", g->n_levels);
+    return AVR_OK;
+}
+
+}  // namespace avr
+
+using namespace avr;
+
+extern "C" int avr_sample_points(const avr_render_geom* geom, const float* rays_o, const float* pos_tx,
+                                 const float* dirs, const float* d_vals, float* pts_n, float* view, float* tx_n,
+                                 int32_t* delay, int device, void* stream) {
+    AVR_REQUIRE(geom && rays_o && pos_tx && dirs && d_vals, "null input");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int64_t n = (int64_t)geo.bs * geo.R * geo.S;
+    if (n == 0) return AVR_OK;
+    sample_points_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(geo, rays_o, pos_tx, dirs, d_vals,
+                                                                                      pts_n, view, tx_n, delay);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+extern "C" int avr_aux_inputs(const avr_render_geom* geom, const float* pos_tx, const float* dirs, const float* dir_tx,
+                              float* u_view, float* u_tx, float* u_dir_tx, int device, void* stream) {
+    AVR_REQUIRE(geom && pos_tx && dirs, "null input");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int n = 3 * (geo.R > geo.bs ? geo.R : geo.bs);
+    if (n == 0) return AVR_OK;
+    aux_inputs_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(geo, pos_tx, dirs, dir_tx, u_view, u_tx, u_dir_tx);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+static int encode_fwd_common(bool raygen, const Geom& geo, const avr_grid_meta* grid, int64_t n_pts, const float* rays_o,
+                             const float* pos_tx, const float* dirs, const float* d_vals, const float* u,
+                             const float* table, float* out, int64_t ld_out, int32_t col0, int32_t n_ones,
+                             int32_t* delay, void* stream) {
+    if (int rc = check_grid(grid)) return rc;
+    AVR_REQUIRE(table && out, "null table/out");
+    AVR_REQUIRE(n_ones >= 0 && col0 >= 0 && ld_out >= col0 + 2 * grid->n_levels + n_ones, "bad output window");
+    AVR_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7u) == 0, "table must be 8-byte aligned");
+    if (n_pts == 0) return AVR_OK;
+    const GridDev gd = make_grid(grid);
+    const int W = 2 * grid->n_levels + n_ones;
+    const size_t smem = (size_t)ENC_PTS * (W | 1) * sizeof(float);
+    const dim3 block(ENC_PTS, ENC_LG);
+    const unsigned blocks = (unsigned)ceil_div(n_pts, ENC_PTS);
+    if (raygen) {
+        AVR_CUDA(cudaFuncSetAttribute(encode_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_fwd_kernel<true><<<blocks, block, smem, (cudaStream_t)stream>>>(
+            geo, gd, n_pts, rays_o, pos_tx, dirs, d_vals, nullptr, (const float2*)table, out, ld_out, col0, n_ones, delay);
+    } else {
+        AVR_CUDA(cudaFuncSetAttribute(encode_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_fwd_kernel<false><<<blocks, block, smem, (cudaStream_t)stream>>>(
+            geo, gd, n_pts, nullptr, nullptr, nullptr, nullptr, u, (const float2*)table, out, ld_out, col0, n_ones, nullptr);
+    }
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+extern "C" int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
+                                     const float* pos_tx, const float* dirs, const float* d_vals, const float* table,
+                                     float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int32_t* delay,
+                                     int device, void* stream) {
+    AVR_REQUIRE(geom && rays_o && dirs && d_vals, "null input");
+    AVR_REQUIRE(delay == nullptr || pos_tx != nullptr, "delay requested without pos_tx");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    return encode_fwd_common(true, geo, grid, (int64_t)geo.bs * geo.R * geo.S, rays_o, pos_tx, dirs, d_vals, nullptr,
+                             table, out, ld_out, col0, n_ones, delay, stream);
+}
+
+extern "C" int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* table,
+                                   float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int device, void* stream) {
+    AVR_REQUIRE(u != nullptr || n_pts == 0, "null input");
+    AVR_ENTER(device);
+    Geom geo = {};
+    return encode_fwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, nullptr, u, table, out, ld_out, col0,
+                             n_ones, nullptr, stream);
+}
+
+static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* grid, int64_t n_pts, const float* rays_o,
+                             const float* dirs, const float* d_vals, const float* u, const float* d_out, int64_t ld_out,
+                             int32_t col0, const uint32_t* gmax_bits, int32_t headroom, int64_t* acc, void* stream) {
+    if (int rc = check_grid(grid)) return rc;
+    AVR_REQUIRE(d_out && gmax_bits && acc, "null d_out/gmax/acc");
+    AVR_REQUIRE(col0 >= 0 && ld_out >= col0 + 2 * grid->n_levels, "bad gradient window");
+    AVR_REQUIRE(headroom >= 0 && headroom <= 56, "log2_headroom out of range");
+    if (n_pts == 0) return AVR_OK;
+    const GridDev gd = make_grid(grid);
+    const int W = 2 * grid->n_levels;
+    const size_t smem = (size_t)ENC_PTS * (W | 1) * sizeof(float);
+    const dim3 block(ENC_PTS, ENC_LG);
+    const unsigned blocks = (unsigned)ceil_div(n_pts, ENC_PTS);
+    if (raygen) {
+        AVR_CUDA(cudaFuncSetAttribute(encode_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_bwd_kernel<true><<<blocks, block, smem, (cudaStream_t)stream>>>(
+            geo, gd, n_pts, rays_o, dirs, d_vals, nullptr, d_out, ld_out, col0, gmax_bits, headroom,
+            (unsigned long long*)acc);
+    } else {
+        AVR_CUDA(cudaFuncSetAttribute(encode_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_bwd_kernel<false><<<blocks, block, smem, (cudaStream_t)stream>>>(
+            geo, gd, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, col0, gmax_bits, headroom,
+            (unsigned long long*)acc);
+    }
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+extern "C" int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
+                                     const float* dirs, const float* d_vals, const float* d_out, int64_t ld_out,
+                                     int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, int64_t* acc,
+                                     int device, void* stream) {
+    AVR_REQUIRE(geom && rays_o && dirs && d_vals, "null input");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    return encode_bwd_common(true, geo, grid, (int64_t)geo.bs * geo.R * geo.S, rays_o, dirs, d_vals, nullptr, d_out,
+                             ld_out, col0, gmax_bits, log2_headroom, acc, stream);
+}
+
+extern "C" int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* d_out,
+                                   int64_t ld_out, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
+                                   int64_t* acc, int device, void* stream) {
+    AVR_REQUIRE(u != nullptr || n_pts == 0, "null input");
+    AVR_ENTER(device);
+    Geom geo = {};
+    return encode_bwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, col0, gmax_bits,
+                             log2_headroom, acc, stream);
+}
+
+extern "C" int avr_absmax_bits(const float* x, int64_t rows, int64_t ld, int32_t col0, int32_t ncols,
+                               uint32_t* gmax_bits, int device, void* stream) {
+    AVR_REQUIRE(gmax_bits, "null gmax_bits");
+    AVR_REQUIRE(x != nullptr || rows == 0, "null input");
+    AVR_ENTER(device);
+    if (rows * ncols == 0) return AVR_OK;
+    int64_t blocks = ceil_div(rows * ncols, 256 * 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    absmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, ld, col0, ncols, gmax_bits);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+extern "C" int avr_grid_grad_finalize(const int64_t* acc, int64_t n, const uint32_t* gmax_bits, int32_t log2_headroom,
+                                      float* grad, int accumulate, int device, void* stream) {
+    AVR_REQUIRE(acc && gmax_bits && grad, "null pointer");
+    AVR_ENTER(device);
+    if (n == 0) return AVR_OK;
+    int64_t blocks = ceil_div(n, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    grad_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const long long*)acc, n, gmax_bits,
+                                                                            log2_headroom, grad, accumulate);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}

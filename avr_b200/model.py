@@ -1,0 +1,197 @@
+"""The neural acoustic field, B200-native: drop-in for the reference ``model.py``.
+
+``Encoding`` / ``Network`` stand where the reference instantiates ``tcnn.Encoding`` / ``tcnn.Network``
+(``/root/reference/model.py:21,43,66-68,117,146,176,258-285``): one flat fp32 ``params`` Parameter per
+module, tcnn's layout, so state-dict keys (``_pos_encoding.params`` ...) line up with
+the reference's checkpoints.  ``AVRModel`` / ``AVRModel_complex`` keep the reference constructor
+(``cfg`` = the YAML ``model:`` section) and ``forward`` signatures (``model.py:183,291``).
+
+Called on its own, ``forward(pts, view, tx, ...)`` evaluates the field on arbitrary points with the
+hand-written kernels (hash-grid gather, fp32 GEMMs) under autograd.  When wrapped by
+``avr_b200.AVRRender`` the renderer instead asks for ``fused_plan()`` and runs the whole
+ray-generation -> encode -> MLP -> composite pipeline without ever materialising the per-point inputs.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def hashgrid_geometry(cfg: dict) -> dict:
+    """Level table of a tcnn ``HashGrid`` config (tcnn defaults for absent keys)."""
+    if cfg.get("otype", "HashGrid") not in ("HashGrid", "Grid"):
+        raise NotImplementedError(f"encoding otype {cfg.get('otype')!r} is not built")
+    n_levels = int(cfg.get("n_levels", 16))
+    n_feat = int(cfg.get("n_features_per_level", 2))
+    log2_size = int(cfg.get("log2_hashmap_size", 19))
+    base = int(cfg.get("base_resolution", 16))
+    log2_pls = np.float32(math.log2(float(cfg.get("per_level_scale", 2.0))))
+    scale, res, size, offset, off = [], [], [], [], 0
+    for lvl in range(n_levels):
+        s = np.float32(np.exp2(np.float32(lvl) * log2_pls, dtype=np.float32) * np.float32(base) - np.float32(1.0))
+        r = int(math.ceil(float(s))) + 1
+        n = min(_round_up(r ** 3, 8), 1 << log2_size)
+        scale.append(float(s)); res.append(r); size.append(n); offset.append(off)
+        off += n
+    return {"n_levels": n_levels, "n_feat": n_feat, "scale": scale, "res": res, "size": size, "offset": offset,
+            "total": off}
+
+
+class Encoding(nn.Module):
+    """Multiresolution hash grid on 3-D unit-cube inputs (``tcnn.Encoding(3, cfg)``)."""
+
+    def __init__(self, n_input_dims: int, encoding_config: dict, dtype=torch.float32, seed: int = 1337):
+        super().__init__()
+        if n_input_dims != 3:
+            raise NotImplementedError("only 3-D hash grids are built")
+        self.geom = hashgrid_geometry(encoding_config)
+        self.n_input_dims = 3
+        self.n_output_dims = self.geom["n_levels"] * self.geom["n_feat"]
+        g = torch.Generator().manual_seed(seed)
+        n = self.geom["total"] * self.geom["n_feat"]
+        self.params = nn.Parameter((torch.rand(n, generator=g) * 2 - 1) * 1e-4)      # tcnn: U(-1e-4, 1e-4)
+        self._meta = None
+
+    @property
+    def meta(self):
+        if self._meta is None:
+            from . import ops
+            self._meta = ops.make_grid_meta(self.geom)
+        return self._meta
+
+    def forward(self, u: torch.Tensor) -> torch.Tensor:
+        return Fn.HashGridFunction.apply(u.contiguous().float(), self.params, self)
+
+
+class Network(nn.Module):
+    """Bias-free ReLU MLP (``tcnn.Network(n_in, n_out, cfg)``).
+
+    ``n_hidden_layers = h`` gives ``h+1`` row-major ``[out, in]`` matrices; the input is padded with ones
+    and the output with unused rows up to a multiple of 16 (FullyFusedMLP) or 8 (CutlassMLP).
+    """
+
+    def __init__(self, n_input_dims: int, n_output_dims: int, network_config: dict, seed: int = 1337):
+        super().__init__()
+        act = network_config.get("activation", "ReLU")
+        out_act = network_config.get("output_activation", "None")
+        if act != "ReLU" or out_act not in ("None", None):
+            raise NotImplementedError("only ReLU hidden / linear output MLPs are built")
+        align = 16 if network_config.get("otype", "FullyFusedMLP") == "FullyFusedMLP" else 8
+        self.width = int(network_config["n_neurons"])
+        self.n_hidden = int(network_config["n_hidden_layers"])
+        if self.n_hidden < 1:
+            raise NotImplementedError("n_hidden_layers must be >= 1")
+        if self.width % 4:
+            raise NotImplementedError("n_neurons must be a multiple of 4")
+        self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
+        self.in_pad, self.out_pad = _round_up(n_input_dims, align), _round_up(n_output_dims, align)
+        dims = [self.in_pad] + [self.width] * self.n_hidden + [self.out_pad]
+        self.shapes = [(dims[i + 1], dims[i]) for i in range(len(dims) - 1)]
+        g = torch.Generator().manual_seed(seed)
+        chunks = [(torch.rand(o * i, generator=g) * 2 - 1) * math.sqrt(6.0 / (i + o)) for (o, i) in self.shapes]
+        self.params = nn.Parameter(torch.cat(chunks))                                # Xavier-uniform
+
+    def matrices(self, flat: torch.Tensor):
+        out, off = [], 0
+        for (o, i) in self.shapes:
+            out.append(flat[off:off + o * i].view(o, i))
+            off += o * i
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return Fn.MLPFunction.apply(x.contiguous().float(), self.params, self)
+
+
+def _reject_channel_embedding(cfg: dict) -> None:
+    ch = cfg.get("channel_embed") or {}
+    if ch.get("is_embed", False) and ch.get("connection_type", None) in ("add", "concat"):
+        raise NotImplementedError(
+            "channel_embed.connection_type add/concat (model.py:11-61,108-113) is not built yet; the five "
+            "BASELINE configs do not set it (SURVEY 8a row a4'')")
+
+
+class AVRModel(nn.Module):
+    """``/root/reference/model.py:63-235`` (MeshRIR / Simu / Real_env)."""
+
+    def __init__(self, cfg: dict, seed: int = 1337):
+        super().__init__()
+        _reject_channel_embedding(cfg)
+        self._pos_encoding = Encoding(3, cfg["pos_encoding_sigma"], seed=seed)
+        self._dir_encoding = Encoding(3, cfg["dir_encoding_sig"], seed=seed + 1)
+        self._tx_encoding = Encoding(3, cfg["tx_encoding_sig"], seed=seed + 2)
+        self.signal_output_dim = int(cfg["signal_output_dim"])
+        self._model_encoder_sigma = Network(self._pos_encoding.n_output_dims, 128, cfg["sigma_encoder_network"], seed + 3)
+        self._model_decoder_sigma = Network(128, 1, cfg["sigma_decoder_network"], seed + 4)
+        sig_in = 128 + self._dir_encoding.n_output_dims + self._tx_encoding.n_output_dims
+        self._model_signal = Network(sig_in, self.signal_output_dim, cfg["signal_network"], seed + 5)
+        self.leaky_slope = 0.01      # model.py:233 -- F.leaky_relu default, cfg["leaky_relu"] is ignored
+
+    def forward(self, pts, view, tx, ch_idx=None):
+        bs, n_pts = pts.size(0), pts.size(1)
+        u_pts = Fn.unit_cube(pts)
+        sigma_feat = self._model_encoder_sigma(self._pos_encoding(u_pts))
+        attn = self._model_decoder_sigma(torch.relu(sigma_feat))
+        sig_in = torch.cat([sigma_feat, self._dir_encoding(Fn.unit_cube(view)), self._tx_encoding(Fn.unit_cube(tx))], -1)
+        signal = self._model_signal(sig_in)
+        attn = torch.abs(torch.nn.functional.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)
+        return attn, signal.view(bs, n_pts, self.signal_output_dim)
+
+    def fused_plan(self) -> dict:
+        return {
+            "x0": [(self._pos_encoding, "point")],
+            "tail": [(self._dir_encoding, "ray"), (self._tx_encoding, "receiver_tx")],
+            "enc": self._model_encoder_sigma, "dec": self._model_decoder_sigma, "sig": self._model_signal,
+            "feat_dim": 128, "sig_relu_feat": False, "slope": self.leaky_slope, "needs_dir_tx": False,
+        }
+
+
+class AVRModel_complex(nn.Module):
+    """``/root/reference/model.py:238-331`` (RAF).  ``ch_idx`` is accepted and ignored."""
+
+    def __init__(self, cfg: dict, seed: int = 1337):
+        super().__init__()
+        self.leaky_slope = float(cfg["leaky_relu"])
+        self.signal_output_dim = int(cfg["signal_output_dim"])
+        self._pos_encoding = Encoding(3, cfg["pos_encoding_sigma"], seed=seed)
+        self._pos_signal_encoding = Encoding(3, cfg["pos_encoding_sig"], seed=seed + 1)
+        self._tx_pos_encoding = Encoding(3, cfg["tx_pos_encoding_sigma"], seed=seed + 2)
+        self._tx_pos_signal_encoding = Encoding(3, cfg["tx_pos_encoding_sig"], seed=seed + 3)
+        self._dir_encoding = Encoding(3, cfg["dir_encoding_sig"], seed=seed + 4)
+        self._tx_dir_encoding = Encoding(3, cfg["tx_dir_encoding_sig"], seed=seed + 5)
+        n_enc = self._pos_encoding.n_output_dims
+        self._model_encoder_sigma = Network(n_enc + self._tx_pos_encoding.n_output_dims, 256,
+                                            cfg["sigma_encoder_network"], seed + 6)
+        self._model_decoder_sigma = Network(256, 1, cfg["sigma_decoder_network"], seed + 7)
+        n_sig = (256 + self._dir_encoding.n_output_dims + self._tx_dir_encoding.n_output_dims +
+                 self._pos_signal_encoding.n_output_dims + self._tx_pos_signal_encoding.n_output_dims)
+        self._model_signal = Network(n_sig, self.signal_output_dim, cfg["signal_network"], seed + 8)
+
+    def forward(self, pts, view, tx, tx_view, ch_idx=None):
+        bs, n_pts = pts.size(0), pts.size(1)
+        u_pts, u_tx = Fn.unit_cube(pts), Fn.unit_cube(tx)
+        sigma_feat = self._model_encoder_sigma(torch.cat([self._pos_encoding(u_pts), self._tx_pos_encoding(u_tx)], -1))
+        attn = self._model_decoder_sigma(torch.relu(sigma_feat))
+        feat = torch.cat([torch.relu(sigma_feat), self._dir_encoding(Fn.unit_cube(view)),
+                          self._tx_dir_encoding(Fn.unit_cube(tx_view)), self._pos_signal_encoding(u_pts),
+                          self._tx_pos_signal_encoding(u_tx)], -1)
+        signal = self._model_signal(feat)
+        attn = torch.abs(torch.nn.functional.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)
+        return attn, signal.reshape(bs, n_pts, self.signal_output_dim)
+
+    def fused_plan(self) -> dict:
+        return {
+            "x0": [(self._pos_encoding, "point"), (self._tx_pos_encoding, "receiver_tx")],
+            "tail": [(self._dir_encoding, "ray"), (self._tx_dir_encoding, "receiver_dir_tx"),
+                     (self._pos_signal_encoding, "point"), (self._tx_pos_signal_encoding, "receiver_tx")],
+            "enc": self._model_encoder_sigma, "dec": self._model_decoder_sigma, "sig": self._model_signal,
+            "feat_dim": 256, "sig_relu_feat": True, "slope": self.leaky_slope, "needs_dir_tx": True,
+        }

@@ -1,0 +1,258 @@
+"""Tensor-level wrappers over the C-ABI (no autograd here; see ``functional.py``).
+
+PyTorch is used for device memory and streams only.  Every function launches hand-written kernels
+from ``libavr_b200.so`` on the current CUDA stream of the tensors' device and fails loudly otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG, GridMeta, RenderGeom  # noqa: F401
+
+
+def _ctx(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.AVRLibraryError("avr_b200 ops need CUDA tensors (there is no CPU fallback)")
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return dev, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_cuda:
+        raise _lib.AVRLibraryError("expected a CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def _dense(t):
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t
+
+
+def make_geom(render_cfg: dict, bs: int, T: int) -> RenderGeom:
+    """``render_cfg`` as in the reference YAML ``render:`` section (renderer.py:20-29)."""
+    R = int(render_cfg["n_azi"]) * int(render_cfg["n_ele"]) + 2
+    lo, hi = render_cfg["xyz_min"], render_cfg["xyz_max"]
+    return RenderGeom(int(bs), R, int(render_cfg["n_samples"]), int(T), float(lo), float(float(hi) - float(lo)),
+                      float(render_cfg["fs"]), float(render_cfg["speed"]))
+
+
+def geom_with_bs(g: RenderGeom, bs: int) -> RenderGeom:
+    return RenderGeom(int(bs), g.R, g.S, g.T, g.xyz_min, g.xyz_span, g.fs, g.speed)
+
+
+def make_grid_meta(geom: dict) -> GridMeta:
+    """``geom`` from ``hashgrid_geometry`` (model.py)."""
+    m = GridMeta()
+    m.n_levels, m.n_feat, m.total = geom["n_levels"], geom["n_feat"], geom["total"]
+    for l in range(geom["n_levels"]):
+        m.scale[l], m.res[l], m.size[l], m.offset[l] = geom["scale"][l], geom["res"][l], geom["size"][l], geom["offset"][l]
+    return m
+
+
+def headroom_bits(n_points: int) -> int:
+    """log2 of the largest number of contributions one table entry can receive (8 corners/point)."""
+    return max(4, int(math.ceil(math.log2(max(1, n_points) * 8))) + 1)
+
+
+# ---- geometry -------------------------------------------------------------------------------------
+def sample_points(g: RenderGeom, rays_o, pos_tx, dirs, d_vals, want_pts=True, want_delay=True):
+    dev, st = _ctx(rays_o)
+    n = g.bs * g.R * g.S
+    pts = torch.empty(g.bs, g.R * g.S, 3, device=rays_o.device) if want_pts else None
+    view = torch.empty_like(pts) if want_pts else None
+    txn = torch.empty_like(pts) if want_pts else None
+    delay = torch.empty(g.bs, g.R, g.S, dtype=torch.int32, device=rays_o.device) if want_delay else None
+    _lib.check(_lib.load().avr_sample_points(C.byref(g), _p(_dense(rays_o)), _p(_dense(pos_tx)), _p(_dense(dirs)),
+                                             _p(_dense(d_vals)), _p(pts), _p(view), _p(txn), _p(delay, torch.int32),
+                                             dev, st), "avr_sample_points")
+    return pts, view, txn, delay
+
+
+def aux_inputs(g: RenderGeom, pos_tx, dirs, dir_tx=None):
+    dev, st = _ctx(pos_tx)
+    u_view = torch.empty(g.R, 3, device=pos_tx.device)
+    u_tx = torch.empty(g.bs, 3, device=pos_tx.device)
+    u_dtx = torch.empty(g.bs, 3, device=pos_tx.device) if dir_tx is not None else None
+    _lib.check(_lib.load().avr_aux_inputs(C.byref(g), _p(_dense(pos_tx)), _p(_dense(dirs)),
+                                          _p(_dense(dir_tx)) if dir_tx is not None else None,
+                                          _p(u_view), _p(u_tx), _p(u_dtx), dev, st), "avr_aux_inputs")
+    return u_view, u_tx, u_dtx
+
+
+# ---- hash grid ------------------------------------------------------------------------------------
+def raygen_encode_fwd(g, meta, rays_o, pos_tx, dirs, d_vals, table, out, col0=0, n_ones=0, delay=None):
+    dev, st = _ctx(out)
+    _lib.check(_lib.load().avr_raygen_encode_fwd(C.byref(g), C.byref(meta), _p(_dense(rays_o)),
+                                                 _p(_dense(pos_tx)) if pos_tx is not None else None, _p(_dense(dirs)),
+                                                 _p(_dense(d_vals)), _p(_dense(table)), _p(out), out.stride(0), col0,
+                                                 n_ones, _p(delay, torch.int32), dev, st), "avr_raygen_encode_fwd")
+
+
+def grid_encode_fwd(meta, u, table, out, col0=0, n_ones=0):
+    dev, st = _ctx(out)
+    _lib.check(_lib.load().avr_grid_encode_fwd(C.byref(meta), _p(_dense(u)), u.shape[0], _p(_dense(table)), _p(out),
+                                               out.stride(0), col0, n_ones, dev, st), "avr_grid_encode_fwd")
+
+
+class GridGradAccumulator:
+    """Deterministic fixed-point accumulation of hash-table gradients (see include/avr_b200.h)."""
+
+    def __init__(self, meta: GridMeta, device, n_points: int, scratch=None):
+        self.meta, self.n = meta, int(meta.total) * 2
+        self.headroom = headroom_bits(n_points)
+        if scratch is not None and scratch.numel() >= self.n:
+            self.acc = scratch[: self.n]
+        else:
+            self.acc = torch.empty(self.n, dtype=torch.int64, device=device)
+        self.acc.zero_()
+        self.gmax = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def observe(self, d_out, col0, ncols):
+        dev, st = _ctx(d_out)
+        rows = d_out.shape[0]
+        _lib.check(_lib.load().avr_absmax_bits(_p(d_out), rows, d_out.stride(0), col0, ncols,
+                                               _p(self.gmax, torch.int32), dev, st), "avr_absmax_bits")
+
+    def add_rays(self, g, rays_o, dirs, d_vals, d_out, col0=0):
+        dev, st = _ctx(d_out)
+        _lib.check(_lib.load().avr_raygen_encode_bwd(C.byref(g), C.byref(self.meta), _p(_dense(rays_o)), _p(_dense(dirs)),
+                                                     _p(_dense(d_vals)), _p(d_out), d_out.stride(0), col0,
+                                                     _p(self.gmax, torch.int32), self.headroom,
+                                                     _p(self.acc, torch.int64), dev, st), "avr_raygen_encode_bwd")
+
+    def add_points(self, u, d_out, col0=0):
+        dev, st = _ctx(d_out)
+        _lib.check(_lib.load().avr_grid_encode_bwd(C.byref(self.meta), _p(_dense(u)), u.shape[0], _p(d_out),
+                                                   d_out.stride(0), col0, _p(self.gmax, torch.int32), self.headroom,
+                                                   _p(self.acc, torch.int64), dev, st), "avr_grid_encode_bwd")
+
+    def finalize(self, grad=None, accumulate=False):
+        if grad is None:
+            grad = torch.empty(self.n, device=self.acc.device)
+        dev, st = _ctx(grad)
+        _lib.check(_lib.load().avr_grid_grad_finalize(_p(self.acc, torch.int64), self.n, _p(self.gmax, torch.int32),
+                                                      self.headroom, _p(grad), 1 if accumulate else 0, dev, st),
+                   "avr_grid_grad_finalize")
+        return grad
+
+
+# ---- dense layers ---------------------------------------------------------------------------------
+def gemm_workspace_bytes(M, N, K) -> int:
+    return int(_lib.load().avr_gemm_workspace_bytes(M, N, K))
+
+
+def gemm(la, lb, M, N, K, A, lda, B, ldb, Cmat, ldc, flags=0, aux=None, ldaux=0, workspace=None):
+    """C[i,j] (+)= sum_k A(i,k) B(j,k); A/B/C/aux are tensors (possibly column views), ld in elements."""
+    dev, st = _ctx(Cmat)
+    ws_ptr, ws_bytes = (None, 0)
+    if workspace is not None:
+        ws_ptr, ws_bytes = C.c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size()
+    _lib.check(_lib.load().avr_gemm(la, lb, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, flags, _p(aux), ldaux,
+                                    ws_ptr, ws_bytes, dev, st), "avr_gemm")
+
+
+def linear_fwd(x, w, y, relu=False, relu_in=False, accum=False):
+    """y[n,m] (+)= sum_k x[n,k] w[m,k]   (x, y may be column views of wider row-major buffers)."""
+    flags = (GEMM_RELU if relu else 0) | (GEMM_RELU_A if relu_in else 0) | (GEMM_ACCUM if accum else 0)
+    gemm(K_CONTIG, K_CONTIG, x.shape[0], w.shape[0], w.shape[1], x, x.stride(0), w, w.stride(0), y, y.stride(0), flags)
+
+
+def linear_bwd_data(dy, w, dx, mask_src=None, accum=False):
+    """dx[n,k] (+)= (sum_m dy[n,m] w[m,k]) * (mask_src[n,k] > 0)."""
+    flags = (GEMM_MASK if mask_src is not None else 0) | (GEMM_ACCUM if accum else 0)
+    gemm(K_CONTIG, I_CONTIG, dy.shape[0], w.shape[1], w.shape[0], dy, dy.stride(0), w, w.stride(0), dx, dx.stride(0),
+         flags, mask_src, mask_src.stride(0) if mask_src is not None else 0)
+
+
+def linear_bwd_weight(dy, x, dw, workspace, accum=False, relu_in=False):
+    """dw[m,k] (+)= sum_n dy[n,m] x[n,k]  (deterministic split-K over the sample points)."""
+    flags = (GEMM_ACCUM if accum else 0) | (GEMM_RELU_B if relu_in else 0)
+    gemm(I_CONTIG, I_CONTIG, dy.shape[1], x.shape[1], x.shape[0], dy, dy.stride(0), x, x.stride(0), dw, dw.stride(0),
+         flags, None, 0, workspace)
+
+
+# ---- broadcast inputs -----------------------------------------------------------------------------
+def rows_broadcast(g, src, per_receiver, dst, col0):
+    dev, st = _ctx(dst)
+    _lib.check(_lib.load().avr_rows_broadcast(C.byref(g), _p(_dense(src)), src.shape[1], 1 if per_receiver else 0,
+                                              _p(dst), dst.stride(0), col0, dev, st), "avr_rows_broadcast")
+
+
+def rows_reduce(g, d_dst, col0, w, per_receiver):
+    dev, st = _ctx(d_dst)
+    rows = g.bs if per_receiver else g.R
+    nbytes = int(_lib.load().avr_rows_reduce_workspace_bytes(C.byref(g), w, 1 if per_receiver else 0))
+    ws = torch.empty(max(1, nbytes // 4), device=d_dst.device)
+    out = torch.empty(rows, w, device=d_dst.device)
+    _lib.check(_lib.load().avr_rows_reduce(C.byref(g), _p(d_dst), d_dst.stride(0), col0, w, 1 if per_receiver else 0,
+                                           _p(out), _p(ws), nbytes, dev, st), "avr_rows_reduce")
+    return out
+
+
+# ---- ray weights / compositing / spectrum ------------------------------------------------------------
+def ray_weights_fwd(g, raw, ld_raw, delta, slope, want_attn=False):
+    dev, st = _ctx(raw)
+    w = torch.empty(g.bs, g.R, g.S, device=raw.device)
+    attn = torch.empty_like(w) if want_attn else None
+    _lib.check(_lib.load().avr_ray_weights_fwd(C.byref(g), _p(raw), ld_raw, _p(_dense(delta)), float(slope), _p(attn),
+                                               _p(w), dev, st), "avr_ray_weights_fwd")
+    return w, attn
+
+
+def ray_weights_bwd(g, raw, ld_raw, delta, slope, d_w, d_raw, ld_draw):
+    dev, st = _ctx(raw)
+    _lib.check(_lib.load().avr_ray_weights_bwd(C.byref(g), _p(raw), ld_raw, _p(_dense(delta)), float(slope),
+                                               _p(_dense(d_w)), _p(d_raw), ld_draw, dev, st), "avr_ray_weights_bwd")
+
+
+def composite_fwd(g, sig, w, delay):
+    dev, st = _ctx(sig)
+    nbytes = int(_lib.load().avr_composite_workspace_bytes(C.byref(g)))
+    ws = torch.empty(max(1, nbytes // 4), device=sig.device)
+    y = torch.empty(g.bs, g.S, g.T, device=sig.device)
+    _lib.check(_lib.load().avr_composite_fwd(C.byref(g), _p(_dense(sig)), _p(_dense(w)), _p(_dense(delay), torch.int32),
+                                             _p(y), _p(ws), nbytes, dev, st), "avr_composite_fwd")
+    return y
+
+
+def composite_bwd(g, sig, w, delay, d_y, want_dsig=True, want_dw=True, d_sig_out=None):
+    dev, st = _ctx(d_y)
+    d_sig = None
+    if want_dsig:
+        d_sig = d_sig_out if d_sig_out is not None else torch.empty(g.bs, g.R, g.S, g.T, device=d_y.device)
+    d_w = torch.empty(g.bs, g.R, g.S, device=d_y.device) if want_dw else None
+    _lib.check(_lib.load().avr_composite_bwd(C.byref(g), _p(_dense(sig)) if sig is not None else None, _p(_dense(w)),
+                                             _p(_dense(delay), torch.int32), _p(_dense(d_y)), _p(d_sig), _p(d_w), dev, st),
+               "avr_composite_bwd")
+    return d_sig, d_w
+
+
+def spectrum_fwd(g, y, tables):
+    dev, st = _ctx(y)
+    ldd = tables["dft"].shape[1]
+    zbuf = torch.empty(g.bs * g.S, g.T, device=y.device)
+    xbuf = torch.empty(g.bs * g.S, ldd, device=y.device)
+    out = torch.empty(g.bs, g.T // 2 + 1, 2, device=y.device)
+    _lib.check(_lib.load().avr_spectrum_fwd(C.byref(g), _p(_dense(y)), _p(tables["gain"]), _p(tables["phase"]),
+                                            _p(tables["dft"]), ldd, _p(zbuf), _p(xbuf), _p(out), dev, st),
+               "avr_spectrum_fwd")
+    return out
+
+
+def spectrum_bwd(g, d_out, tables):
+    dev, st = _ctx(d_out)
+    ldd = tables["dft"].shape[1]
+    xbuf = torch.empty(g.bs * g.S, ldd, device=d_out.device)
+    d_y = torch.empty(g.bs, g.S, g.T, device=d_out.device)
+    _lib.check(_lib.load().avr_spectrum_bwd(C.byref(g), _p(_dense(d_out)), _p(tables["gain"]), _p(tables["phase"]),
+                                            _p(tables["dft"]), ldd, _p(xbuf), _p(d_y), dev, st), "avr_spectrum_bwd")
+    return d_y

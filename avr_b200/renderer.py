@@ -1,0 +1,121 @@
+"""``AVRRender`` -- drop-in for ``/root/reference/renderer.py`` (class ``AVRRender``, lines 14-124).
+
+Same constructor (``AVRRender(networks_fn, **cfg['render'])``, keys read as at renderer.py:20-29, extras
+ignored), same ``forward(rays_o, position_tx, direction_tx=None, ch_idx=None) -> [bs, T//2+1, 2]`` fp32 on
+the input device, usable under ``torch.optim``, ``state_dict``, ``DDP`` and ``torch.no_grad()`` exactly
+like the reference module (avr_runner.py:60-73,168-178; avr_runner_ddp.py:98).
+
+Two execution paths, both made only of ``libavr_b200`` CUDA kernels (there is no CPU fallback -- CPU
+tensors raise):
+
+* ``networks_fn`` is an ``avr_b200.model`` field (has ``fused_plan``): the fused native step
+  (``fused.FusedRenderFunction``).
+* any other ``networks_fn(pts, view, tx[, dir_tx], ch_idx=...) -> (attn, signal)``: the ray-generation
+  kernel materialises the network inputs the reference would build, the user network runs as is, and the
+  compositing / spectrum kernels consume its outputs (``functional.CompositeFunction``).
+"""
+from __future__ import annotations
+
+import inspect
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops, tables
+from .functional import CompositeFunction
+from .fused import FusedRenderFunction, plan_modules
+
+
+class AVRRender(nn.Module):
+    """Acoustic volume renderer (see module docstring)."""
+
+    def __init__(self, networks_fn, **kwargs) -> None:
+        super().__init__()
+        self.network_fn = networks_fn
+        self.n_samples = kwargs["n_samples"]
+        self.near = kwargs["near"]
+        self.far = kwargs["far"]
+        self.n_azi = kwargs["n_azi"]
+        self.n_ele = kwargs["n_ele"]
+        self.speed = kwargs["speed"]
+        self.fs = kwargs["fs"]
+        self.pathloss = kwargs["pathloss"]
+        self.xyz_min = kwargs["xyz_min"]
+        self.xyz_max = kwargs["xyz_max"]
+        #: receivers rendered per kernel pass (bounds the activation memory of large inference batches)
+        self.max_receivers_per_pass = int(kwargs.get("max_receivers_per_pass", 8))
+        self._tables = {}
+
+    # -- configuration -----------------------------------------------------------------------------
+    def render_cfg(self) -> dict:
+        return {"n_samples": self.n_samples, "near": self.near, "far": self.far, "n_azi": self.n_azi,
+                "n_ele": self.n_ele, "speed": self.speed, "fs": self.fs, "pathloss": self.pathloss,
+                "xyz_min": self.xyz_min, "xyz_max": self.xyz_max}
+
+    def tables_for(self, T: int, device) -> tables.RenderTables:
+        key = (int(T), str(device))
+        if key not in self._tables:
+            self._tables[key] = tables.RenderTables(self.render_cfg(), int(T), device)
+        return self._tables[key]
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward(self, rays_o, position_tx, direction_tx=None, ch_idx=None, azi_rand=None):
+        """rays_o[bs,3] receiver positions, position_tx[bs,3], direction_tx[bs,3] (RAF), ch_idx[bs].
+
+        ``azi_rand`` (``[n_azi]`` in [0,1), optional) injects the azimuth jitter that the reference draws
+        from the global CPU generator on every call (renderer.py:149); tests use it for repeatability.
+        """
+        if not rays_o.is_cuda:
+            raise _lib.AVRLibraryError("avr_b200.AVRRender runs on CUDA tensors only (no CPU fallback); "
+                                       "the CPU reference path is oracle/render_ref.py")
+        _lib.load()
+        device = rays_o.device
+        rays_o = rays_o.detach().contiguous().float()
+        position_tx = position_tx.detach().to(device).contiguous().float()
+        if direction_tx is not None:
+            direction_tx = direction_tx.detach().to(device).contiguous().float()
+        dirs = tables.direction_table(self.n_azi, self.n_ele, azi_rand).to(device, non_blocking=True)
+        bs = position_tx.size(0)
+        step = max(1, self.max_receivers_per_pass)
+        outs = []
+        for b0 in range(0, bs, step):
+            sl = slice(b0, min(bs, b0 + step))
+            outs.append(self._render_pass(rays_o[sl], position_tx[sl],
+                                          direction_tx[sl] if direction_tx is not None else None,
+                                          ch_idx[sl] if ch_idx is not None else None, dirs))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def _render_pass(self, rays_o, position_tx, direction_tx, ch_idx, dirs):
+        net = self.network_fn
+        bs = rays_o.size(0)
+        if hasattr(net, "fused_plan"):
+            plan = net.fused_plan()
+            if plan["needs_dir_tx"] and direction_tx is None:
+                raise ValueError("this field needs direction_tx (AVRModel_complex, model.py:291)")
+            T = int(net.signal_output_dim)
+            tab = self.tables_for(T, rays_o.device)
+            geom = ops.make_geom(self.render_cfg(), bs, T)
+            params = [m.params for m in plan_modules(plan)]
+            return FusedRenderFunction.apply(plan, geom, tab.dev, rays_o, position_tx,
+                                             direction_tx if plan["needs_dir_tx"] else None, dirs, *params)
+
+        # generic networks_fn: build what renderer.py:54-62 builds, call the network, composite.
+        cfg = self.render_cfg()
+        geom0 = ops.make_geom(cfg, bs, 1)
+        d_vals = torch.linspace(0., 1., self.n_samples) * (self.far - self.near) + self.near
+        d_vals = d_vals.to(rays_o.device)
+        pts, view, txn, _ = ops.sample_points(geom0, rays_o, position_tx, dirs, d_vals, want_delay=False)
+        args = [pts, view, txn]
+        if direction_tx is not None:
+            args.append(direction_tx[:, None, :].expand(bs, pts.size(1), 3))
+        kwargs = {}
+        if ch_idx is not None and "ch_idx" in inspect.signature(net.forward).parameters:
+            kwargs["ch_idx"] = ch_idx
+        attn, signal = net(*args, **kwargs)
+        T = signal.size(-1)
+        geom = ops.make_geom(cfg, bs, T)
+        tab = self.tables_for(T, rays_o.device)
+        _, _, _, delay = ops.sample_points(geom, rays_o, position_tx, dirs, tab.dev["d"], want_pts=False)
+        attn = attn.reshape(bs, geom.R, geom.S)
+        signal = signal.reshape(bs, geom.R, geom.S, T)
+        return CompositeFunction.apply(attn, signal, delay, geom, tab.dev)

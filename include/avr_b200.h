@@ -1,0 +1,190 @@
+/*
+ * avr_b200 -- C-ABI of the B200-native (sm_100a) AVR acoustic volume-rendering hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native code of
+ * its own: the functions below replace what `renderer.py` / `model.py` execute inside
+ * tiny-cuda-nn and ATen.  Each entry cites the reference lines it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success, else an AVR_ERR_* / cudaError_t value;
+ *     avr_last_error() gives a thread-local message.  Nothing throws, nothing exits.
+ *   - everything is asynchronous on `stream` (a cudaStream_t passed as void*) of CUDA
+ *     device `device`; no call synchronises, allocates or retains pointers.
+ *   - all buffers are device pointers owned by the caller (PyTorch allocates outputs and
+ *     workspaces); fp32 unless said otherwise; matrices row-major with an explicit leading
+ *     dimension (`ld*`, in elements) so column blocks of wider buffers can be addressed.
+ *   - point / row order is the reference's: n = (b*R + r)*S + s   (renderer.py:55-58).
+ *   - no global mutable state: safe under concurrent calls from several host threads
+ *     (nn.DataParallel, the autograd engine's device threads).
+ */
+#ifndef AVR_B200_H
+#define AVR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVR_B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define AVR_API __attribute__((visibility("default")))
+#else
+#define AVR_API
+#endif
+#define AVR_MAX_LEVELS 32
+
+enum {
+    AVR_OK = 0,
+    AVR_ERR_INVALID = 10001,      /* bad argument (null pointer, misaligned, bad shape) */
+    AVR_ERR_UNSUPPORTED = 10002   /* valid request this build does not implement */
+};
+
+/* Render geometry: the per-(b,r,s) arithmetic of renderer.py:54-62,86-87 / renderer_cpu.py:46-52,76-77. */
+typedef struct avr_render_geom {
+    int32_t bs, R, S, T;   /* receivers, rays (n_azi*n_ele+2), samples per ray, IR length */
+    float xyz_min;         /* (float)xyz_min                                   */
+    float xyz_span;        /* (float)((double)xyz_max - (double)xyz_min)       */
+    float fs, speed;       /* (float)fs, (float)speed                          */
+} avr_render_geom;
+
+/* Multiresolution hash grid (tiny-cuda-nn "HashGrid", 3-D input, linear interpolation,
+ * coherent-prime hash) -- what tcnn.Encoding(3, cfg) at model.py:66-68,258-264 builds. */
+typedef struct avr_grid_meta {
+    int32_t n_levels, n_feat;             /* n_feat must be 2 in this build */
+    float scale[AVR_MAX_LEVELS];          /* exp2f(l*log2(pls))*base - 1                 */
+    uint32_t res[AVR_MAX_LEVELS];         /* ceil(scale)+1                               */
+    uint32_t size[AVR_MAX_LEVELS];        /* entries in level l                          */
+    uint32_t offset[AVR_MAX_LEVELS];      /* first entry of level l in the flat table    */
+    uint32_t total;                       /* sum(size)                                   */
+} avr_grid_meta;
+
+/* Epilogue / operand flags of avr_gemm */
+enum {
+    AVR_GEMM_RELU = 1,        /* C = max(C, 0)                                             */
+    AVR_GEMM_ACCUM = 2,       /* C += product (otherwise C = product)                      */
+    AVR_GEMM_MASK = 4,        /* product *= (aux[i,j] > 0)  (ReLU backward)                */
+    AVR_GEMM_RELU_A = 8,      /* A := max(A, 0) on load (consumer-side ReLU)               */
+    AVR_GEMM_RELU_B = 16      /* B := max(B, 0) on load                                    */
+};
+/* Operand layouts of avr_gemm: element (i,k) of an operand P with leading dimension ld */
+enum {
+    AVR_K_CONTIG = 0,         /* P[i*ld + k]  (reduction index contiguous)                  */
+    AVR_I_CONTIG = 1          /* P[k*ld + i]  (output index contiguous)                     */
+};
+
+AVR_API int avr_abi_version(void);
+AVR_API const char* avr_last_error(void);
+/* number of kernels launched by this library (process-wide) since the last reset */
+AVR_API int64_t avr_launch_count(int reset);
+
+/* ---- ray generation + sampling (+ delays) -------------------------------------------------
+ * renderer.py:54-62 (ray_pts, normalize_points, network_view/tx) and :86-87 (tx->point delay).
+ * Writes the network inputs the reference would materialise -- used by the generic
+ * `networks_fn` path and by the bit-exactness tests.  Any output pointer may be NULL.
+ *   rays_o[bs,3], pos_tx[bs,3], dirs[R,3], d_vals[S]
+ *   pts_n[bs,P,3], view[bs,P,3], tx_n[bs,P,3]  (normalised to [-1,1]; P = R*S)
+ *   delay[bs,R,S] int32 in [0,T-1] */
+AVR_API int avr_sample_points(const avr_render_geom* geom, const float* rays_o, const float* pos_tx,
+                      const float* dirs, const float* d_vals, float* pts_n, float* view, float* tx_n,
+                      int32_t* delay, int device, void* stream);
+
+/* Unit-cube inputs of the per-ray / per-receiver encodings (renderer.py:59-60 + model.py:188-189,
+ * 309-311): u_view[R,3] = (-dirs+1)/2, u_tx[bs,3] = (normalize(pos_tx)+1)/2,
+ * u_dir_tx[bs,3] = (dir_tx+1)/2.  dir_tx and any output may be NULL. */
+AVR_API int avr_aux_inputs(const avr_render_geom* geom, const float* pos_tx, const float* dirs, const float* dir_tx,
+                   float* u_view, float* u_tx, float* u_dir_tx, int device, void* stream);
+
+/* ---- fused ray generation + sampling + hash-grid encode --------------------------------------
+ * renderer.py:54-58 + model.py:187,191 (tcnn kernel_grid forward) in one kernel: sample positions
+ * are produced in registers and encoded; nothing of shape [bs,P,3] reaches HBM.
+ *   table[total*2]; out rows n=(b,r,s): out[n*ld_out + col0 + 2*l + f];
+ *   columns [col0+2L, col0+2L+n_ones) are set to 1 (tcnn input padding);
+ *   delay (optional, int32[bs,R,S]) as in avr_sample_points. */
+AVR_API int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
+                          const float* pos_tx, const float* dirs, const float* d_vals, const float* table,
+                          float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int32_t* delay,
+                          int device, void* stream);
+
+/* Backward of the above w.r.t. the table (tcnn kernel_grid_backward), DETERMINISTIC:
+ * contributions are accumulated as 2^e-scaled int64 (integer addition is associative), `e`
+ * derived on the device from absmax(d_out) and `log2_headroom` >= log2(max contributions per
+ * entry).  acc[total*2] int64 must be zeroed by the caller (or hold a previous partial sum
+ * taken with the same gmax_bits); gmax_bits is a device uint32 filled by avr_absmax_bits. */
+AVR_API int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
+                          const float* dirs, const float* d_vals, const float* d_out, int64_t ld_out,
+                          int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, int64_t* acc,
+                          int device, void* stream);
+
+/* Encode explicit unit-cube points u[N,3] (model.py:191,219-220 on arbitrary inputs). */
+AVR_API int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* table,
+                        float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int device, void* stream);
+AVR_API int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* d_out,
+                        int64_t ld_out, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
+                        int64_t* acc, int device, void* stream);
+/* gmax_bits = max(gmax_bits, bit pattern of max |x[i, col0:col0+ncols]|)  (caller zeroes it first) */
+AVR_API int avr_absmax_bits(const float* x, int64_t rows, int64_t ld, int32_t col0, int32_t ncols,
+                    uint32_t* gmax_bits, int device, void* stream);
+/* grad[i] (+)= (float)(acc[i] * 2^-e) */
+AVR_API int avr_grid_grad_finalize(const int64_t* acc, int64_t n, const uint32_t* gmax_bits, int32_t log2_headroom,
+                           float* grad, int accumulate, int device, void* stream);
+
+/* ---- dense layers (tcnn FullyFusedMLP / CutlassMLP, model.py:117,146,176) ---------------------
+ * C[i,j] (+)= sum_k A(i,k) * B(j,k),  i<M, j<N, k<K, fp32 FMA accumulation.
+ * `workspace` (>= avr_gemm_workspace_bytes) enables deterministic split-K for long reductions;
+ * pass NULL/0 to force a single pass.  aux (MASK) has C's shape with leading dimension ldaux. */
+AVR_API int64_t avr_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+AVR_API int avr_gemm(int layout_a, int layout_b, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+             const float* B, int64_t ldb, float* C, int64_t ldc, int flags, const float* aux, int64_t ldaux,
+             void* workspace, int64_t workspace_bytes, int device, void* stream);
+
+/* ---- broadcast inputs of the signal network (renderer.py:59-60; model.py:219-221) ------------
+ * dst[n, col0:col0+w] = src[row(n), 0:w] with row(n) = r (per_receiver=0) or b (per_receiver=1). */
+AVR_API int avr_rows_broadcast(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,
+                       float* dst, int64_t ld_dst, int32_t col0, int device, void* stream);
+/* transpose of the above: d_src[row, :] = sum over the points mapped to `row` (fixed order). */
+AVR_API int64_t avr_rows_reduce_workspace_bytes(const avr_render_geom* geom, int32_t w, int per_receiver);
+AVR_API int avr_rows_reduce(const avr_render_geom* geom, const float* d_dst, int64_t ld_dst, int32_t col0, int32_t w,
+                    int per_receiver, float* d_src, float* workspace, int64_t workspace_bytes,
+                    int device, void* stream);
+
+/* ---- density -> alpha -> transmittance -> ray weights (renderer.py:167-190; model.py:233) ----
+ * attn = |leaky_relu(raw, slope)|; alpha = 1-exp(-attn*delta[s]); w = alpha*prod_{j<s}(1-alpha_j+1e-6)
+ * raw is read as raw[n*ld_raw]; attn / w are [bs,R,S] dense (attn may be NULL). One warp per ray.
+ * slope < 0: raw already is the density (generic networks_fn path), no activation is applied. */
+AVR_API int avr_ray_weights_fwd(const avr_render_geom* geom, const float* raw, int64_t ld_raw, const float* delta,
+                        float slope, float* attn, float* w, int device, void* stream);
+/* d_raw[n*ld_draw] = dL/draw given d_w[bs,R,S] (recomputes alpha / transmittance from raw) */
+AVR_API int avr_ray_weights_bwd(const avr_render_geom* geom, const float* raw, int64_t ld_raw, const float* delta,
+                        float slope, const float* d_w, float* d_raw, int64_t ld_draw, int device, void* stream);
+
+/* ---- compositing (renderer.py:79-118), ray reduction done in the time domain ----------------
+ * y[b,s,t] = sum_r w[b,r,s] * (t >= delay[b,r,s]) * sig[b,r,s,t]          (masks :82-90, sums :118,192)
+ * sig[bs,R,S,T] is streamed exactly once; `workspace` holds per-ray-chunk partial sums. */
+AVR_API int64_t avr_composite_workspace_bytes(const avr_render_geom* geom);
+AVR_API int avr_composite_fwd(const avr_render_geom* geom, const float* sig, const float* w, const int32_t* delay,
+                      float* y, void* workspace, int64_t workspace_bytes, int device, void* stream);
+/* d_sig[b,r,s,t] = w*(t>=delay)*d_y[b,s,t];  d_w[b,r,s] = sum_t (t>=delay)*sig*d_y[b,s,t]
+ * (d_sig may be NULL when only d_w is wanted, sig may be NULL when only d_sig is wanted) */
+AVR_API int avr_composite_bwd(const avr_render_geom* geom, const float* sig, const float* w, const int32_t* delay,
+                      const float* d_y, float* d_sig, float* d_w, int device, void* stream);
+
+/* ---- spectrum: tail mask * path loss, real DFT, per-sample phase, sum over samples ----------
+ * (renderer.py:82-83,96-109,118-121).  Small tables come from the host glue:
+ *   gain[S,T]      = (t < T-1-shift[s]) ? pl[shift[s]+t] : 0
+ *   phase[S,F,2]   = (cos ang[s,f], -sin ang[s,f])              (exp(-j*ang), renderer.py:108)
+ *   dft[T,ldd]     = columns (cos(2 pi f t/T), -sin(2 pi f t/T)) interleaved, ldd >= 2F, ldd%4==0
+ * fwd:  z = y*gain;  X = z @ dft;  out[b,f,:] = sum_s X[b,s,f] * phase[s,f]        -> out[bs,F,2]
+ * bwd:  d_y = gain * ( (conj-phase-weighted d_out) @ dft^T )
+ * xbuf: scratch [bs*S, ldd] floats (z is formed in place in zbuf [bs*S,T]). */
+AVR_API int avr_spectrum_fwd(const avr_render_geom* geom, const float* y, const float* gain, const float* phase,
+                     const float* dft, int64_t ldd, float* zbuf, float* xbuf, float* out,
+                     int device, void* stream);
+AVR_API int avr_spectrum_bwd(const avr_render_geom* geom, const float* d_out, const float* gain, const float* phase,
+                     const float* dft, int64_t ldd, float* xbuf, float* d_y, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVR_B200_H */

@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic: tables, configs, C-ABI surface, loud failure, gradient arena."""
+import os
+import re
+
+import pytest
+import torch
+
+import avr_b200
+from avr_b200 import _lib, tables
+from avr_b200.configs import CONFIGS, get_config
+from oracle import field_ref, render_ref
+from oracle.reference_shim import REFERENCE_ROOT, reference_available
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported_and_bound(built_library):
+    header = open(os.path.join(ROOT, "include", "avr_b200.h")).read()
+    declared = set(re.findall(r"AVR_API\s+[\w\s\*]+?\b(avr_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(built_library, name)
+    assert built_library.avr_abi_version() == 1
+
+
+def test_renderer_refuses_cpu_tensors():
+    from avr_b200.configs import tiny_config
+    cfg = tiny_config()
+    ren = avr_b200.AVRRender(avr_b200.AVRModel(cfg["model"]), **cfg["render"])
+    with pytest.raises(_lib.AVRLibraryError):
+        ren(torch.zeros(1, 3), torch.zeros(1, 3))
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_tables_bit_exact_vs_oracle(name):
+    cfg = get_config(name)
+    r, T = cfg["render"], cfg["model"]["signal_output_dim"]
+    ref = render_ref.static_tables(r, T)
+    tab = tables.RenderTables(r, T, "cpu")
+    assert torch.equal(tab.host["d"], ref["d"])
+    assert torch.equal(tab.host["tau"], ref["tau"])
+    assert torch.equal(tab.host["shift"], ref["shift"])
+    assert torch.equal(tab.host["pl"], ref["pl"])
+    assert torch.equal(tab.dev["delta"], ref["delta"])
+    assert torch.equal(torch.view_as_complex(tab.dev["phase"]), ref["phase"].to(torch.complex64))
+    # gain = tail mask * shifted path loss, exactly the product the reference applies in two steps
+    t = torch.arange(T)
+    tail = ((torch.arange(T - 1, -1, -1)[None, :] - ref["shift"][:, None]) > 0).float()
+    pl_all = torch.stack([ref["pl"][int(i):int(i) + T] for i in ref["shift"]])
+    assert torch.equal(tab.dev["gain"], tail * pl_all)
+    torch.manual_seed(4)
+    a = tables.direction_table(r["n_azi"], r["n_ele"])
+    torch.manual_seed(4)
+    b = render_ref.direction_table(r["n_azi"], r["n_ele"])
+    assert torch.equal(a, b)
+
+
+def test_dft_matrix_matches_rfft():
+    T = 200
+    m = tables.dft_matrix(T).double()
+    x = torch.randn(5, T, dtype=torch.float64)
+    spec = torch.fft.rfft(x, dim=-1)
+    got = x @ m
+    F = T // 2 + 1
+    assert torch.allclose(got[:, 0:2 * F:2], spec.real, atol=1e-5)
+    assert torch.allclose(got[:, 1:2 * F:2], spec.imag, atol=1e-5)
+    assert m.shape[1] % 4 == 0 and float(m[:, 2 * F:].abs().max() if m.shape[1] > 2 * F else 0) == 0
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_grid_geometry_matches_oracle_and_survey(name):
+    from avr_b200.model import hashgrid_geometry
+    for key, sub in get_config(name)["model"].items():
+        if isinstance(sub, dict) and sub.get("otype") == "HashGrid":
+            a, b = hashgrid_geometry(sub), field_ref.hashgrid_geometry(sub)
+            assert a == b
+            if sub["log2_hashmap_size"] == 18:
+                assert a["total"] * 2 == 9510912          # SURVEY 8 "derived sizes"
+                assert a["size"][:4] == [4096, 32768, 262144, 262144]
+            else:
+                assert a["total"] * 2 == 36249600
+
+
+def test_parameter_counts_match_survey():
+    for name, total in (("simu", 30089216), ("meshrir", 57237504), ("raf_furnished", 58994688)):
+        cfg = get_config(name)
+        cls = avr_b200.AVRModel if cfg["model_class"] == "AVRModel" else avr_b200.AVRModel_complex
+        net = cls(cfg["model"])
+        assert sum(p.numel() for p in net.parameters()) == total, name
+        names = {k for k, _ in net.named_parameters()}
+        assert "_pos_encoding.params" in names and "_model_signal.params" in names
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+def test_configs_match_reference_yaml():
+    import yaml
+    files = {"simu": "avr_simu.yml", "meshrir": "avr_meshrir.yml", "raf_furnished": "avr_raf_furnished.yml",
+             "real_exp_ch_emb_1": "avr_real_exp_ch_emb_1.yml"}
+    for name, fn in files.items():
+        y = yaml.safe_load(open(os.path.join(REFERENCE_ROOT, "config_files", fn)))
+        ours = get_config(name)
+        assert ours["render"] == y["render"], name
+        assert ours["model"] == y["model"], name
+        assert ours["dataset_type"] == y["path"]["dataset_type"]
+
+
+def test_state_dict_interchange_with_oracle():
+    from avr_b200.configs import tiny_config
+    for mc, ours, ref in (("AVRModel", avr_b200.AVRModel, field_ref.AVRModelRef),
+                          ("AVRModel_complex", avr_b200.AVRModel_complex, field_ref.AVRModelComplexRef)):
+        cfg = tiny_config(mc)
+        a, b = ours(cfg["model"]), ref(cfg["model"])
+        a.load_state_dict(b.state_dict())
+        for (ka, va), (kb, vb) in zip(sorted(a.state_dict().items()), sorted(b.state_dict().items())):
+            assert ka == kb and torch.equal(va, vb)
+
+
+def test_grad_arena_views_and_rebind():
+    p1, p2 = torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(3, 3))
+    arena = avr_b200.GradArena([p1, p2])
+    (p1.sum() * 2 + (p2 * 3).sum()).backward()
+    assert p1.grad.data_ptr() == arena.flat.data_ptr()
+    assert torch.equal(arena.flat[:5], torch.full((5,), 2.0))
+    assert torch.equal(arena.flat[8:17], torch.full((9,), 3.0))
+    arena.zero_()
+    assert float(arena.flat.abs().sum()) == 0 and p2.grad.data_ptr() == arena.flat[8:].data_ptr()
