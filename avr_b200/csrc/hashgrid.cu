@@ -285,7 +285,9 @@ using namespace avr;
 extern "C" int avr_sample_points(const avr_render_geom* geom, const float* rays_o, const float* pos_tx,
                                  const float* dirs, const float* d_vals, float* pts_n, float* view, float* tx_n,
                                  int32_t* delay, int device, void* stream) {
-    AVR_REQUIRE(geom && rays_o && pos_tx && dirs && d_vals, "null input");
+    AVR_REQUIRE(geom, "null geometry");
+    if ((int64_t)geom->bs * geom->R * geom->S == 0) return AVR_OK;
+    AVR_REQUIRE(rays_o && pos_tx && dirs && d_vals, "null input");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     const int64_t n = (int64_t)geo.bs * geo.R * geo.S;

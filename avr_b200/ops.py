@@ -14,6 +14,30 @@ from . import _lib
 from ._lib import GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG, GridMeta, RenderGeom  # noqa: F401
 
 
+# ---- optional per-launch timing (bench.py): CUDA events on the launching stream ----------------------
+PROFILE = None          # set to a list to collect (name, work, unit, start_event, end_event)
+
+
+class _timed:
+    __slots__ = ("name", "work", "unit", "start")
+
+    def __init__(self, name, work, unit):
+        self.name, self.work, self.unit, self.start = name, work, unit, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE.append((self.name, self.work, self.unit, self.start, end))
+        return False
+
+
 def _ctx(t: torch.Tensor):
     if not t.is_cuda:
         raise _lib.AVRLibraryError("avr_b200 ops need CUDA tensors (there is no CPU fallback)")
@@ -91,10 +115,13 @@ def aux_inputs(g: RenderGeom, pos_tx, dirs, dir_tx=None):
 # ---- hash grid ------------------------------------------------------------------------------------
 def raygen_encode_fwd(g, meta, rays_o, pos_tx, dirs, d_vals, table, out, col0=0, n_ones=0, delay=None):
     dev, st = _ctx(out)
-    _lib.check(_lib.load().avr_raygen_encode_fwd(C.byref(g), C.byref(meta), _p(_dense(rays_o)),
-                                                 _p(_dense(pos_tx)) if pos_tx is not None else None, _p(_dense(dirs)),
-                                                 _p(_dense(d_vals)), _p(_dense(table)), _p(out), out.stride(0), col0,
-                                                 n_ones, _p(delay, torch.int32), dev, st), "avr_raygen_encode_fwd")
+    n_pts = g.bs * g.R * g.S
+    with _timed("raygen_encode_fwd", float(n_pts) * meta.n_levels * 72, "byte"):     # 8 corners*8 B + 8 B out
+        _lib.check(_lib.load().avr_raygen_encode_fwd(C.byref(g), C.byref(meta), _p(_dense(rays_o)),
+                                                     _p(_dense(pos_tx)) if pos_tx is not None else None,
+                                                     _p(_dense(dirs)), _p(_dense(d_vals)), _p(_dense(table)), _p(out),
+                                                     out.stride(0), col0, n_ones, _p(delay, torch.int32), dev, st),
+                   "avr_raygen_encode_fwd")
 
 
 def grid_encode_fwd(meta, u, table, out, col0=0, n_ones=0):
@@ -124,10 +151,12 @@ class GridGradAccumulator:
 
     def add_rays(self, g, rays_o, dirs, d_vals, d_out, col0=0):
         dev, st = _ctx(d_out)
-        _lib.check(_lib.load().avr_raygen_encode_bwd(C.byref(g), C.byref(self.meta), _p(_dense(rays_o)), _p(_dense(dirs)),
-                                                     _p(_dense(d_vals)), _p(d_out), d_out.stride(0), col0,
-                                                     _p(self.gmax, torch.int32), self.headroom,
-                                                     _p(self.acc, torch.int64), dev, st), "avr_raygen_encode_bwd")
+        n_pts = g.bs * g.R * g.S
+        with _timed("raygen_encode_bwd", float(n_pts) * self.meta.n_levels * 136, "byte"):   # 8 B d_out + 8 corners*16 B rmw
+            _lib.check(_lib.load().avr_raygen_encode_bwd(C.byref(g), C.byref(self.meta), _p(_dense(rays_o)),
+                                                         _p(_dense(dirs)), _p(_dense(d_vals)), _p(d_out), d_out.stride(0),
+                                                         col0, _p(self.gmax, torch.int32), self.headroom,
+                                                         _p(self.acc, torch.int64), dev, st), "avr_raygen_encode_bwd")
 
     def add_points(self, u, d_out, col0=0):
         dev, st = _ctx(d_out)
@@ -156,8 +185,9 @@ def gemm(la, lb, M, N, K, A, lda, B, ldb, Cmat, ldc, flags=0, aux=None, ldaux=0,
     ws_ptr, ws_bytes = (None, 0)
     if workspace is not None:
         ws_ptr, ws_bytes = C.c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size()
-    _lib.check(_lib.load().avr_gemm(la, lb, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, flags, _p(aux), ldaux,
-                                    ws_ptr, ws_bytes, dev, st), "avr_gemm")
+    with _timed("sgemm", 2.0 * M * N * K, "flop"):
+        _lib.check(_lib.load().avr_gemm(la, lb, M, N, K, _p(A), lda, _p(B), ldb, _p(Cmat), ldc, flags, _p(aux), ldaux,
+                                        ws_ptr, ws_bytes, dev, st), "avr_gemm")
 
 
 def linear_fwd(x, w, y, relu=False, relu_in=False, accum=False):
@@ -219,8 +249,11 @@ def composite_fwd(g, sig, w, delay):
     nbytes = int(_lib.load().avr_composite_workspace_bytes(C.byref(g)))
     ws = torch.empty(max(1, nbytes // 4), device=sig.device)
     y = torch.empty(g.bs, g.S, g.T, device=sig.device)
-    _lib.check(_lib.load().avr_composite_fwd(C.byref(g), _p(_dense(sig)), _p(_dense(w)), _p(_dense(delay), torch.int32),
-                                             _p(y), _p(ws), nbytes, dev, st), "avr_composite_fwd")
+    n_pts = g.bs * g.R * g.S
+    with _timed("composite_fwd", float(n_pts) * (g.T * 4 + 8) + g.bs * g.S * g.T * 4.0, "byte"):
+        _lib.check(_lib.load().avr_composite_fwd(C.byref(g), _p(_dense(sig)), _p(_dense(w)),
+                                                 _p(_dense(delay), torch.int32), _p(y), _p(ws), nbytes, dev, st),
+                   "avr_composite_fwd")
     return y
 
 
@@ -230,9 +263,12 @@ def composite_bwd(g, sig, w, delay, d_y, want_dsig=True, want_dw=True, d_sig_out
     if want_dsig:
         d_sig = d_sig_out if d_sig_out is not None else torch.empty(g.bs, g.R, g.S, g.T, device=d_y.device)
     d_w = torch.empty(g.bs, g.R, g.S, device=d_y.device) if want_dw else None
-    _lib.check(_lib.load().avr_composite_bwd(C.byref(g), _p(_dense(sig)) if sig is not None else None, _p(_dense(w)),
-                                             _p(_dense(delay), torch.int32), _p(_dense(d_y)), _p(d_sig), _p(d_w), dev, st),
-               "avr_composite_bwd")
+    n_pts = g.bs * g.R * g.S
+    nbytes = float(n_pts) * g.T * 4 * ((1 if want_dsig else 0) + (1 if (want_dw and sig is not None) else 0))
+    with _timed("composite_bwd", nbytes, "byte"):
+        _lib.check(_lib.load().avr_composite_bwd(C.byref(g), _p(_dense(sig)) if sig is not None else None,
+                                                 _p(_dense(w)), _p(_dense(delay), torch.int32), _p(_dense(d_y)),
+                                                 _p(d_sig), _p(d_w), dev, st), "avr_composite_bwd")
     return d_sig, d_w
 
 
