@@ -1,0 +1,536 @@
+// Dense layers on the 5th-generation tensor cores: tcgen05.mma + TMEM accumulators + TMA operand staging.
+//
+// Replaces the tiny-cuda-nn FullyFusedMLP / CutlassMLP kernels of model.py:117,146,176 (and their backward).
+// tcnn computes in fp16 with fp16 accumulators; the parity target here is the fp32 oracle (1e-4 rel-L2 on
+// the IR and on every parameter gradient), which single-pass bf16/tf32 products cannot meet.  Operands are
+// therefore stored as an error-compensated PAIR of bf16 planes, x = hi + lo with hi = bf16(x),
+// lo = bf16(x - hi) (16 mantissa bits, the same 4 bytes/element as fp32), and every product is evaluated as
+//        A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (three tcgen05.mma into one fp32 TMEM accumulator)
+// which leaves a relative error of ~2^-17 per product -- fp32-grade for this network -- at 1/3 of the bf16
+// tensor rate instead of the ~1/50 an fp32 SIMT GEMM gets.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of both planes of the A and B tiles into
+//               a ring of shared-memory stages, completion on mbarriers
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues 12 tcgen05.mma (4 k16 steps x 3 products)
+//               per 64-wide k-block, tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's MMAs
+//               overlap), apply mask / accumulate / ReLU, split into hi/lo planes (or write fp32), store
+// Two operand modes: K-major x K-major (forward, backward-data with a pre-transposed weight) and
+// MN-major x MN-major with split-K over the sample points (weight gradients, deterministic second pass).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace avr {
+
+enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16 };
+
+struct UmmaParams {
+    int M, N, K;            // K-major: rows, cols, reduction.  MN-major: A extent, B extent, reduction (points)
+    int BN;                 // tile columns (multiple of 16, <= 256)
+    int tiles_m, tiles_n, k_splits, k_per_split;
+    int stages, tmem_cols;
+    int flags;
+    __nv_bfloat16* c; long long ldc, c_plane;          // plane-pair output
+    __nv_bfloat16* c2; long long ldc2, c2_plane;       // second (ReLU'd) plane-pair output
+    const __nv_bfloat16* mask; long long ldmask;       // hi plane of the activation whose sign gates the result
+    float* c32; long long ldc32;                       // fp32 output / split-K partials
+};
+
+constexpr int UM = 128;            // UMMA_M
+constexpr int UBK = 64;            // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int UTHREADS = 192;
+constexpr uint32_t A_PLANE_BYTES = UM * 128;          // 16 KB
+constexpr uint32_t A_TILE_BYTES = 2 * A_PLANE_BYTES;  // hi + lo
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// store 8 consecutive values of one row as hi/lo planes (16 B each)
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* base, long long plane, const float* v, bool relu) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        __nv_bfloat16 ah, al, bh, bl;
+        split_bf16(a, ah, al);
+        split_bf16(b, bh, bl);
+        h[i] = pack2(ah, bh);
+        l[i] = pack2(al, bl);
+    }
+    *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(base + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <bool MN_MAJOR>
+__global__ void __launch_bounds__(UTHREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bn_rows = MN_MAJOR ? ((p.BN + 63) / 64) * 64 : p.BN;     // B rows (K-major) / MN extent (MN-major) in smem
+    const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
+    const uint32_t b_tile_bytes = (uint32_t)bn_rows * 256u;
+    const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.stages;
+    const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+    if (warp == 0) {
+        // ===================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int split = tile % p.k_splits;
+                const int mn = tile / p.k_splits;
+                const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
+                const int k_beg = split * p.k_per_split;
+                const int k_end = min(p.K, k_beg + p.k_per_split);
+                for (int k0 = k_beg; k0 < k_end; k0 += UBK) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_TILE_BYTES;
+                    mbar_expect_tx(full, stage_bytes);
+                    if (!MN_MAJOR) {
+                        tma_load_3d(sa, &tmA, full, k0, m0, 0);
+                        tma_load_3d(sb, &tmB, full, k0, n0, 0);
+                    } else {
+                        tma_load_3d(sa, &tmA, full, m0, k0, 0);
+                        tma_load_3d(sa + 16384, &tmA, full, m0 + 64, k0, 0);
+                        for (int i = 0; i < bn_rows / 64; ++i) tma_load_3d(sb + 16384 * i, &tmB, full, n0 + 64 * i, k0, 0);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer
+        if (lane == 0) {
+            uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+            if (MN_MAJOR) idesc |= (1u << 15) | (1u << 16);
+            int stage = 0, iter = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+                const int split = tile % p.k_splits;
+                const int k_beg = split * p.k_per_split;
+                const int k_end = min(p.K, k_beg + p.k_per_split);
+                const int acc = iter & 1;
+                mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                uint32_t accumulate = 0;
+                for (int k0 = k_beg; k0 < k_end; k0 += UBK) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_TILE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < UBK / 16; ++j) {
+                        uint64_t a_hi, a_lo, b_hi, b_lo;
+                        if (!MN_MAJOR) {
+                            a_hi = smem_desc(sa + 32 * j, 16, 1024);
+                            a_lo = smem_desc(sa + A_PLANE_BYTES + 32 * j, 16, 1024);
+                            b_hi = smem_desc(sb + 32 * j, 16, 1024);
+                            b_lo = smem_desc(sb + b_plane_bytes + 32 * j, 16, 1024);
+                        } else {
+                            a_hi = smem_desc(sa + 2048 * j, 16384, 1024);
+                            a_lo = smem_desc(sa + 8192 + 2048 * j, 16384, 1024);
+                            b_hi = smem_desc(sb + 2048 * j, 16384, 1024);
+                            b_lo = smem_desc(sb + 8192 + 2048 * j, 16384, 1024);
+                        }
+                        umma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate);      // small terms first
+                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+                        accumulate = 1u;
+                    }
+                    umma_commit(bar_empty + 8 * stage);                          // frees the stage when the MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);                                // accumulator complete
+            }
+        }
+    } else {
+        // ===================================== epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+        const int lane_grp = warp & 3;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            const int split = tile % p.k_splits;
+            const int mn = tile / p.k_splits;
+            const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
+            const int acc = iter & 1;
+            mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
+            tc_fence_after();
+            const long long row = m0 + lane_grp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
+            const bool row_ok = row < p.M;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);                                       // warp-collective: outside the row guard
+                if (!row_ok) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long col = n0 + c0 + 8 * h;
+                    if (col >= p.N) continue;
+                    float* x = v + 8 * h;
+                    if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
+                        float* dst = MN_MAJOR ? p.c32 + ((long long)split * p.M + row) * p.N + col : p.c32 + row * p.ldc32 + col;
+                        if (!MN_MAJOR && (p.flags & UF_ACCUM)) {
+                            const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
+                            x[0] += o0.x; x[1] += o0.y; x[2] += o0.z; x[3] += o0.w; x[4] += o1.x; x[5] += o1.y; x[6] += o1.z; x[7] += o1.w;
+                        }
+                        if (p.flags & UF_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+                        }
+                        *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                        continue;
+                    }
+                    if (p.flags & UF_MASK) {
+                        const uint4 m = *reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col);
+                        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (!(bf_lo(mw[i]) > 0.f)) x[2 * i] = 0.f;
+                            if (!(bf_hi(mw[i]) > 0.f)) x[2 * i + 1] = 0.f;
+                        }
+                    }
+                    __nv_bfloat16* dst = p.c + row * p.ldc + col;
+                    if (p.flags & UF_ACCUM) {
+                        const uint4 oh = *reinterpret_cast<const uint4*>(dst), ol = *reinterpret_cast<const uint4*>(dst + p.c_plane);
+                        const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            x[2 * i] += bf_lo(hw[i]) + bf_lo(lw[i]);
+                            x[2 * i + 1] += bf_hi(hw[i]) + bf_hi(lw[i]);
+                        }
+                    }
+                    store_planes8(dst, p.c_plane, x, (p.flags & UF_RELU) != 0);
+                    if (p.flags & UF_DUAL_RELU) store_planes8(p.c2 + row * p.ldc2 + col, p.c2_plane, x, true);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// fp32 [rows, cols] (ld) -> bf16 plane pair [2][rows][ldp]; optionally transposed (out[c][r] = in[r][c])
+__global__ void planes_split_kernel(const float* __restrict__ x, long long rows, long long cols, long long ld,
+                                    __nv_bfloat16* __restrict__ out, long long ldp, long long plane, int transpose, int relu) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols, c = i - r * cols;
+    float v = x[r * ld + c];
+    if (relu) v = fmaxf(v, 0.f);
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    const long long o = transpose ? c * ldp + r : r * ldp + c;
+    out[o] = hi;
+    out[o + plane] = lo;
+}
+
+__global__ void planes_merge_kernel(const __nv_bfloat16* __restrict__ in, long long rows, long long cols, long long ldp,
+                                    long long plane, float* __restrict__ out, long long ld) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols, c = i - r * cols;
+    out[r * ld + c] = __bfloat162float(in[r * ldp + c]) + __bfloat162float(in[r * ldp + c + plane]);
+}
+
+// dW[m, n] (+)= sum over splits of partial[split][m][n]   (fixed order)
+__global__ void umma_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, long long N,
+                                          float* __restrict__ C, long long ldc, int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    const long long r = i / N, c = i - r * N;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[((long long)z * M + r) * N + c];
+    C[r * ldc + c] = accumulate ? C[r * ldc + c] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    });
+    return fn;
+}
+
+// plane-pair tensor [2][rows][ld] of bf16, logical width `cols`; box = (64 cols, box_rows, 2 planes), 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
+                    int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(AVR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld * 2) % 16 || (plane * 2) % 16)
+        return fail(AVR_ERR_INVALID, "plane tensors need 16-byte aligned base, row pitch and plane pitch");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(AVR_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+    return AVR_OK;
+}
+
+static int pick_bn(long long N) {
+    if (N <= 256) return (int)(ceil_div(N, 16) * 16);
+    if (N % 256 == 0) return 256;
+    if (N % 128 == 0) return 128;
+    // e.g. 1600: prefer the multiple of 16 <= 256 that wastes least
+    int best = 256;
+    long long best_waste = ceil_div(N, 256) * 256 - N;
+    for (int bn = 240; bn >= 128; bn -= 16) {
+        long long waste = ceil_div(N, bn) * bn - N;
+        if (waste < best_waste) { best = bn; best_waste = waste; }
+    }
+    return best;
+}
+
+static int tmem_cols_for(int bn) {
+    int need = 2 * bn, c = 32;
+    while (c < need) c <<= 1;
+    return c;
+}
+
+static int num_sms(int device) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n > 0 ? n : 148;
+}
+
+}  // namespace avr
+
+using namespace avr;
+
+extern "C" {
+
+// x fp32 [rows, cols] (ld) -> plane pair; transpose != 0 writes out[c, r]
+AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
+                             int64_t plane_stride, int transpose, int relu, int device, void* stream) {
+    AVR_REQUIRE(planes && (x || rows * cols == 0), "null pointer");
+    AVR_ENTER(device);
+    if (rows * cols == 0) return AVR_OK;
+    planes_split_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, rows, cols, ld, (__nv_bfloat16*)planes, ldp, plane_stride, transpose, relu);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride, float* out,
+                             int64_t ld, int device, void* stream) {
+    AVR_REQUIRE(planes && out, "null pointer");
+    AVR_ENTER(device);
+    if (rows * cols == 0) return AVR_OK;
+    planes_merge_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)planes, rows, cols, ldp, plane_stride, out, ld);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+// C[M,N] = A[M,K] . B[N,K]^T on plane pairs (both K-major).  Output: plane pair (default) or fp32 (UF_OUT_F32).
+AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
+                             const void* b_planes, int64_t ldb, int64_t b_plane, int flags, void* c_planes, int64_t ldc,
+                             int64_t c_plane, void* c2_planes, int64_t ldc2, int64_t c2_plane, const void* mask_hi,
+                             int64_t ldmask, float* c_f32, int64_t ldc32, int device, void* stream) {
+    AVR_REQUIRE(a_planes && b_planes, "null operand");
+    AVR_REQUIRE(M >= 0 && N > 0 && K > 0, "bad dimensions");
+    AVR_REQUIRE(N % 8 == 0, "N must be a multiple of 8");
+    AVR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension overflow");
+    if (flags & UF_OUT_F32) AVR_REQUIRE(c_f32 && ldc32 % 4 == 0 && aligned16(c_f32), "fp32 output must be 16-byte aligned");
+    else AVR_REQUIRE(c_planes && ldc % 8 == 0 && c_plane % 8 == 0 && aligned16(c_planes), "plane output must be 16-byte aligned");
+    if (flags & UF_MASK) AVR_REQUIRE(mask_hi && ldmask % 8 == 0 && aligned16(mask_hi), "mask must be 16-byte aligned");
+    if (flags & UF_DUAL_RELU) AVR_REQUIRE(c2_planes && ldc2 % 8 == 0 && c2_plane % 8 == 0 && aligned16(c2_planes), "second output misaligned");
+    AVR_ENTER(device);
+    if (M == 0) return AVR_OK;
+    UmmaParams p = {};
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.BN = pick_bn(N);
+    p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
+    p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
+    p.tmem_cols = tmem_cols_for(p.BN);
+    p.flags = flags;
+    p.c = (__nv_bfloat16*)c_planes; p.ldc = ldc; p.c_plane = c_plane;
+    p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
+    p.mask = (const __nv_bfloat16*)mask_hi; p.ldmask = ldmask;
+    p.c32 = c_f32; p.ldc32 = ldc32;
+    const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)p.BN * 256u;
+    p.stages = (int)((220 * 1024) / stage_bytes);
+    if (p.stages > 6) p.stages = 6;
+    if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    CUtensorMap ta, tb;
+    if (int rc = make_map(&ta, a_planes, M, K, lda, a_plane, UM)) return rc;
+    if (int rc = make_map(&tb, b_planes, N, K, ldb, b_plane, p.BN)) return rc;
+    AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
+    umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, p);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const int bn = pick_bn(N);
+    const int64_t tiles = ceil_div(M, UM) * ceil_div(N, bn);
+    int64_t splits = ceil_div(2 * 148, tiles);
+    const int64_t max_by_k = ceil_div(K, 1024);
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits < 1) splits = 1;
+    return splits * M * N * (int64_t)sizeof(float);
+}
+
+// C[M,N] (+)= sum_k A[k,M] * B[k,N] on plane pairs stored [K, M] and [K, N] (both MN-major); fp32 output,
+// deterministic split-K over k (the sample points).
+AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
+                             const void* b_planes, int64_t ldb, int64_t b_plane, float* c, int64_t ldc, int accumulate,
+                             void* workspace, int64_t workspace_bytes, int device, void* stream) {
+    AVR_REQUIRE(a_planes && b_planes && c && workspace, "null pointer");
+    AVR_REQUIRE(M > 0 && N > 0 && K >= 0, "bad dimensions");
+    AVR_REQUIRE(M % 8 == 0 && N % 8 == 0, "M and N must be multiples of 8");
+    AVR_REQUIRE(K < (1ll << 31), "dimension overflow");
+    AVR_ENTER(device);
+    UmmaParams p = {};
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.BN = pick_bn(N);
+    p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
+    const int64_t need = avr_umma_gemm_tn_workspace_bytes(M, N, K);
+    AVR_REQUIRE(workspace_bytes >= need && aligned16(workspace), "workspace too small or misaligned");
+    int64_t splits = need / (M * N * (int64_t)sizeof(float));
+    if (splits < 1) splits = 1;
+    p.k_per_split = (int)(ceil_div(ceil_div(K, splits), UBK) * UBK);
+    if (p.k_per_split < UBK) p.k_per_split = UBK;
+    p.k_splits = (int)(K > 0 ? ceil_div(K, p.k_per_split) : 1);
+    p.tmem_cols = tmem_cols_for(p.BN);
+    p.c32 = (float*)workspace;
+    const int bn_rows = (p.BN + 63) / 64 * 64;
+    const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)bn_rows * 256u;
+    p.stages = (int)((220 * 1024) / stage_bytes);
+    if (p.stages > 6) p.stages = 6;
+    if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K > 0) {
+        CUtensorMap ta, tb;
+        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64)) return rc;
+        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64)) return rc;
+        AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
+        const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
+        umma_gemm_kernel<true><<<grid, UTHREADS, smem, st>>>(ta, tb, p);
+        AVR_LAUNCH_CHECK();
+    } else {
+        p.k_splits = 0;
+    }
+    umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>((const float*)workspace, p.k_splits, M, N, c,
+                                                                            ldc, accumulate);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+}  // extern "C"

@@ -292,3 +292,91 @@ def spectrum_bwd(g, d_out, tables):
     _lib.check(_lib.load().avr_spectrum_bwd(C.byref(g), _p(_dense(d_out)), _p(tables["gain"]), _p(tables["phase"]),
                                             _p(tables["dft"]), ldd, _p(xbuf), _p(d_y), dev, st), "avr_spectrum_bwd")
     return d_y
+
+
+# ---- tensor-core dense layers on bf16 plane pairs ------------------------------------------------------
+from ._lib import UMMA_ACCUM, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU  # noqa: E402,F401
+
+
+class PlanePair:
+    """x = hi + lo stored as a bf16 buffer ``[2, rows, ld]``; optionally a column window of it."""
+
+    __slots__ = ("buf", "rows", "ld", "col0", "cols")
+
+    def __init__(self, buf, col0=0, cols=None):
+        assert buf.dtype == torch.bfloat16 and buf.dim() == 3 and buf.shape[0] == 2 and buf.is_contiguous()
+        self.buf, self.rows, self.ld = buf, buf.shape[1], buf.shape[2]
+        self.col0 = col0
+        self.cols = self.ld - col0 if cols is None else cols
+        assert col0 % 8 == 0 and self.ld % 8 == 0, "plane windows must stay 16-byte aligned"
+
+    @staticmethod
+    def empty(rows, cols, device, ld=None):
+        ld = cols if ld is None else ld
+        ld = (ld + 7) // 8 * 8
+        return PlanePair(torch.empty(2, rows, ld, dtype=torch.bfloat16, device=device), 0, cols)
+
+    def window(self, col0, cols):
+        return PlanePair(self.buf, self.col0 + col0, cols)
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + 2 * self.col0)
+
+    @property
+    def plane(self):
+        return self.rows * self.ld
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
+def planes_split(x, out: PlanePair, transpose=False, relu=False):
+    """fp32 ``x[rows, cols]`` (row stride ``x.stride(0)``) -> plane pair (``out[c, r]`` when ``transpose``)."""
+    dev, st = _ctx(x)
+    rows, cols = x.shape
+    assert x.stride(1) == 1
+    _lib.check(_lib.load().avr_planes_split(_p(x), rows, cols, x.stride(0), out.ptr, out.ld, out.plane,
+                                            1 if transpose else 0, 1 if relu else 0, dev, st), "avr_planes_split")
+    return out
+
+
+def planes_merge(pp: PlanePair):
+    dev, st = _ctx(pp.buf)
+    out = torch.empty(pp.rows, pp.cols, device=pp.device)
+    _lib.check(_lib.load().avr_planes_merge(pp.ptr, pp.rows, pp.cols, pp.ld, pp.plane, _p(out), pp.cols, dev, st),
+               "avr_planes_merge")
+    return out
+
+
+def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask: PlanePair = None,
+            c_f32=None):
+    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane pair or (UMMA_OUT_F32) an fp32 tensor."""
+    dev, st = _ctx(a.buf)
+    M, K, N = a.rows, a.cols, b.rows
+    assert b.cols == K, (b.cols, K)
+    none = C.c_void_p(None)
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
+        _lib.check(_lib.load().avr_umma_gemm_nt(
+            M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, flags,
+            c.ptr if c is not None else none, c.ld if c is not None else 0, c.plane if c is not None else 0,
+            c2.ptr if c2 is not None else none, c2.ld if c2 is not None else 0, c2.plane if c2 is not None else 0,
+            mask.ptr if mask is not None else none, mask.ld if mask is not None else 0,
+            _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0, dev, st), "avr_umma_gemm_nt")
+
+
+def umma_tn_workspace_bytes(M, N, K) -> int:
+    return int(_lib.load().avr_umma_gemm_tn_workspace_bytes(M, N, K))
+
+
+def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
+    """C[M,N] (+)= sum_k A[k,M] B[k,N]  (A, B plane pairs over the same rows k); fp32 C (may be a column view)."""
+    dev, st = _ctx(a.buf)
+    K, M, N = a.rows, a.cols, b.cols
+    assert b.rows == K
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
+        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, _p(c_f32),
+                                                c_f32.stride(0), 1 if accumulate else 0,
+                                                C.c_void_p(workspace.data_ptr()),
+                                                workspace.numel() * workspace.element_size(), dev, st), "avr_umma_gemm_tn")

@@ -139,6 +139,36 @@ AVR_API int avr_gemm(int layout_a, int layout_b, int64_t M, int64_t N, int64_t K
              const float* B, int64_t ldb, float* C, int64_t ldc, int flags, const float* aux, int64_t ldaux,
              void* workspace, int64_t workspace_bytes, int device, void* stream);
 
+/* ---- dense layers on the tensor cores (tcgen05.mma / TMEM / TMA), fp32-grade accuracy ----------------
+ * Operands are error-compensated PAIRS of bf16 planes, x = hi + lo (hi = bf16(x), lo = bf16(x - hi)): a
+ * "plane pair" is a bf16 buffer [2][rows][ld] addressed by (base, ld, plane_stride), all in elements, with
+ * 16-byte aligned base / row pitch / plane pitch.  Products are evaluated as hi*hi + hi*lo + lo*hi in one
+ * fp32 TMEM accumulator (relative error ~2^-17 per product). */
+enum {
+    AVR_UMMA_RELU = 1,        /* out = max(out, 0)                                                   */
+    AVR_UMMA_ACCUM = 2,       /* out += previous contents of the output                              */
+    AVR_UMMA_MASK = 4,        /* product *= (mask_hi[i,j] > 0)   (ReLU backward; before ACCUM)       */
+    AVR_UMMA_OUT_F32 = 8,     /* write fp32 c_f32 instead of a plane pair                            */
+    AVR_UMMA_DUAL_RELU = 16   /* additionally write max(out,0) as a second plane pair (c2)           */
+};
+/* fp32 [rows, cols] (ld) <-> plane pair; transpose != 0 writes planes[c, r] = x[r, c]; relu != 0 clamps */
+AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
+                             int64_t plane_stride, int transpose, int relu, int device, void* stream);
+AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride,
+                             float* out, int64_t ld, int device, void* stream);
+/* C[M,N] = A[M,K] . B[N,K]^T   (A, B plane pairs with the reduction index contiguous; N % 8 == 0).
+ * Forward layers (B = W[out,in]) and backward-data (B = transposed weight planes W^T[in,out]). */
+AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
+                             const void* b_planes, int64_t ldb, int64_t b_plane, int flags, void* c_planes, int64_t ldc,
+                             int64_t c_plane, void* c2_planes, int64_t ldc2, int64_t c2_plane, const void* mask_hi,
+                             int64_t ldmask, float* c_f32, int64_t ldc32, int device, void* stream);
+/* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane pairs; weight gradients).
+ * fp32 output; deterministic split-K over the points through `workspace`. */
+AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
+AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
+                             const void* b_planes, int64_t ldb, int64_t b_plane, float* c, int64_t ldc, int accumulate,
+                             void* workspace, int64_t workspace_bytes, int device, void* stream);
+
 /* ---- broadcast inputs of the signal network (renderer.py:59-60; model.py:219-221) ------------
  * dst[n, col0:col0+w] = src[row(n), 0:w] with row(n) = r (per_receiver=0) or b (per_receiver=1). */
 AVR_API int avr_rows_broadcast(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,

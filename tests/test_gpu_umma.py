@@ -1,0 +1,82 @@
+"""tcgen05 / TMEM / TMA dense layers (3 x bf16 error-compensated products) against float64."""
+import pytest
+import torch
+
+from avr_b200 import ops
+from avr_b200.ops import PlanePair
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 2e-5        # ~2^-17 per product, random signs
+
+
+def _pp(x, ld=None):
+    out = PlanePair.empty(x.shape[0], x.shape[1], DEV, ld)
+    return ops.planes_split(x.to(DEV).contiguous(), out)
+
+
+def test_planes_roundtrip(built_library):
+    x = torch.randn(300, 72, generator=torch.Generator().manual_seed(0)) * 3
+    pp = _pp(x, ld=80)
+    back = ops.planes_merge(pp).cpu()
+    assert float((back - x).abs().max() / x.abs().max()) < 2 ** -16
+    t = PlanePair.empty(72, 300, DEV, 304)
+    ops.planes_split(x.to(DEV), t, transpose=True, relu=True)
+    assert rel_l2(ops.planes_merge(t), x.clamp_min(0).t()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 128, 48), (4099, 512, 512), (300, 16, 128), (777, 208, 128),
+                                   (513, 48, 128), (2050, 1600, 512), (256, 80, 208), (130, 512, 208)])
+def test_umma_nt_plain(built_library, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    a, b = _pp(A), _pp(B)
+    c = PlanePair.empty(M, N, DEV)
+    ops.umma_nt(a, b, 0, c)
+    ref = A.double() @ B.double().t()
+    assert rel_l2(ops.planes_merge(c), ref) < TOL
+    c32 = torch.empty(M, N, device=DEV)
+    ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c32)
+    assert rel_l2(c32, ref) < TOL
+
+
+def test_umma_nt_epilogues(built_library):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 1500, 256, 128
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    act, old = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
+    a, b, mask = _pp(A), _pp(B), _pp(act)
+    ref = A.double() @ B.double().t()
+    c = PlanePair.empty(M, N, DEV)
+    ops.umma_nt(a, b, ops.UMMA_RELU, c)
+    assert rel_l2(ops.planes_merge(c), ref.clamp_min(0)) < TOL
+    c, c2 = PlanePair.empty(M, N, DEV), PlanePair.empty(M, N, DEV)
+    ops.umma_nt(a, b, ops.UMMA_DUAL_RELU, c, c2)
+    assert rel_l2(ops.planes_merge(c), ref) < TOL and rel_l2(ops.planes_merge(c2), ref.clamp_min(0)) < TOL
+    c = _pp(old)
+    ops.umma_nt(a, b, ops.UMMA_MASK | ops.UMMA_ACCUM, c, mask=mask)
+    assert rel_l2(ops.planes_merge(c), ref * (act > 0) + old.double()) < TOL
+    # column windows of wider buffers (how concatenated network inputs are addressed)
+    wide = PlanePair.empty(M, 416, DEV)
+    wide.buf.zero_()
+    ops.umma_nt(a, b, 0, wide.window(128, N))
+    m = ops.planes_merge(wide)
+    assert rel_l2(m[:, 128:128 + N], ref) < TOL and float(m[:, :128].abs().max()) == 0 and float(m[:, 384:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (512, 512, 20000), (16, 128, 5000), (128, 48, 3001), (512, 208, 7777),
+                                   (1600, 512, 4100), (128, 80, 64)])
+def test_umma_tn_weight_grad(built_library, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    dY, X = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    a, b = _pp(dY), _pp(X)
+    ws = torch.empty(max(4, ops.umma_tn_workspace_bytes(M, N, K) // 4), device=DEV)
+    outs = []
+    for _ in range(2):
+        c = torch.zeros(M, N + 8, device=DEV)
+        ops.umma_tn(a, b, c[:, :N], ws)
+        outs.append(c.cpu())
+    assert torch.equal(outs[0], outs[1])                     # deterministic split-K
+    assert rel_l2(outs[0][:, :N], dY.double().t() @ X.double()) < TOL
+    assert float(outs[0][:, N:].abs().max()) == 0
