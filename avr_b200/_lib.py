@@ -44,25 +44,32 @@ SIGNATURES = {
     "avr_launch_count": (_I64, [C.c_int]),
     "avr_sample_points": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_aux_inputs": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
-    "avr_raygen_encode_fwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, C.c_int, _P]),
-    "avr_raygen_encode_bwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _I64, _I32, _P, _I32, _P, C.c_int, _P]),
-    "avr_grid_encode_fwd": (C.c_int, [_M, _P, _I64, _P, _P, _I64, _I32, _I32, C.c_int, _P]),
-    "avr_grid_encode_bwd": (C.c_int, [_M, _P, _I64, _P, _I64, _I32, _P, _I32, _P, C.c_int, _P]),
-    "avr_absmax_bits": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, C.c_int, _P]),
+    "avr_raygen_encode_fwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, C.c_int, _P]),
+    "avr_raygen_encode_bwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _I64, _I64, _I32, _P, _I32, _P, C.c_int, _P]),
+    "avr_grid_encode_fwd": (C.c_int, [_M, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _I32, C.c_int, _P]),
+    "avr_grid_encode_bwd": (C.c_int, [_M, _P, _I64, _P, _I64, _I64, _I32, _P, _I32, _P, C.c_int, _P]),
+    "avr_absmax_bits": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _P, C.c_int, _P]),
     "avr_grid_grad_finalize": (C.c_int, [_P, _I64, _P, _I32, _P, C.c_int, C.c_int, _P]),
     "avr_gemm_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "avr_gemm": (C.c_int, [C.c_int, C.c_int, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, C.c_int, _P, _I64,
                            _P, _I64, C.c_int, _P]),
-    "avr_planes_split": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, C.c_int, C.c_int, C.c_int, _P]),
-    "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, _P, _I64, C.c_int, _P]),
-    "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, _P, _I64,
-                                   _I64, _P, _I64, _P, _I64, C.c_int, _P]),
+    "avr_planes_split": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P]),
+    "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.c_int, _P, _I64,
+                                   _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_tn_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P, _I64,
                                    C.c_int, _P]),
-    "avr_rows_broadcast": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I64, _I32, C.c_int, _P]),
+    "avr_delay_sort": (C.c_int, [_G, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "avr_collapse_fwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, C.c_int, _P]),
+    "avr_collapse_bwd_data": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _P,
+                                        C.c_int, _P]),
+    "avr_collapse_bwd_weight_workspace_bytes": (_I64, [_G, _I32, _I32]),
+    "avr_collapse_bwd_weight": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _I64, C.c_int, _I32, _P, _I64,
+                                          C.c_int, _P]),
+    "avr_rows_broadcast": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I64, _I64, _I32, _I32, C.c_int, _P]),
     "avr_rows_reduce_workspace_bytes": (_I64, [_G, _I32, C.c_int]),
-    "avr_rows_reduce": (C.c_int, [_G, _P, _I64, _I32, _I32, C.c_int, _P, _P, _I64, C.c_int, _P]),
+    "avr_rows_reduce": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "avr_ray_weights_fwd": (C.c_int, [_G, _P, _I64, _P, _F, _P, _P, C.c_int, _P]),
     "avr_ray_weights_bwd": (C.c_int, [_G, _P, _I64, _P, _F, _P, _P, _I64, C.c_int, _P]),
     "avr_composite_workspace_bytes": (_I64, [_G]),

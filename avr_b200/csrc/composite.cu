@@ -5,6 +5,7 @@
 // linear in the signal and the phase / path loss depend only on the sample index s, so the ray sum is
 // taken in the time domain first (SURVEY App. A "reordered"): the [ray, sample, freq] tensor of the
 // reference never exists, `sig` is streamed exactly once, and only bs*S rows reach the DFT.
+#include <cuda_bf16.h>
 #include <math.h>
 #include "common.cuh"
 
@@ -295,20 +296,32 @@ __global__ void phase_bwd_kernel(const float* __restrict__ d_out, const float* _
 // broadcast rows into / reduce rows out of the signal-network input buffer
 // ------------------------------------------------------------------------------------------------
 __global__ void rows_broadcast_kernel(const Geom geo, const float* __restrict__ src, int w, int per_receiver,
-                                      float* __restrict__ dst, int64_t ld_dst, int col0) {
+                                      void* __restrict__ dst_v, int64_t ld_dst, int64_t dst_plane, int dst_np, int col0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_pts = (int64_t)geo.bs * geo.R * geo.S;
     if (i >= n_pts * w) return;
     const int64_t n = i / w;
     const int c = (int)(i - n * w);
     const int64_t row = per_receiver ? n / ((int64_t)geo.R * geo.S) : (n / geo.S) % geo.R;
-    dst[n * ld_dst + col0 + c] = __ldg(src + row * w + c);
+    const float v = __ldg(src + row * w + c);
+    const int64_t o = n * ld_dst + col0 + c;
+    if (dst_plane == 0) {
+        reinterpret_cast<float*>(dst_v)[o] = v;
+    } else {
+        __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(dst_v);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        db[o] = hi;
+        db[o + dst_plane] = mid;
+        if (dst_np == 3) db[o + 2 * dst_plane] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    }
 }
 
 // stage 1: partial[row, chunk, c] = sum over the chunk's contributing points (fixed order)
 __global__ void __launch_bounds__(256)
-rows_reduce_kernel(const Geom geo, const float* __restrict__ d_dst, int64_t ld_dst, int col0, int w, int per_receiver,
-                   int items_per_chunk, float* __restrict__ partial) {
+rows_reduce_kernel(const Geom geo, const void* __restrict__ d_dst_v, int64_t ld_dst, int64_t d_plane, int col0, int w,
+                   int per_receiver, int items_per_chunk, float* __restrict__ partial) {
     __shared__ float red[8][33];
     const int row = blockIdx.x, chunk = blockIdx.y;
     const int lane = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -323,7 +336,12 @@ rows_reduce_kernel(const Geom geo, const float* __restrict__ d_dst, int64_t ld_d
                 int64_t n;
                 if (per_receiver) n = (int64_t)row * geo.R * geo.S + j;
                 else { const int64_t b = j / geo.S, s = j - b * geo.S; n = (b * geo.R + row) * geo.S + s; }
-                acc += __ldg(d_dst + n * ld_dst + col0 + c);
+                const int64_t o = n * ld_dst + col0 + c;
+                if (d_plane == 0) acc += __ldg(reinterpret_cast<const float*>(d_dst_v) + o);
+                else {
+                    const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(d_dst_v);
+                    acc += __bfloat162float(db[o]) + __bfloat162float(db[o + d_plane]);
+                }
             }
         }
         red[y][lane] = acc;
@@ -505,7 +523,8 @@ extern "C" int avr_spectrum_bwd(const avr_render_geom* geom, const float* d_out,
 }
 
 extern "C" int avr_rows_broadcast(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,
-                                  float* dst, int64_t ld_dst, int32_t col0, int device, void* stream) {
+                                  void* dst, int64_t ld_dst, int64_t dst_plane, int32_t dst_nplanes, int32_t col0, int device,
+                                  void* stream) {
     AVR_REQUIRE(geom && src && dst, "null pointer");
     AVR_REQUIRE(w > 0 && col0 >= 0 && ld_dst >= col0 + w, "bad column window");
     AVR_ENTER(device);
@@ -513,7 +532,7 @@ extern "C" int avr_rows_broadcast(const avr_render_geom* geom, const float* src,
     const int64_t total = (int64_t)geo.bs * geo.R * geo.S * w;
     if (total == 0) return AVR_OK;
     rows_broadcast_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(geo, src, w, per_receiver, dst,
-                                                                                         ld_dst, col0);
+                                                                                         ld_dst, dst_plane, dst_nplanes, col0);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
@@ -527,9 +546,9 @@ extern "C" int64_t avr_rows_reduce_workspace_bytes(const avr_render_geom* geom, 
     return rows * chunks * (int64_t)w * (int64_t)sizeof(float);
 }
 
-extern "C" int avr_rows_reduce(const avr_render_geom* geom, const float* d_dst, int64_t ld_dst, int32_t col0, int32_t w,
-                               int per_receiver, float* d_src, float* workspace, int64_t workspace_bytes, int device,
-                               void* stream) {
+extern "C" int avr_rows_reduce(const avr_render_geom* geom, const void* d_dst, int64_t ld_dst, int64_t d_plane,
+                               int32_t col0, int32_t w, int per_receiver, float* d_src, float* workspace,
+                               int64_t workspace_bytes, int device, void* stream) {
     AVR_REQUIRE(geom && d_dst && d_src && workspace, "null pointer");
     AVR_REQUIRE(w > 0 && col0 >= 0 && ld_dst >= col0 + w, "bad column window");
     AVR_REQUIRE(workspace_bytes >= avr_rows_reduce_workspace_bytes(geom, w, per_receiver), "workspace too small");
@@ -541,8 +560,8 @@ extern "C" int avr_rows_reduce(const avr_render_geom* geom, const float* d_dst, 
     const int chunks = rows_reduce_plan(geo, per_receiver, &ipc);
     AVR_REQUIRE(chunks <= 65535, "too many reduce chunks");
     cudaStream_t st = (cudaStream_t)stream;
-    rows_reduce_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, st>>>(geo, d_dst, ld_dst, col0, w, per_receiver, ipc,
-                                                                             workspace);
+    rows_reduce_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, st>>>(geo, d_dst, ld_dst, d_plane, col0, w,
+                                                                             per_receiver, ipc, workspace);
     AVR_LAUNCH_CHECK();
     rows_reduce_final_kernel<<<(unsigned)ceil_div((int64_t)rows * w, 256), 256, 0, st>>>(workspace, rows, chunks, w, d_src);
     AVR_LAUNCH_CHECK();

@@ -8,6 +8,7 @@
 // written as contiguous rows.  The backward recomputes the sample positions (nothing is saved) and
 // accumulates 2^e-scaled int64 contributions with red.global.add.u64 -- integer addition is
 // associative, so the result is bit-identical from run to run regardless of scheduling.
+#include <cuda_bf16.h>
 #include <math.h>
 #include "common.cuh"
 
@@ -137,8 +138,8 @@ template <bool RAYGEN>
 __global__ void __launch_bounds__(ENC_PTS* ENC_LG)
 encode_fwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t n_pts, const float* __restrict__ rays_o,
                   const float* __restrict__ pos_tx, const float* __restrict__ dirs, const float* __restrict__ d_vals,
-                  const float* __restrict__ u_in, const float2* __restrict__ table, float* __restrict__ out,
-                  int64_t ld_out, int col0, int n_ones, int* __restrict__ delay) {
+                  const float* __restrict__ u_in, const float2* __restrict__ table, void* __restrict__ out_v,
+                  int64_t ld_out, int64_t out_plane, int out_np, int col0, int n_ones, int* __restrict__ delay) {
     extern __shared__ float tile[];
     const int W = 2 * grid.n_levels + n_ones;
     const int Wp = W | 1;                                   // odd stride: conflict-free column writes
@@ -172,7 +173,20 @@ encode_fwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
     const int64_t n0 = (int64_t)blockIdx.x * ENC_PTS;
     for (int idx = tid; idx < ENC_PTS * W; idx += ENC_PTS * ENC_LG) {
         const int pp = idx / W, c = idx - pp * W;
-        if (n0 + pp < n_pts) out[(n0 + pp) * ld_out + col0 + c] = tile[pp * Wp + c];
+        if (n0 + pp >= n_pts) continue;
+        const float v = tile[pp * Wp + c];
+        const int64_t o = (n0 + pp) * ld_out + col0 + c;
+        if (out_plane == 0) {
+            reinterpret_cast<float*>(out_v)[o] = v;
+        } else {                                            // error-compensated bf16 plane pair (tensor-core operand)
+            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_v);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(hi);
+            const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+            ob[o] = hi;
+            ob[o + out_plane] = mid;
+            if (out_np == 3) ob[o + 2 * out_plane] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        }
     }
 }
 
@@ -180,8 +194,8 @@ template <bool RAYGEN>
 __global__ void __launch_bounds__(ENC_PTS* ENC_LG)
 encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t n_pts, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ d_vals, const float* __restrict__ u_in,
-                  const float* __restrict__ d_out, int64_t ld_out, int col0, const uint32_t* __restrict__ gmax_bits,
-                  int headroom, unsigned long long* __restrict__ acc) {
+                  const void* __restrict__ d_out_v, int64_t ld_out, int64_t d_plane, int col0,
+                  const uint32_t* __restrict__ gmax_bits, int headroom, unsigned long long* __restrict__ acc) {
     extern __shared__ float tile[];
     bool ok, poisoned;
     const int e = fixed_exponent(__ldg(gmax_bits), headroom, ok, poisoned);
@@ -194,7 +208,16 @@ encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
     const int64_t n0 = (int64_t)blockIdx.x * ENC_PTS;
     for (int idx = tid; idx < ENC_PTS * W; idx += ENC_PTS * ENC_LG) {
         const int pp = idx / W, c = idx - pp * W;
-        tile[pp * Wp + c] = (n0 + pp < n_pts) ? __ldg(d_out + (n0 + pp) * ld_out + col0 + c) : 0.f;
+        float v = 0.f;
+        if (n0 + pp < n_pts) {
+            const int64_t o = (n0 + pp) * ld_out + col0 + c;
+            if (d_plane == 0) v = __ldg(reinterpret_cast<const float*>(d_out_v) + o);
+            else {
+                const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(d_out_v);
+                v = __bfloat162float(db[o]) + __bfloat162float(db[o + d_plane]);
+            }
+        }
+        tile[pp * Wp + c] = v;
     }
     __syncthreads();
     const int64_t n = n0 + p;
@@ -213,14 +236,20 @@ encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
     }
 }
 
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t rows, int64_t ld, int col0, int ncols,
+__global__ void absmax_kernel(const void* __restrict__ x_v, int64_t rows, int64_t ld, int64_t plane, int col0, int ncols,
                               uint32_t* __restrict__ gmax_bits) {
     uint32_t m = 0;
     const int64_t total = rows * ncols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / ncols;
         const int c = (int)(i - r * ncols);
-        m = max(m, __float_as_uint(fabsf(__ldg(x + r * ld + col0 + c))));   // |x| bit patterns order like values; NaN sorts last
+        float v;
+        if (plane == 0) v = __ldg(reinterpret_cast<const float*>(x_v) + r * ld + col0 + c);
+        else {
+            const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x_v);
+            v = __bfloat162float(xb[r * ld + col0 + c]) + __bfloat162float(xb[r * ld + col0 + c + plane]);
+        }
+        m = max(m, __float_as_uint(fabsf(v)));   // |x| bit patterns order like values; NaN sorts last
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -312,10 +341,11 @@ extern "C" int avr_aux_inputs(const avr_render_geom* geom, const float* pos_tx, 
 
 static int encode_fwd_common(bool raygen, const Geom& geo, const avr_grid_meta* grid, int64_t n_pts, const float* rays_o,
                              const float* pos_tx, const float* dirs, const float* d_vals, const float* u,
-                             const float* table, float* out, int64_t ld_out, int32_t col0, int32_t n_ones,
-                             int32_t* delay, void* stream) {
+                             const float* table, void* out, int64_t ld_out, int64_t out_plane, int out_np,
+                             int32_t col0, int32_t n_ones, int32_t* delay, void* stream) {
     if (int rc = check_grid(grid)) return rc;
     AVR_REQUIRE(table && out, "null table/out");
+    AVR_REQUIRE(out_plane == 0 || out_np == 2 || out_np == 3, "plane count must be 2 or 3");
     AVR_REQUIRE(n_ones >= 0 && col0 >= 0 && ld_out >= col0 + 2 * grid->n_levels + n_ones, "bad output window");
     AVR_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7u) == 0, "table must be 8-byte aligned");
     if (n_pts == 0) return AVR_OK;
@@ -327,11 +357,13 @@ static int encode_fwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
     if (raygen) {
         AVR_CUDA(cudaFuncSetAttribute(encode_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_fwd_kernel<true><<<blocks, block, smem, (cudaStream_t)stream>>>(
-            geo, gd, n_pts, rays_o, pos_tx, dirs, d_vals, nullptr, (const float2*)table, out, ld_out, col0, n_ones, delay);
+            geo, gd, n_pts, rays_o, pos_tx, dirs, d_vals, nullptr, (const float2*)table, out, ld_out, out_plane, out_np, col0,
+            n_ones, delay);
     } else {
         AVR_CUDA(cudaFuncSetAttribute(encode_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_fwd_kernel<false><<<blocks, block, smem, (cudaStream_t)stream>>>(
-            geo, gd, n_pts, nullptr, nullptr, nullptr, nullptr, u, (const float2*)table, out, ld_out, col0, n_ones, nullptr);
+            geo, gd, n_pts, nullptr, nullptr, nullptr, nullptr, u, (const float2*)table, out, ld_out, out_plane, out_np, col0,
+            n_ones, nullptr);
     }
     AVR_LAUNCH_CHECK();
     return AVR_OK;
@@ -339,28 +371,30 @@ static int encode_fwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
 
 extern "C" int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
                                      const float* pos_tx, const float* dirs, const float* d_vals, const float* table,
-                                     float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int32_t* delay,
-                                     int device, void* stream) {
+                                     void* out, int64_t ld_out, int64_t out_plane, int32_t out_nplanes, int32_t col0,
+                                     int32_t n_ones, int32_t* delay, int device, void* stream) {
     AVR_REQUIRE(geom && rays_o && dirs && d_vals, "null input");
     AVR_REQUIRE(delay == nullptr || pos_tx != nullptr, "delay requested without pos_tx");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     return encode_fwd_common(true, geo, grid, (int64_t)geo.bs * geo.R * geo.S, rays_o, pos_tx, dirs, d_vals, nullptr,
-                             table, out, ld_out, col0, n_ones, delay, stream);
+                             table, out, ld_out, out_plane, out_nplanes, col0, n_ones, delay, stream);
 }
 
 extern "C" int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* table,
-                                   float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int device, void* stream) {
+                                   void* out, int64_t ld_out, int64_t out_plane, int32_t out_nplanes, int32_t col0,
+                                   int32_t n_ones, int device, void* stream) {
     AVR_REQUIRE(u != nullptr || n_pts == 0, "null input");
     AVR_ENTER(device);
     Geom geo = {};
-    return encode_fwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, nullptr, u, table, out, ld_out, col0,
-                             n_ones, nullptr, stream);
+    return encode_fwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, nullptr, u, table, out, ld_out, out_plane,
+                             out_nplanes, col0, n_ones, nullptr, stream);
 }
 
 static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* grid, int64_t n_pts, const float* rays_o,
-                             const float* dirs, const float* d_vals, const float* u, const float* d_out, int64_t ld_out,
-                             int32_t col0, const uint32_t* gmax_bits, int32_t headroom, int64_t* acc, void* stream) {
+                             const float* dirs, const float* d_vals, const float* u, const void* d_out, int64_t ld_out,
+                             int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t headroom, int64_t* acc,
+                             void* stream) {
     if (int rc = check_grid(grid)) return rc;
     AVR_REQUIRE(d_out && gmax_bits && acc, "null d_out/gmax/acc");
     AVR_REQUIRE(col0 >= 0 && ld_out >= col0 + 2 * grid->n_levels, "bad gradient window");
@@ -374,12 +408,12 @@ static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
     if (raygen) {
         AVR_CUDA(cudaFuncSetAttribute(encode_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_bwd_kernel<true><<<blocks, block, smem, (cudaStream_t)stream>>>(
-            geo, gd, n_pts, rays_o, dirs, d_vals, nullptr, d_out, ld_out, col0, gmax_bits, headroom,
+            geo, gd, n_pts, rays_o, dirs, d_vals, nullptr, d_out, ld_out, d_plane, col0, gmax_bits, headroom,
             (unsigned long long*)acc);
     } else {
         AVR_CUDA(cudaFuncSetAttribute(encode_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_bwd_kernel<false><<<blocks, block, smem, (cudaStream_t)stream>>>(
-            geo, gd, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, col0, gmax_bits, headroom,
+            geo, gd, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, d_plane, col0, gmax_bits, headroom,
             (unsigned long long*)acc);
     }
     AVR_LAUNCH_CHECK();
@@ -387,27 +421,27 @@ static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
 }
 
 extern "C" int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
-                                     const float* dirs, const float* d_vals, const float* d_out, int64_t ld_out,
-                                     int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, int64_t* acc,
-                                     int device, void* stream) {
+                                     const float* dirs, const float* d_vals, const void* d_out, int64_t ld_out,
+                                     int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
+                                     int64_t* acc, int device, void* stream) {
     AVR_REQUIRE(geom && rays_o && dirs && d_vals, "null input");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     return encode_bwd_common(true, geo, grid, (int64_t)geo.bs * geo.R * geo.S, rays_o, dirs, d_vals, nullptr, d_out,
-                             ld_out, col0, gmax_bits, log2_headroom, acc, stream);
+                             ld_out, d_plane, col0, gmax_bits, log2_headroom, acc, stream);
 }
 
-extern "C" int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* d_out,
-                                   int64_t ld_out, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
-                                   int64_t* acc, int device, void* stream) {
+extern "C" int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const void* d_out,
+                                   int64_t ld_out, int64_t d_plane, int32_t col0, const uint32_t* gmax_bits,
+                                   int32_t log2_headroom, int64_t* acc, int device, void* stream) {
     AVR_REQUIRE(u != nullptr || n_pts == 0, "null input");
     AVR_ENTER(device);
     Geom geo = {};
-    return encode_bwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, col0, gmax_bits,
-                             log2_headroom, acc, stream);
+    return encode_bwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, d_plane, col0,
+                             gmax_bits, log2_headroom, acc, stream);
 }
 
-extern "C" int avr_absmax_bits(const float* x, int64_t rows, int64_t ld, int32_t col0, int32_t ncols,
+extern "C" int avr_absmax_bits(const void* x, int64_t rows, int64_t ld, int64_t plane, int32_t col0, int32_t ncols,
                                uint32_t* gmax_bits, int device, void* stream) {
     AVR_REQUIRE(gmax_bits, "null gmax_bits");
     AVR_REQUIRE(x != nullptr || rows == 0, "null input");
@@ -415,7 +449,7 @@ extern "C" int avr_absmax_bits(const float* x, int64_t rows, int64_t ld, int32_t
     if (rows * ncols == 0) return AVR_OK;
     int64_t blocks = ceil_div(rows * ncols, 256 * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    absmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, ld, col0, ncols, gmax_bits);
+    absmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, ld, plane, col0, ncols, gmax_bits);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

@@ -32,6 +32,7 @@ struct UmmaParams {
     int BN;                 // tile columns (multiple of 16, <= 256)
     int tiles_m, tiles_n, k_splits, k_per_split;
     int stages, tmem_cols;
+    int na, nb, nc;         // planes used of A / B (2: hi,mid  3: hi,mid,lo) and written to C
     int flags;
     __nv_bfloat16* c; long long ldc, c_plane;          // plane-pair output
     __nv_bfloat16* c2; long long ldc2, c2_plane;       // second (ReLU'd) plane-pair output
@@ -111,21 +112,23 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// store 8 consecutive values of one row as hi/lo planes (16 B each)
-__device__ __forceinline__ void store_planes8(__nv_bfloat16* base, long long plane, const float* v, bool relu) {
-    uint32_t h[4], l[4];
+// store 8 consecutive values of one row as 2 (hi,mid) or 3 (hi,mid,lo) bf16 planes, 16 B per plane
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* base, long long plane, const float* v, bool relu, int nplanes) {
+    uint32_t h[4], m[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float a = v[2 * i], b = v[2 * i + 1];
         if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        __nv_bfloat16 ah, al, bh, bl;
-        split_bf16(a, ah, al);
-        split_bf16(b, bh, bl);
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+        const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
         h[i] = pack2(ah, bh);
-        l[i] = pack2(al, bl);
+        m[i] = pack2(am, bm);
+        l[i] = pack2(__float2bfloat16_rn(ar - __bfloat162float(am)), __float2bfloat16_rn(br - __bfloat162float(bm)));
     }
     *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + plane) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(base + plane) = make_uint4(m[0], m[1], m[2], m[3]);
+    if (nplanes == 3) *reinterpret_cast<uint4*>(base + 2 * plane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -137,8 +140,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bn_rows = MN_MAJOR ? ((p.BN + 63) / 64) * 64 : p.BN;     // B rows (K-major) / MN extent (MN-major) in smem
     const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
-    const uint32_t b_tile_bytes = (uint32_t)bn_rows * 256u;
-    const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
+    const uint32_t a_tile_bytes = MN_MAJOR ? A_TILE_BYTES : (uint32_t)p.na * A_PLANE_BYTES;
+    const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)bn_rows * 256u : (uint32_t)p.nb * b_plane_bytes;
+    const uint32_t stage_bytes = a_tile_bytes + b_tile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.stages;
     const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16;
@@ -176,7 +180,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int k0 = k_beg; k0 < k_end; k0 += UBK) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
-                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_TILE_BYTES;
+                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_tile_bytes;
                     mbar_expect_tx(full, stage_bytes);
                     if (!MN_MAJOR) {
                         tma_load_3d(sa, &tmA, full, k0, m0, 0);
@@ -209,7 +213,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int k0 = k_beg; k0 < k_end; k0 += UBK) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + A_TILE_BYTES;
+                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_tile_bytes;
 #pragma unroll
                     for (int j = 0; j < UBK / 16; ++j) {
                         uint64_t a_hi, a_lo, b_hi, b_lo;
@@ -218,6 +222,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             a_lo = smem_desc(sa + A_PLANE_BYTES + 32 * j, 16, 1024);
                             b_hi = smem_desc(sb + 32 * j, 16, 1024);
                             b_lo = smem_desc(sb + b_plane_bytes + 32 * j, 16, 1024);
+                            if (p.na == 3 && p.nb == 3) {
+                                // 24-bit operands: six products, smallest first (fp32-grade pre-activations, so that
+                                // ReLU decisions agree with an fp32 evaluation)
+                                const uint64_t a_l3 = smem_desc(sa + 2 * A_PLANE_BYTES + 32 * j, 16, 1024);
+                                const uint64_t b_l3 = smem_desc(sb + 2 * b_plane_bytes + 32 * j, 16, 1024);
+                                umma_bf16(d_tmem, a_l3, b_hi, idesc, accumulate);
+                                umma_bf16(d_tmem, a_hi, b_l3, idesc, 1u);
+                                umma_bf16(d_tmem, a_lo, b_lo, idesc, 1u);
+                                accumulate = 1u;
+                            }
                         } else {
                             a_hi = smem_desc(sa + 2048 * j, 16384, 1024);
                             a_lo = smem_desc(sa + 8192 + 2048 * j, 16384, 1024);
@@ -284,15 +298,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     __nv_bfloat16* dst = p.c + row * p.ldc + col;
                     if (p.flags & UF_ACCUM) {
                         const uint4 oh = *reinterpret_cast<const uint4*>(dst), ol = *reinterpret_cast<const uint4*>(dst + p.c_plane);
+                        uint4 o3 = make_uint4(0u, 0u, 0u, 0u);
+                        if (p.nc == 3) o3 = *reinterpret_cast<const uint4*>(dst + 2 * p.c_plane);
                         const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
+                        const uint32_t tw[4] = {o3.x, o3.y, o3.z, o3.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            x[2 * i] += bf_lo(hw[i]) + bf_lo(lw[i]);
-                            x[2 * i + 1] += bf_hi(hw[i]) + bf_hi(lw[i]);
+                            x[2 * i] += bf_lo(hw[i]) + (bf_lo(lw[i]) + bf_lo(tw[i]));
+                            x[2 * i + 1] += bf_hi(hw[i]) + (bf_hi(lw[i]) + bf_hi(tw[i]));
                         }
                     }
-                    store_planes8(dst, p.c_plane, x, (p.flags & UF_RELU) != 0);
-                    if (p.flags & UF_DUAL_RELU) store_planes8(p.c2 + row * p.ldc2 + col, p.c2_plane, x, true);
+                    store_planes8(dst, p.c_plane, x, (p.flags & UF_RELU) != 0, p.nc);
+                    if (p.flags & UF_DUAL_RELU) store_planes8(p.c2 + row * p.ldc2 + col, p.c2_plane, x, true, p.nc);
                 }
             }
             tc_fence_before();
@@ -309,7 +326,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // fp32 [rows, cols] (ld) -> bf16 plane pair [2][rows][ldp]; optionally transposed (out[c][r] = in[r][c])
 __global__ void planes_split_kernel(const float* __restrict__ x, long long rows, long long cols, long long ld,
-                                    __nv_bfloat16* __restrict__ out, long long ldp, long long plane, int transpose, int relu) {
+                                    __nv_bfloat16* __restrict__ out, long long ldp, long long plane, int nplanes,
+                                    int transpose, int relu) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const long long r = i / cols, c = i - r * cols;
@@ -320,14 +338,17 @@ __global__ void planes_split_kernel(const float* __restrict__ x, long long rows,
     const long long o = transpose ? c * ldp + r : r * ldp + c;
     out[o] = hi;
     out[o + plane] = lo;
+    if (nplanes == 3) out[o + 2 * plane] = __float2bfloat16_rn((v - __bfloat162float(hi)) - __bfloat162float(lo));
 }
 
 __global__ void planes_merge_kernel(const __nv_bfloat16* __restrict__ in, long long rows, long long cols, long long ldp,
-                                    long long plane, float* __restrict__ out, long long ld) {
+                                    long long plane, int nplanes, float* __restrict__ out, long long ld) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const long long r = i / cols, c = i - r * cols;
-    out[r * ld + c] = __bfloat162float(in[r * ldp + c]) + __bfloat162float(in[r * ldp + c + plane]);
+    float tail = __bfloat162float(in[r * ldp + c + plane]);
+    if (nplanes == 3) tail += __bfloat162float(in[r * ldp + c + 2 * plane]);
+    out[r * ld + c] = __bfloat162float(in[r * ldp + c]) + tail;
 }
 
 // dW[m, n] (+)= sum over splits of partial[split][m][n]   (fixed order)
@@ -361,14 +382,14 @@ static EncodeTiledFn encode_fn() {
 
 // plane-pair tensor [2][rows][ld] of bf16, logical width `cols`; box = (64 cols, box_rows, 2 planes), 128B swizzle
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
-                    int box_rows) {
+                    int box_rows, int nplanes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(AVR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld * 2) % 16 || (plane * 2) % 16)
         return fail(AVR_ERR_INVALID, "plane tensors need 16-byte aligned base, row pitch and plane pitch");
-    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nplanes};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)nplanes};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -377,14 +398,14 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return AVR_OK;
 }
 
-static int pick_bn(long long N) {
-    if (N <= 256) return (int)(ceil_div(N, 16) * 16);
-    if (N % 256 == 0) return 256;
-    if (N % 128 == 0) return 128;
-    // e.g. 1600: prefer the multiple of 16 <= 256 that wastes least
-    int best = 256;
-    long long best_waste = ceil_div(N, 256) * 256 - N;
-    for (int bn = 240; bn >= 128; bn -= 16) {
+static int pick_bn(long long N, int max_bn = 256) {
+    if (N <= max_bn) return (int)(ceil_div(N, 16) * 16);
+    if (N % max_bn == 0) return max_bn;
+    if (max_bn == 256 && N % 128 == 0) return 128;
+    // e.g. 1600: prefer the multiple of 16 <= max_bn that wastes least
+    int best = max_bn;
+    long long best_waste = ceil_div(N, max_bn) * max_bn - N;
+    for (int bn = max_bn - 16; bn >= max_bn / 2; bn -= 16) {
         long long waste = ceil_div(N, bn) * bn - N;
         if (waste < best_waste) { best = bn; best_waste = waste; }
     }
@@ -411,33 +432,39 @@ extern "C" {
 
 // x fp32 [rows, cols] (ld) -> plane pair; transpose != 0 writes out[c, r]
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
-                             int64_t plane_stride, int transpose, int relu, int device, void* stream) {
+                             int64_t plane_stride, int nplanes, int transpose, int relu, int device, void* stream) {
     AVR_REQUIRE(planes && (x || rows * cols == 0), "null pointer");
+    AVR_REQUIRE(nplanes == 2 || nplanes == 3, "nplanes must be 2 or 3");
     AVR_ENTER(device);
     if (rows * cols == 0) return AVR_OK;
     planes_split_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, rows, cols, ld, (__nv_bfloat16*)planes, ldp, plane_stride, transpose, relu);
+        x, rows, cols, ld, (__nv_bfloat16*)planes, ldp, plane_stride, nplanes, transpose, relu);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
 
-AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride, float* out,
-                             int64_t ld, int device, void* stream) {
+AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride, int nplanes,
+                             float* out, int64_t ld, int device, void* stream) {
     AVR_REQUIRE(planes && out, "null pointer");
+    AVR_REQUIRE(nplanes == 2 || nplanes == 3, "nplanes must be 2 or 3");
     AVR_ENTER(device);
     if (rows * cols == 0) return AVR_OK;
     planes_merge_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)planes, rows, cols, ldp, plane_stride, out, ld);
+        (const __nv_bfloat16*)planes, rows, cols, ldp, plane_stride, nplanes, out, ld);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
 
 // C[M,N] = A[M,K] . B[N,K]^T on plane pairs (both K-major).  Output: plane pair (default) or fp32 (UF_OUT_F32).
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
-                             const void* b_planes, int64_t ldb, int64_t b_plane, int flags, void* c_planes, int64_t ldc,
-                             int64_t c_plane, void* c2_planes, int64_t ldc2, int64_t c2_plane, const void* mask_hi,
-                             int64_t ldmask, float* c_f32, int64_t ldc32, int device, void* stream) {
+                             int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
+                             void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
+                             int64_t c2_plane, const void* mask_hi, int64_t ldmask, float* c_f32, int64_t ldc32,
+                             int device, void* stream) {
     AVR_REQUIRE(a_planes && b_planes, "null operand");
+    AVR_REQUIRE((a_nplanes == 2 || a_nplanes == 3) && (b_nplanes == 2 || b_nplanes == 3) && (c_nplanes == 2 || c_nplanes == 3),
+                "plane counts must be 2 or 3");
+    if (!(a_nplanes == 3 && b_nplanes == 3)) a_nplanes = b_nplanes = 2;     // six products need 24 bits on both sides
     AVR_REQUIRE(M >= 0 && N > 0 && K > 0, "bad dimensions");
     AVR_REQUIRE(N % 8 == 0, "N must be a multiple of 8");
     AVR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension overflow");
@@ -449,7 +476,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     if (M == 0) return AVR_OK;
     UmmaParams p = {};
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.BN = pick_bn(N);
+    p.na = a_nplanes; p.nb = b_nplanes; p.nc = c_nplanes;
+    p.BN = pick_bn(N, a_nplanes == 3 ? 128 : 256);
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
     p.tmem_cols = tmem_cols_for(p.BN);
@@ -458,14 +486,14 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
     p.mask = (const __nv_bfloat16*)mask_hi; p.ldmask = ldmask;
     p.c32 = c_f32; p.ldc32 = ldc32;
-    const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)p.BN * 256u;
+    const uint32_t stage_bytes = (uint32_t)p.na * A_PLANE_BYTES + (uint32_t)p.nb * (uint32_t)p.BN * 128u;
     p.stages = (int)((220 * 1024) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     CUtensorMap ta, tb;
-    if (int rc = make_map(&ta, a_planes, M, K, lda, a_plane, UM)) return rc;
-    if (int rc = make_map(&tb, b_planes, N, K, ldb, b_plane, p.BN)) return rc;
+    if (int rc = make_map(&ta, a_planes, M, K, lda, a_plane, UM, p.na)) return rc;
+    if (int rc = make_map(&tb, b_planes, N, K, ldb, b_plane, p.BN, p.nb)) return rc;
     AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
@@ -498,6 +526,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     UmmaParams p = {};
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.BN = pick_bn(N);
+    p.na = p.nb = p.nc = 2;
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     const int64_t need = avr_umma_gemm_tn_workspace_bytes(M, N, K);
     AVR_REQUIRE(workspace_bytes >= need && aligned16(workspace), "workspace too small or misaligned");
@@ -517,8 +546,8 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     cudaStream_t st = (cudaStream_t)stream;
     if (K > 0) {
         CUtensorMap ta, tb;
-        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64)) return rc;
-        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64)) return rc;
+        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, 2)) return rc;
+        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, 2)) return rc;
         AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);

@@ -1,0 +1,249 @@
+"""The fused native render step on the tensor cores (default path of ``AVRRender`` for ``avr_b200`` fields).
+
+Same contract as ``fused.FusedRenderFunction`` (SURVEY 8a rows a1-a11 in one autograd node) with two
+B200-first changes:
+
+* every activation is an error-compensated bf16 hi/lo plane pair and every dense layer runs on
+  ``tcgen05.mma`` with TMEM accumulators (``csrc/umma_gemm.cu``): fp32-grade accuracy at tensor-core rate;
+* the ``width -> T`` output layer of the signal network is never evaluated per sample point: it is fused with
+  the delay-masked ray reduction as a prefix sum over delay-sorted rays (``csrc/collapse.cu``), so the
+  ``[bs,R,S,T]`` signal tensor and its gradient (0.84 GB / receiver each at simu) do not exist.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .fused import plan_modules
+from .ops import PlanePair
+
+
+FWD_PLANES = 3      # forward operands carry 24 mantissa bits (six products): ReLU decisions must match fp32
+BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough
+
+
+def _weight_planes(net, params, transpose, n):
+    """Plane sets of every matrix of ``net`` (``W[out,in]``) or of its transpose (``W^T[in,out]``)."""
+    out = []
+    for w in net.matrices(params):
+        o, i = w.shape
+        pp = PlanePair.empty(i, o, w.device, n=n) if transpose else PlanePair.empty(o, i, w.device, n=n)
+        ops.planes_split(w, pp, transpose=transpose)
+        out.append(pp)
+    return out
+
+
+def _assemble(segments, buf: PlanePair, col, end_col, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot):
+    """Encode ``segments`` into columns ``[col, ...)`` of ``buf``; pad up to ``end_col`` with ones."""
+    dev = rays_o.device
+    for k, (mod, kind) in enumerate(segments):
+        w = mod.n_output_dims
+        last = k == len(segments) - 1
+        n_ones = end_col - (col + w) if last else 0
+        if kind == "point":
+            delay = delay_slot.pop() if delay_slot else None
+            ops.raygen_encode_fwd(geom, mod.meta, rays_o, pos_tx, dirs, d_vals, params_of(mod), buf, col0=col,
+                                  n_ones=n_ones, delay=delay)
+        else:
+            u = small_in[kind]
+            small = torch.empty(u.shape[0], w, device=dev)
+            ops.grid_encode_fwd(mod.meta, u, params_of(mod), small)
+            ops.rows_broadcast(geom, small, kind != "ray", buf, col)
+            if n_ones:                                                       # tcnn pads the network input with ones
+                c0 = buf.col0 + col + w
+                buf.buf[0, :, c0:c0 + n_ones] = 1.0
+                buf.buf[1:, :, c0:c0 + n_ones] = 0.0
+        col += w
+    return col
+
+
+class FusedRenderTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, geom, tables, tspan, rays_o, pos_tx, dir_tx, dirs, *params):
+        mods = plan_modules(plan)
+        pmap = {id(m): p.detach() for m, p in zip(mods, params)}
+        params_of = lambda m: pmap[id(m)]                                    # noqa: E731
+        enc_net, dec_net, sig_net = plan["enc"], plan["dec"], plan["sig"]
+        feat_dim, T = plan["feat_dim"], geom.T
+        if sig_net.out_pad != T or T % 8:
+            raise NotImplementedError("signal_output_dim must be a multiple of 8")
+        if enc_net.out_pad != feat_dim or feat_dim % 8:
+            raise NotImplementedError("sigma feature width must be a multiple of 16")
+        dev = rays_o.device
+        n_rows = geom.bs * geom.R * geom.S
+        d_vals = tables["d"]
+        u_view, u_tx, u_dtx = ops.aux_inputs(geom, pos_tx, dirs, dir_tx)
+        small_in = {"ray": u_view, "receiver_tx": u_tx, "receiver_dir_tx": u_dtx}
+        delay = torch.empty(geom.bs, geom.R, geom.S, dtype=torch.int32, device=dev)
+        delay_slot = [delay]
+
+        # ---- sigma encoder ------------------------------------------------------------------------
+        x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
+        _assemble(plan["x0"], x0, 0, enc_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot)
+        if delay_slot:
+            _, _, _, delay = ops.sample_points(geom, rays_o, pos_tx, dirs, d_vals, want_pts=False)
+        w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_PLANES)
+        acts_enc, h = [], x0
+        for li in range(len(w_enc) - 1):
+            y = PlanePair.empty(n_rows, w_enc[li].rows, dev, n=FWD_PLANES)
+            ops.umma_nt(h, w_enc[li], ops.UMMA_RELU, y)
+            acts_enc.append(y)
+            h = y
+        # sigma_feat lands directly in the signal network's input buffer (no concat)
+        sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev, n=FWD_PLANES)
+        feat_win = sig_in.window(0, feat_dim)
+        if plan["sig_relu_feat"]:
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win)               # both consumers read relu(feat)
+            dec_in = feat_win
+        else:
+            dec_in = PlanePair.empty(n_rows, feat_dim, dev, n=FWD_PLANES)
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_in)  # raw feat + relu(feat)
+
+        # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
+        w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_PLANES)
+        acts_dec, h = [], dec_in
+        for li in range(len(w_dec) - 1):
+            y = PlanePair.empty(n_rows, w_dec[li].rows, dev, n=FWD_PLANES)
+            ops.umma_nt(h, w_dec[li], ops.UMMA_RELU, y)
+            acts_dec.append(y)
+            h = y
+        dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
+        ops.umma_nt(h, w_dec[-1], ops.UMMA_OUT_F32, c_f32=dec_out)
+        w, _ = ops.ray_weights_fwd(geom, dec_out, dec_out.stride(0), tables["delta"], plan["slope"])
+
+        # ---- signal network hidden layers + collapsed output layer ---------------------------------
+        _assemble(plan["tail"], sig_in, feat_dim, sig_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals,
+                  params_of, [])
+        sig_mats = sig_net.matrices(params_of(sig_net))
+        w_sig = _weight_planes(sig_net, params_of(sig_net), False, FWD_PLANES)[:-1]
+        acts_sig, h = [], sig_in
+        for li in range(len(w_sig)):
+            y = PlanePair.empty(n_rows, w_sig[li].rows, dev, n=FWD_PLANES)
+            ops.umma_nt(h, w_sig[li], ops.UMMA_RELU, y)
+            acts_sig.append(y)
+            h = y
+        sort = ops.delay_sort(geom, delay, w)
+        y_t = ops.collapse_fwd(geom, h, sort, sig_mats[-1])
+        out = ops.spectrum_fwd(geom, y_t, tables)
+
+        if any(ctx.needs_input_grad[8:]):
+            ctx.plan, ctx.geom, ctx.tables, ctx.tspan = plan, geom, tables, tspan
+            ctx.small_in = small_in
+            ctx.bufs = dict(x0=x0, acts_enc=acts_enc, sig_in=sig_in, dec_in=dec_in, acts_dec=acts_dec, dec_out=dec_out,
+                            acts_sig=acts_sig, sort=sort)
+            ctx.save_for_backward(rays_o, dirs, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        plan, geom, tables, B = ctx.plan, ctx.geom, ctx.tables, ctx.bufs
+        rays_o, dirs, *params = ctx.saved_tensors
+        mods = plan_modules(plan)
+        pmap = {id(m): p.detach() for m, p in zip(mods, params)}
+        enc_net, dec_net, sig_net = plan["enc"], plan["dec"], plan["sig"]
+        feat_dim = plan["feat_dim"]
+        dev = d_out.device
+        n_rows = geom.bs * geom.R * geom.S
+        d_vals = tables["d"]
+        grads = {}
+        ws_bytes = max(ops.umma_tn_workspace_bytes(o, i, n_rows) for n in (enc_net, dec_net, sig_net) for (o, i) in n.shapes)
+        ws = torch.empty(max(4, ws_bytes // 4), device=dev)
+
+        def hidden_backward(net, g, acts, first_input, g_flat):
+            """Back-propagate through layers len(acts)..1 of ``net`` given g = d(pre-activation of the last
+            hidden layer); fills the weight gradients of layers >= 1 and of layer 0; returns g at layer 0."""
+            wt = _weight_planes(net, pmap[id(net)], True, BWD_PLANES)
+            d_mats = net.matrices(g_flat)
+            for li in range(len(acts) - 1, 0, -1):
+                x = acts[li - 1]
+                ops.umma_tn(g, x, d_mats[li], ws)
+                gx = PlanePair.empty(n_rows, x.cols, dev)
+                ops.umma_nt(g, wt[li], ops.UMMA_MASK, gx, mask=x)
+                g = gx
+            ops.umma_tn(g, first_input, d_mats[0], ws)
+            return g, wt, d_mats
+
+        # ---- spectrum, collapsed output layer --------------------------------------------------------
+        d_y = ops.spectrum_bwd(geom, d_out.contiguous().float(), tables)
+        sig_mats = sig_net.matrices(pmap[id(sig_net)])
+        g_sig = torch.empty_like(pmap[id(sig_net)])
+        d_sig_mats = sig_net.matrices(g_sig)
+        h_last = B["acts_sig"][-1]
+        g = PlanePair.empty(n_rows, h_last.cols, dev)
+        d_w = ops.collapse_bwd_data(geom, h_last, B["sort"], sig_mats[-1], d_y, g)
+        ops.collapse_bwd_weight(geom, h_last, B["sort"], d_y, d_sig_mats[-1], ctx.tspan)
+
+        # ---- signal network hidden layers ----------------------------------------------------------------
+        sig_in, dec_in = B["sig_in"], B["dec_in"]
+        g, wt_sig, _ = hidden_backward(sig_net, g, B["acts_sig"], sig_in, g_sig)
+        grads[id(sig_net)] = g_sig
+        d_feat = PlanePair.empty(n_rows, feat_dim, dev)
+        wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
+        if plan["sig_relu_feat"]:
+            ops.umma_nt(g, wt0.row_window(0, feat_dim), ops.UMMA_MASK, d_feat, mask=dec_in)
+        else:
+            ops.umma_nt(g, wt0.row_window(0, feat_dim), 0, d_feat)
+        tail_w = sig_net.in_pad - feat_dim
+        d_tail = PlanePair.empty(n_rows, tail_w, dev)
+        ops.umma_nt(g, wt0.row_window(feat_dim, tail_w), 0, d_tail)
+        B["acts_sig"] = None
+
+        # ---- density path: ray weights -> sigma decoder ---------------------------------------------------
+        d_dec_out = torch.zeros_like(B["dec_out"])
+        ops.ray_weights_bwd(geom, B["dec_out"], B["dec_out"].stride(0), tables["delta"], plan["slope"], d_w, d_dec_out,
+                            d_dec_out.stride(0))
+        wt_dec = _weight_planes(dec_net, pmap[id(dec_net)], True, BWD_PLANES)
+        g_dec = torch.empty_like(pmap[id(dec_net)])
+        d_dec_mats = dec_net.matrices(g_dec)
+        g = PlanePair.empty(n_rows, dec_net.out_pad, dev)
+        ops.planes_split(d_dec_out, g)
+        acts_dec = B["acts_dec"]
+        n_dec = len(d_dec_mats)
+        for li in range(n_dec - 1, 0, -1):
+            x = acts_dec[li - 1]
+            ops.umma_tn(g, x, d_dec_mats[li], ws)
+            gx = PlanePair.empty(n_rows, x.cols, dev)
+            ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=x)
+            g = gx
+        ops.umma_tn(g, dec_in, d_dec_mats[0], ws)
+        ops.umma_nt(g, wt_dec[0], ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=dec_in)      # d_feat += relu'(feat) * ...
+        grads[id(dec_net)] = g_dec
+
+        # ---- sigma encoder -----------------------------------------------------------------------------------
+        wt_enc = _weight_planes(enc_net, pmap[id(enc_net)], True, BWD_PLANES)
+        g_enc = torch.empty_like(pmap[id(enc_net)])
+        d_enc_mats = enc_net.matrices(g_enc)
+        acts_enc = B["acts_enc"]
+        g = d_feat
+        for li in range(len(d_enc_mats) - 1, 0, -1):
+            x = acts_enc[li - 1]
+            ops.umma_tn(g, x, d_enc_mats[li], ws)
+            gx = PlanePair.empty(n_rows, x.cols, dev)
+            ops.umma_nt(g, wt_enc[li], ops.UMMA_MASK, gx, mask=x)
+            g = gx
+        x0 = B["x0"]
+        ops.umma_tn(g, x0, d_enc_mats[0], ws)
+        d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
+        ops.umma_nt(g, wt_enc[0], 0, d_x0)
+        grads[id(enc_net)] = g_enc
+
+        # ---- hash tables (deterministic fixed-point scatter) ---------------------------------------------------
+        scratch = torch.empty(max(int(m.meta.total) * 2 for (m, _) in plan["x0"] + plan["tail"]), dtype=torch.int64,
+                              device=dev)
+        for segments, d_buf in ((plan["x0"], d_x0), (plan["tail"], d_tail)):
+            col = 0
+            for mod, kind in segments:
+                wdt = mod.n_output_dims
+                if kind == "point":
+                    acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch)
+                    acc.observe(d_buf, col, wdt)
+                    acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col)
+                else:
+                    small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
+                    acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch)
+                    acc.observe(small, 0, wdt)
+                    acc.add_points(ctx.small_in[kind], small)
+                grads[id(mod)] = acc.finalize()
+                col += wdt
+        ctx.bufs = None
+        return (None,) * 8 + tuple(grads[id(m)] for m in mods)

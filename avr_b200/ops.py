@@ -1,7 +1,11 @@
-"""Tensor-level wrappers over the C-ABI (no autograd here; see ``functional.py``).
+"""Tensor-level wrappers over the C-ABI (no autograd here; see ``functional.py`` / ``fused.py``).
 
 PyTorch is used for device memory and streams only.  Every function launches hand-written kernels
 from ``libavr_b200.so`` on the current CUDA stream of the tensors' device and fails loudly otherwise.
+
+Buffers come in two formats: plain fp32 tensors, and ``PlanePair`` -- the error-compensated bf16
+hi/lo pair that feeds the tcgen05 tensor-core GEMMs (``include/avr_b200.h``, "dense layers on the
+tensor cores").  Kernels that produce or consume activations accept either.
 """
 from __future__ import annotations
 
@@ -11,8 +15,8 @@ import math
 import torch
 
 from . import _lib
-from ._lib import GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG, GridMeta, RenderGeom  # noqa: F401
-
+from ._lib import (GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG,  # noqa: F401
+                   UMMA_ACCUM, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta, RenderGeom)
 
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream ----------------------
 PROFILE = None          # set to a list to collect (name, work, unit, start_event, end_event)
@@ -38,7 +42,58 @@ class _timed:
         return False
 
 
-def _ctx(t: torch.Tensor):
+class PlanePair:
+    """x = hi + mid (+ lo) stored as a bf16 buffer ``[n, rows, ld]`` (n = 2: 16 mantissa bits, n = 3: 24);
+    optionally a row / column window of it."""
+
+    __slots__ = ("buf", "ld", "row0", "rows", "col0", "cols")
+
+    def __init__(self, buf, col0=0, cols=None, row0=0, rows=None):
+        assert buf.dtype == torch.bfloat16 and buf.dim() == 3 and buf.shape[0] in (2, 3) and buf.is_contiguous()
+        self.buf, self.ld = buf, buf.shape[2]
+        self.row0 = row0
+        self.rows = buf.shape[1] - row0 if rows is None else rows
+        self.col0 = col0
+        self.cols = self.ld - col0 if cols is None else cols
+        assert col0 % 8 == 0 and self.ld % 8 == 0, "plane windows must stay 16-byte aligned"
+
+    @staticmethod
+    def empty(rows, cols, device, ld=None, n=2):
+        ld = cols if ld is None else ld
+        ld = (ld + 7) // 8 * 8
+        return PlanePair(torch.empty(n, rows, ld, dtype=torch.bfloat16, device=device), 0, cols)
+
+    @staticmethod
+    def zeros(rows, cols, device, ld=None, n=2):
+        pp = PlanePair.empty(rows, cols, device, ld, n)
+        pp.buf.zero_()
+        return pp
+
+    @property
+    def n(self):
+        return self.buf.shape[0]
+
+    def window(self, col0, cols):
+        return PlanePair(self.buf, self.col0 + col0, cols, self.row0, self.rows)
+
+    def row_window(self, row0, rows):
+        return PlanePair(self.buf, self.col0, self.cols, self.row0 + row0, rows)
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + 2 * (self.row0 * self.ld + self.col0))
+
+    @property
+    def plane(self):
+        return self.buf.shape[1] * self.ld
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
+def _ctx(t):
+    t = t.buf if isinstance(t, PlanePair) else t
     if not t.is_cuda:
         raise _lib.AVRLibraryError("avr_b200 ops need CUDA tensors (there is no CPU fallback)")
     dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
@@ -61,16 +116,29 @@ def _dense(t):
     return t
 
 
+def _np(x):
+    return x.n if isinstance(x, PlanePair) else 0
+
+
+def _mat(x):
+    """-> (pointer, leading dimension, plane stride [0 = fp32]) of a 2-D fp32 tensor / view or a PlanePair."""
+    if isinstance(x, PlanePair):
+        return x.ptr, x.ld, x.plane
+    if x.dtype != torch.float32 or not x.is_cuda or x.stride(-1) != 1:
+        raise TypeError("expected a CUDA fp32 tensor with unit inner stride")
+    return C.c_void_p(x.data_ptr()), x.stride(0), 0
+
+
+def _rows(x):
+    return x.rows if isinstance(x, PlanePair) else x.shape[0]
+
+
 def make_geom(render_cfg: dict, bs: int, T: int) -> RenderGeom:
     """``render_cfg`` as in the reference YAML ``render:`` section (renderer.py:20-29)."""
     R = int(render_cfg["n_azi"]) * int(render_cfg["n_ele"]) + 2
     lo, hi = render_cfg["xyz_min"], render_cfg["xyz_max"]
     return RenderGeom(int(bs), R, int(render_cfg["n_samples"]), int(T), float(lo), float(float(hi) - float(lo)),
                       float(render_cfg["fs"]), float(render_cfg["speed"]))
-
-
-def geom_with_bs(g: RenderGeom, bs: int) -> RenderGeom:
-    return RenderGeom(int(bs), g.R, g.S, g.T, g.xyz_min, g.xyz_span, g.fs, g.speed)
 
 
 def make_grid_meta(geom: dict) -> GridMeta:
@@ -90,7 +158,6 @@ def headroom_bits(n_points: int) -> int:
 # ---- geometry -------------------------------------------------------------------------------------
 def sample_points(g: RenderGeom, rays_o, pos_tx, dirs, d_vals, want_pts=True, want_delay=True):
     dev, st = _ctx(rays_o)
-    n = g.bs * g.R * g.S
     pts = torch.empty(g.bs, g.R * g.S, 3, device=rays_o.device) if want_pts else None
     view = torch.empty_like(pts) if want_pts else None
     txn = torch.empty_like(pts) if want_pts else None
@@ -114,20 +181,23 @@ def aux_inputs(g: RenderGeom, pos_tx, dirs, dir_tx=None):
 
 # ---- hash grid ------------------------------------------------------------------------------------
 def raygen_encode_fwd(g, meta, rays_o, pos_tx, dirs, d_vals, table, out, col0=0, n_ones=0, delay=None):
+    """``out``: fp32 ``[N, ld]`` tensor or PlanePair; encoded columns land at ``col0``."""
     dev, st = _ctx(out)
+    ptr, ld, plane = _mat(out)
     n_pts = g.bs * g.R * g.S
     with _timed("raygen_encode_fwd", float(n_pts) * meta.n_levels * 72, "byte"):     # SURVEY 8d: 8 corners*8 B + 8 B out
         _lib.check(_lib.load().avr_raygen_encode_fwd(C.byref(g), C.byref(meta), _p(_dense(rays_o)),
                                                      _p(_dense(pos_tx)) if pos_tx is not None else None,
-                                                     _p(_dense(dirs)), _p(_dense(d_vals)), _p(_dense(table)), _p(out),
-                                                     out.stride(0), col0, n_ones, _p(delay, torch.int32), dev, st),
+                                                     _p(_dense(dirs)), _p(_dense(d_vals)), _p(_dense(table)), ptr, ld,
+                                                     plane, _np(out), col0, n_ones, _p(delay, torch.int32), dev, st),
                    "avr_raygen_encode_fwd")
 
 
 def grid_encode_fwd(meta, u, table, out, col0=0, n_ones=0):
     dev, st = _ctx(out)
-    _lib.check(_lib.load().avr_grid_encode_fwd(C.byref(meta), _p(_dense(u)), u.shape[0], _p(_dense(table)), _p(out),
-                                               out.stride(0), col0, n_ones, dev, st), "avr_grid_encode_fwd")
+    ptr, ld, plane = _mat(out)
+    _lib.check(_lib.load().avr_grid_encode_fwd(C.byref(meta), _p(_dense(u)), u.shape[0], _p(_dense(table)), ptr, ld, plane,
+                                               _np(out), col0, n_ones, dev, st), "avr_grid_encode_fwd")
 
 
 class GridGradAccumulator:
@@ -145,23 +215,25 @@ class GridGradAccumulator:
 
     def observe(self, d_out, col0, ncols):
         dev, st = _ctx(d_out)
-        rows = d_out.shape[0]
-        _lib.check(_lib.load().avr_absmax_bits(_p(d_out), rows, d_out.stride(0), col0, ncols,
-                                               _p(self.gmax, torch.int32), dev, st), "avr_absmax_bits")
+        ptr, ld, plane = _mat(d_out)
+        _lib.check(_lib.load().avr_absmax_bits(ptr, _rows(d_out), ld, plane, col0, ncols, _p(self.gmax, torch.int32),
+                                               dev, st), "avr_absmax_bits")
 
     def add_rays(self, g, rays_o, dirs, d_vals, d_out, col0=0):
         dev, st = _ctx(d_out)
+        ptr, ld, plane = _mat(d_out)
         n_pts = g.bs * g.R * g.S
         with _timed("raygen_encode_bwd", float(n_pts) * self.meta.n_levels * 136, "byte"):   # 8 B d_out + 8 corners*16 B rmw
             _lib.check(_lib.load().avr_raygen_encode_bwd(C.byref(g), C.byref(self.meta), _p(_dense(rays_o)),
-                                                         _p(_dense(dirs)), _p(_dense(d_vals)), _p(d_out), d_out.stride(0),
-                                                         col0, _p(self.gmax, torch.int32), self.headroom,
+                                                         _p(_dense(dirs)), _p(_dense(d_vals)), ptr, ld, plane, col0,
+                                                         _p(self.gmax, torch.int32), self.headroom,
                                                          _p(self.acc, torch.int64), dev, st), "avr_raygen_encode_bwd")
 
     def add_points(self, u, d_out, col0=0):
         dev, st = _ctx(d_out)
-        _lib.check(_lib.load().avr_grid_encode_bwd(C.byref(self.meta), _p(_dense(u)), u.shape[0], _p(d_out),
-                                                   d_out.stride(0), col0, _p(self.gmax, torch.int32), self.headroom,
+        ptr, ld, plane = _mat(d_out)
+        _lib.check(_lib.load().avr_grid_encode_bwd(C.byref(self.meta), _p(_dense(u)), u.shape[0], ptr, ld, plane, col0,
+                                                   _p(self.gmax, torch.int32), self.headroom,
                                                    _p(self.acc, torch.int64), dev, st), "avr_grid_encode_bwd")
 
     def finalize(self, grad=None, accumulate=False):
@@ -174,7 +246,7 @@ class GridGradAccumulator:
         return grad
 
 
-# ---- dense layers ---------------------------------------------------------------------------------
+# ---- dense layers, fp32 SIMT ------------------------------------------------------------------------
 def gemm_workspace_bytes(M, N, K) -> int:
     return int(_lib.load().avr_gemm_workspace_bytes(M, N, K))
 
@@ -210,20 +282,75 @@ def linear_bwd_weight(dy, x, dw, workspace, accum=False, relu_in=False):
          flags, None, 0, workspace)
 
 
+# ---- dense layers, tensor cores (tcgen05) on bf16 plane pairs -----------------------------------------
+def planes_split(x, out: PlanePair, transpose=False, relu=False):
+    """fp32 ``x[rows, cols]`` (row stride ``x.stride(0)``) -> plane pair (``out[c, r]`` when ``transpose``)."""
+    dev, st = _ctx(x)
+    rows, cols = x.shape
+    assert x.stride(1) == 1
+    _lib.check(_lib.load().avr_planes_split(_p(x), rows, cols, x.stride(0), out.ptr, out.ld, out.plane, out.n,
+                                            1 if transpose else 0, 1 if relu else 0, dev, st), "avr_planes_split")
+    return out
+
+
+def planes_merge(pp: PlanePair):
+    dev, st = _ctx(pp)
+    out = torch.empty(pp.rows, pp.cols, device=pp.device)
+    _lib.check(_lib.load().avr_planes_merge(pp.ptr, pp.rows, pp.cols, pp.ld, pp.plane, pp.n, _p(out), pp.cols, dev, st),
+               "avr_planes_merge")
+    return out
+
+
+def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask: PlanePair = None,
+            c_f32=None):
+    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane pair or (UMMA_OUT_F32) an fp32 tensor."""
+    dev, st = _ctx(a)
+    M, K, N = a.rows, a.cols, b.rows
+    assert b.cols == K, (b.cols, K)
+    none = C.c_void_p(None)
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
+        _lib.check(_lib.load().avr_umma_gemm_nt(
+            M, N, K, a.ptr, a.ld, a.plane, a.n, b.ptr, b.ld, b.plane, b.n, flags,
+            c.ptr if c is not None else none, c.ld if c is not None else 0, c.plane if c is not None else 0,
+            c.n if c is not None else 2,
+            c2.ptr if c2 is not None else none, c2.ld if c2 is not None else 0, c2.plane if c2 is not None else 0,
+            mask.ptr if mask is not None else none, mask.ld if mask is not None else 0,
+            _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0, dev, st), "avr_umma_gemm_nt")
+
+
+def umma_tn_workspace_bytes(M, N, K) -> int:
+    return int(_lib.load().avr_umma_gemm_tn_workspace_bytes(M, N, K))
+
+
+def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
+    """C[M,N] (+)= sum_k A[k,M] B[k,N]  (A, B plane pairs over the same rows k); fp32 C (may be a column view)."""
+    dev, st = _ctx(a)
+    K, M, N = a.rows, a.cols, b.cols
+    assert b.rows == K
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
+        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, _p(c_f32),
+                                                c_f32.stride(0), 1 if accumulate else 0,
+                                                C.c_void_p(workspace.data_ptr()),
+                                                workspace.numel() * workspace.element_size(), dev, st), "avr_umma_gemm_tn")
+
+
 # ---- broadcast inputs -----------------------------------------------------------------------------
 def rows_broadcast(g, src, per_receiver, dst, col0):
     dev, st = _ctx(dst)
+    ptr, ld, plane = _mat(dst)
     _lib.check(_lib.load().avr_rows_broadcast(C.byref(g), _p(_dense(src)), src.shape[1], 1 if per_receiver else 0,
-                                              _p(dst), dst.stride(0), col0, dev, st), "avr_rows_broadcast")
+                                              ptr, ld, plane, _np(dst), col0, dev, st), "avr_rows_broadcast")
 
 
 def rows_reduce(g, d_dst, col0, w, per_receiver):
     dev, st = _ctx(d_dst)
+    ptr, ld, plane = _mat(d_dst)
     rows = g.bs if per_receiver else g.R
+    device = d_dst.device
     nbytes = int(_lib.load().avr_rows_reduce_workspace_bytes(C.byref(g), w, 1 if per_receiver else 0))
-    ws = torch.empty(max(1, nbytes // 4), device=d_dst.device)
-    out = torch.empty(rows, w, device=d_dst.device)
-    _lib.check(_lib.load().avr_rows_reduce(C.byref(g), _p(d_dst), d_dst.stride(0), col0, w, 1 if per_receiver else 0,
+    ws = torch.empty(max(1, nbytes // 4), device=device)
+    out = torch.empty(rows, w, device=device)
+    _lib.check(_lib.load().avr_rows_reduce(C.byref(g), ptr, ld, plane, col0, w, 1 if per_receiver else 0,
                                            _p(out), _p(ws), nbytes, dev, st), "avr_rows_reduce")
     return out
 
@@ -294,89 +421,57 @@ def spectrum_bwd(g, d_out, tables):
     return d_y
 
 
-# ---- tensor-core dense layers on bf16 plane pairs ------------------------------------------------------
-from ._lib import UMMA_ACCUM, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU  # noqa: E402,F401
+# ---- output layer fused with the ray reduction ---------------------------------------------------------
+def delay_sort(g, delay, w):
+    """-> (order, sdelay int32 [bs,S,R], sw fp32 [bs,S,R]): rays of each (b,s) sorted by delay (stable)."""
+    dev, st = _ctx(w)
+    order = torch.empty(g.bs, g.S, g.R, dtype=torch.int32, device=w.device)
+    sdelay = torch.empty_like(order)
+    sw = torch.empty(g.bs, g.S, g.R, device=w.device)
+    _lib.check(_lib.load().avr_delay_sort(C.byref(g), _p(_dense(delay), torch.int32), _p(_dense(w)), _p(order, torch.int32),
+                                          _p(sdelay, torch.int32), _p(sw), dev, st), "avr_delay_sort")
+    return order, sdelay, sw
 
 
-class PlanePair:
-    """x = hi + lo stored as a bf16 buffer ``[2, rows, ld]``; optionally a column window of it."""
-
-    __slots__ = ("buf", "rows", "ld", "col0", "cols")
-
-    def __init__(self, buf, col0=0, cols=None):
-        assert buf.dtype == torch.bfloat16 and buf.dim() == 3 and buf.shape[0] == 2 and buf.is_contiguous()
-        self.buf, self.rows, self.ld = buf, buf.shape[1], buf.shape[2]
-        self.col0 = col0
-        self.cols = self.ld - col0 if cols is None else cols
-        assert col0 % 8 == 0 and self.ld % 8 == 0, "plane windows must stay 16-byte aligned"
-
-    @staticmethod
-    def empty(rows, cols, device, ld=None):
-        ld = cols if ld is None else ld
-        ld = (ld + 7) // 8 * 8
-        return PlanePair(torch.empty(2, rows, ld, dtype=torch.bfloat16, device=device), 0, cols)
-
-    def window(self, col0, cols):
-        return PlanePair(self.buf, self.col0 + col0, cols)
-
-    @property
-    def ptr(self):
-        return C.c_void_p(self.buf.data_ptr() + 2 * self.col0)
-
-    @property
-    def plane(self):
-        return self.rows * self.ld
-
-    @property
-    def device(self):
-        return self.buf.device
+def collapse_tspan(render_cfg) -> int:
+    """Static bound on the delay spread within one (b,s): |dist(tx,p) - dist(tx,rx)| <= |p - rx| <= far."""
+    return int(math.ceil(2.0 * float(render_cfg["far"]) * float(render_cfg["fs"]) / float(render_cfg["speed"]))) + 4
 
 
-def planes_split(x, out: PlanePair, transpose=False, relu=False):
-    """fp32 ``x[rows, cols]`` (row stride ``x.stride(0)``) -> plane pair (``out[c, r]`` when ``transpose``)."""
-    dev, st = _ctx(x)
-    rows, cols = x.shape
-    assert x.stride(1) == 1
-    _lib.check(_lib.load().avr_planes_split(_p(x), rows, cols, x.stride(0), out.ptr, out.ld, out.plane,
-                                            1 if transpose else 0, 1 if relu else 0, dev, st), "avr_planes_split")
-    return out
+def collapse_fwd(g, act: PlanePair, sort, w_out):
+    dev, st = _ctx(act)
+    order, sdelay, sw = sort
+    y = torch.empty(g.bs, g.S, g.T, device=act.device)
+    n_pts = g.bs * g.R * g.S
+    with _timed("collapse_fwd", float(n_pts) * act.cols * 4 + float(g.bs * g.S) * g.T * act.cols * 4, "byte"):
+        _lib.check(_lib.load().avr_collapse_fwd(C.byref(g), act.ptr, act.ld, act.plane, act.cols, _p(order, torch.int32),
+                                                _p(sdelay, torch.int32), _p(sw), _p(w_out), w_out.stride(0), _p(y), dev, st),
+                   "avr_collapse_fwd")
+    return y
 
 
-def planes_merge(pp: PlanePair):
-    dev, st = _ctx(pp.buf)
-    out = torch.empty(pp.rows, pp.cols, device=pp.device)
-    _lib.check(_lib.load().avr_planes_merge(pp.ptr, pp.rows, pp.cols, pp.ld, pp.plane, _p(out), pp.cols, dev, st),
-               "avr_planes_merge")
-    return out
+def collapse_bwd_data(g, act: PlanePair, sort, w_out, d_y, d_act: PlanePair):
+    dev, st = _ctx(act)
+    order, sdelay, sw = sort
+    d_w = torch.empty(g.bs, g.R, g.S, device=act.device)
+    n_pts = g.bs * g.R * g.S
+    with _timed("collapse_bwd_data", float(n_pts) * act.cols * 8 + float(g.bs * g.S) * g.T * act.cols * 4, "byte"):
+        _lib.check(_lib.load().avr_collapse_bwd_data(C.byref(g), act.ptr, act.ld, act.plane, act.cols,
+                                                     _p(order, torch.int32), _p(sdelay, torch.int32), _p(sw), _p(w_out),
+                                                     w_out.stride(0), _p(_dense(d_y)), d_act.ptr, d_act.ld, d_act.plane,
+                                                     _p(d_w), dev, st), "avr_collapse_bwd_data")
+    return d_w
 
 
-def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask: PlanePair = None,
-            c_f32=None):
-    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane pair or (UMMA_OUT_F32) an fp32 tensor."""
-    dev, st = _ctx(a.buf)
-    M, K, N = a.rows, a.cols, b.rows
-    assert b.cols == K, (b.cols, K)
-    none = C.c_void_p(None)
-    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
-        _lib.check(_lib.load().avr_umma_gemm_nt(
-            M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, flags,
-            c.ptr if c is not None else none, c.ld if c is not None else 0, c.plane if c is not None else 0,
-            c2.ptr if c2 is not None else none, c2.ld if c2 is not None else 0, c2.plane if c2 is not None else 0,
-            mask.ptr if mask is not None else none, mask.ld if mask is not None else 0,
-            _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0, dev, st), "avr_umma_gemm_nt")
-
-
-def umma_tn_workspace_bytes(M, N, K) -> int:
-    return int(_lib.load().avr_umma_gemm_tn_workspace_bytes(M, N, K))
-
-
-def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
-    """C[M,N] (+)= sum_k A[k,M] B[k,N]  (A, B plane pairs over the same rows k); fp32 C (may be a column view)."""
-    dev, st = _ctx(a.buf)
-    K, M, N = a.rows, a.cols, b.cols
-    assert b.rows == K
-    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
-        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, _p(c_f32),
-                                                c_f32.stride(0), 1 if accumulate else 0,
-                                                C.c_void_p(workspace.data_ptr()),
-                                                workspace.numel() * workspace.element_size(), dev, st), "avr_umma_gemm_tn")
+def collapse_bwd_weight(g, act: PlanePair, sort, d_y, d_wout, tspan, accumulate=False):
+    dev, st = _ctx(act)
+    order, sdelay, sw = sort
+    nbytes = int(_lib.load().avr_collapse_bwd_weight_workspace_bytes(C.byref(g), act.cols, tspan))
+    ws = torch.empty((nbytes + 3) // 4, device=act.device)
+    n_pts = g.bs * g.R * g.S
+    with _timed("collapse_bwd_weight", float(n_pts) * act.cols * 4 + 2.0 * g.bs * g.S * tspan * act.cols * 4, "byte"):
+        _lib.check(_lib.load().avr_collapse_bwd_weight(C.byref(g), act.ptr, act.ld, act.plane, act.cols,
+                                                       _p(order, torch.int32), _p(sdelay, torch.int32), _p(sw),
+                                                       _p(_dense(d_y)), _p(d_wout), d_wout.stride(0),
+                                                       1 if accumulate else 0, tspan, C.c_void_p(ws.data_ptr()),
+                                                       ws.numel() * 4, dev, st), "avr_collapse_bwd_weight")

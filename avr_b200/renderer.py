@@ -24,6 +24,7 @@ import torch.nn as nn
 from . import _lib, ops, tables
 from .functional import CompositeFunction
 from .fused import FusedRenderFunction, plan_modules
+from .fused_tc import FusedRenderTC
 
 
 class AVRRender(nn.Module):
@@ -44,6 +45,11 @@ class AVRRender(nn.Module):
         self.xyz_max = kwargs["xyz_max"]
         #: receivers rendered per kernel pass (bounds the activation memory of large inference batches)
         self.max_receivers_per_pass = int(kwargs.get("max_receivers_per_pass", 8))
+        #: "tc": dense layers on tcgen05 tensor cores (3 x bf16 error-compensated) + collapsed output layer;
+        #: "simt": exact-fp32 FMA GEMMs and the literal signal tensor (slower; kept as an independent check)
+        self.dense = kwargs.get("dense", "tc")
+        if self.dense not in ("tc", "simt"):
+            raise ValueError("dense must be 'tc' or 'simt'")
         self._tables = {}
 
     # -- configuration -----------------------------------------------------------------------------
@@ -96,8 +102,11 @@ class AVRRender(nn.Module):
             tab = self.tables_for(T, rays_o.device)
             geom = ops.make_geom(self.render_cfg(), bs, T)
             params = [m.params for m in plan_modules(plan)]
-            return FusedRenderFunction.apply(plan, geom, tab.dev, rays_o, position_tx,
-                                             direction_tx if plan["needs_dir_tx"] else None, dirs, *params)
+            dtx = direction_tx if plan["needs_dir_tx"] else None
+            if self.dense == "tc":
+                return FusedRenderTC.apply(plan, geom, tab.dev, ops.collapse_tspan(self.render_cfg()), rays_o,
+                                           position_tx, dtx, dirs, *params)
+            return FusedRenderFunction.apply(plan, geom, tab.dev, rays_o, position_tx, dtx, dirs, *params)
 
         # generic networks_fn: build what renderer.py:54-62 builds, call the network, composite.
         cfg = self.render_cfg()

@@ -101,11 +101,15 @@ AVR_API int avr_aux_inputs(const avr_render_geom* geom, const float* pos_tx, con
  * are produced in registers and encoded; nothing of shape [bs,P,3] reaches HBM.
  *   table[total*2]; out rows n=(b,r,s): out[n*ld_out + col0 + 2*l + f];
  *   columns [col0+2L, col0+2L+n_ones) are set to 1 (tcnn input padding);
- *   delay (optional, int32[bs,R,S]) as in avr_sample_points. */
+ *   delay (optional, int32[bs,R,S]) as in avr_sample_points.
+ *   out_plane == 0: `out` is fp32.  out_plane > 0: `out` is a bf16 plane set (see "dense layers on the
+ *   tensor cores") of out_nplanes (2 or 3) planes with that plane stride, ld_out in bf16 elements; readers
+ *   of plane sets (d_out, d_dst, x) use the first two planes.  The same convention holds for the
+ *   d_out / x / dst / d_dst arguments below that carry a `*_plane` companion. */
 AVR_API int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
                           const float* pos_tx, const float* dirs, const float* d_vals, const float* table,
-                          float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int32_t* delay,
-                          int device, void* stream);
+                          void* out, int64_t ld_out, int64_t out_plane, int32_t out_nplanes, int32_t col0,
+                          int32_t n_ones, int32_t* delay, int device, void* stream);
 
 /* Backward of the above w.r.t. the table (tcnn kernel_grid_backward), DETERMINISTIC:
  * contributions are accumulated as 2^e-scaled int64 (integer addition is associative), `e`
@@ -113,18 +117,19 @@ AVR_API int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_me
  * entry).  acc[total*2] int64 must be zeroed by the caller (or hold a previous partial sum
  * taken with the same gmax_bits); gmax_bits is a device uint32 filled by avr_absmax_bits. */
 AVR_API int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
-                          const float* dirs, const float* d_vals, const float* d_out, int64_t ld_out,
-                          int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, int64_t* acc,
+                          const float* dirs, const float* d_vals, const void* d_out, int64_t ld_out,
+                          int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, int64_t* acc,
                           int device, void* stream);
 
 /* Encode explicit unit-cube points u[N,3] (model.py:191,219-220 on arbitrary inputs). */
 AVR_API int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* table,
-                        float* out, int64_t ld_out, int32_t col0, int32_t n_ones, int device, void* stream);
-AVR_API int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* d_out,
-                        int64_t ld_out, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
+                        void* out, int64_t ld_out, int64_t out_plane, int32_t out_nplanes, int32_t col0, int32_t n_ones,
+                        int device, void* stream);
+AVR_API int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const void* d_out,
+                        int64_t ld_out, int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
                         int64_t* acc, int device, void* stream);
 /* gmax_bits = max(gmax_bits, bit pattern of max |x[i, col0:col0+ncols]|)  (caller zeroes it first) */
-AVR_API int avr_absmax_bits(const float* x, int64_t rows, int64_t ld, int32_t col0, int32_t ncols,
+AVR_API int avr_absmax_bits(const void* x, int64_t rows, int64_t ld, int64_t plane, int32_t col0, int32_t ncols,
                     uint32_t* gmax_bits, int device, void* stream);
 /* grad[i] (+)= (float)(acc[i] * 2^-e) */
 AVR_API int avr_grid_grad_finalize(const int64_t* acc, int64_t n, const uint32_t* gmax_bits, int32_t log2_headroom,
@@ -140,10 +145,13 @@ AVR_API int avr_gemm(int layout_a, int layout_b, int64_t M, int64_t N, int64_t K
              void* workspace, int64_t workspace_bytes, int device, void* stream);
 
 /* ---- dense layers on the tensor cores (tcgen05.mma / TMEM / TMA), fp32-grade accuracy ----------------
- * Operands are error-compensated PAIRS of bf16 planes, x = hi + lo (hi = bf16(x), lo = bf16(x - hi)): a
- * "plane pair" is a bf16 buffer [2][rows][ld] addressed by (base, ld, plane_stride), all in elements, with
- * 16-byte aligned base / row pitch / plane pitch.  Products are evaluated as hi*hi + hi*lo + lo*hi in one
- * fp32 TMEM accumulator (relative error ~2^-17 per product). */
+ * Operands are error-compensated SETS of bf16 planes, x = hi + mid (+ lo) with hi = bf16(x),
+ * mid = bf16(x - hi), lo = bf16(x - hi - mid): a bf16 buffer [nplanes][rows][ld] addressed by
+ * (base, ld, plane_stride), all in elements, with 16-byte aligned base / row pitch / plane pitch.
+ *   2 planes x 2 planes: hi*hi + hi*mid + mid*hi            (~2^-17 per product; gradients: errors enter linearly)
+ *   3 planes x 3 planes: + hi*lo + lo*hi + mid*mid          (~2^-24: fp32-grade pre-activations, needed in the
+ *                        forward pass so that ReLU decisions agree with an fp32 evaluation -- DESIGN.md 5)
+ * all accumulated in one fp32 TMEM accumulator. */
 enum {
     AVR_UMMA_RELU = 1,        /* out = max(out, 0)                                                   */
     AVR_UMMA_ACCUM = 2,       /* out += previous contents of the output                              */
@@ -153,15 +161,16 @@ enum {
 };
 /* fp32 [rows, cols] (ld) <-> plane pair; transpose != 0 writes planes[c, r] = x[r, c]; relu != 0 clamps */
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
-                             int64_t plane_stride, int transpose, int relu, int device, void* stream);
+                             int64_t plane_stride, int nplanes, int transpose, int relu, int device, void* stream);
 AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride,
-                             float* out, int64_t ld, int device, void* stream);
+                             int nplanes, float* out, int64_t ld, int device, void* stream);
 /* C[M,N] = A[M,K] . B[N,K]^T   (A, B plane pairs with the reduction index contiguous; N % 8 == 0).
  * Forward layers (B = W[out,in]) and backward-data (B = transposed weight planes W^T[in,out]). */
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
-                             const void* b_planes, int64_t ldb, int64_t b_plane, int flags, void* c_planes, int64_t ldc,
-                             int64_t c_plane, void* c2_planes, int64_t ldc2, int64_t c2_plane, const void* mask_hi,
-                             int64_t ldmask, float* c_f32, int64_t ldc32, int device, void* stream);
+                             int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
+                             void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
+                             int64_t c2_plane, const void* mask_hi, int64_t ldmask, float* c_f32, int64_t ldc32,
+                             int device, void* stream);
 /* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane pairs; weight gradients).
  * fp32 output; deterministic split-K over the points through `workspace`. */
 AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
@@ -169,14 +178,37 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
                              const void* b_planes, int64_t ldb, int64_t b_plane, float* c, int64_t ldc, int accumulate,
                              void* workspace, int64_t workspace_bytes, int device, void* stream);
 
+/* ---- output layer fused with the ray reduction ("collapse"; model.py:231 + renderer.py:86-90,115-118) -----
+ * y[b,s,t] = sum_r w[b,r,s] [t >= delay[b,r,s]] (H[b,r,s,:] . W_out[t,:]) evaluated as a prefix sum over the
+ * rays of each (b,s) sorted by delay, so neither signal[bs,R,S,T] nor its gradient is ever formed.
+ *   H: plane pair [bs*R*S, width] (post-ReLU last hidden activation);  W_out: fp32 [T, width] (ld = ldw).
+ *   avr_delay_sort: stable counting sort by delay -> order / sdelay / sw, each [bs,S,R]. */
+AVR_API int avr_delay_sort(const avr_render_geom* geom, const int32_t* delay, const float* w, int32_t* order,
+                           int32_t* sdelay, float* sw, int device, void* stream);
+AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
+                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             const float* w_out, int64_t ldw, float* y, int device, void* stream);
+/* d_act = (H > 0) * w * g[delay] as a plane pair (gradient w.r.t. the pre-activation), d_w[bs,R,S] = H . g[delay] */
+AVR_API int avr_collapse_bwd_data(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
+                                  int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                                  const float* w_out, int64_t ldw, const float* d_y, void* d_act_planes, int64_t ld_d,
+                                  int64_t d_plane, float* d_w, int device, void* stream);
+/* d_W_out[T, width] (+)= sum_{b,s} d_y[b,s,t] G[b,s,t,:]; tspan >= max over (b,s) of (max delay - min delay) */
+AVR_API int64_t avr_collapse_bwd_weight_workspace_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan);
+AVR_API int avr_collapse_bwd_weight(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
+                                    int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                                    const float* d_y, float* d_wout, int64_t ldw, int accumulate, int32_t tspan,
+                                    void* workspace, int64_t workspace_bytes, int device, void* stream);
+
 /* ---- broadcast inputs of the signal network (renderer.py:59-60; model.py:219-221) ------------
  * dst[n, col0:col0+w] = src[row(n), 0:w] with row(n) = r (per_receiver=0) or b (per_receiver=1). */
 AVR_API int avr_rows_broadcast(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,
-                       float* dst, int64_t ld_dst, int32_t col0, int device, void* stream);
+                       void* dst, int64_t ld_dst, int64_t dst_plane, int32_t dst_nplanes, int32_t col0, int device,
+                       void* stream);
 /* transpose of the above: d_src[row, :] = sum over the points mapped to `row` (fixed order). */
 AVR_API int64_t avr_rows_reduce_workspace_bytes(const avr_render_geom* geom, int32_t w, int per_receiver);
-AVR_API int avr_rows_reduce(const avr_render_geom* geom, const float* d_dst, int64_t ld_dst, int32_t col0, int32_t w,
-                    int per_receiver, float* d_src, float* workspace, int64_t workspace_bytes,
+AVR_API int avr_rows_reduce(const avr_render_geom* geom, const void* d_dst, int64_t ld_dst, int64_t d_plane, int32_t col0,
+                    int32_t w, int per_receiver, float* d_src, float* workspace, int64_t workspace_bytes,
                     int device, void* stream);
 
 /* ---- density -> alpha -> transmittance -> ray weights (renderer.py:167-190; model.py:233) ----

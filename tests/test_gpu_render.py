@@ -34,13 +34,14 @@ def _check_grads(native, ref_net, tol=TOL):
     return worst
 
 
+@pytest.mark.parametrize("dense", ["tc", "simt"])
 @pytest.mark.parametrize("name", GOLDEN_CASES[:3])
-def test_fused_render_vs_golden(built_library, name):
+def test_fused_render_vs_golden(built_library, name, dense):
     g = load_golden(name)
     model_class, cfg = case_config(name)
     ref_net = oracle_field(model_class, cfg["model"], g)
     native = _native_from(ref_net, model_class, cfg["model"])
-    ren = avr_b200.AVRRender(native, **cfg["render"])
+    ren = avr_b200.AVRRender(native, **cfg["render"], dense=dense)
     dtx = g["dir_tx"].to(DEV) if "dir_tx" in g else None
     out = ren(g["rx"].to(DEV), g["tx"].to(DEV), dtx, azi_rand=g["azi_rand"])
     assert out.shape == g["out"].shape and out.dtype == torch.float32
@@ -73,12 +74,13 @@ def test_generic_network_path_vs_golden(built_library):
     assert rel_l2(net.signal.grad, g["grad/signal"]) < 1e-5
 
 
+@pytest.mark.parametrize("dense", ["tc", "simt"])
 @pytest.mark.parametrize("model_class,kw,bs", [
     ("AVRModel", dict(n_azi=12, n_ele=6, n_samples=24, T=400, width_sigma=64, width_signal=128), 3),
     ("AVRModel", dict(n_azi=9, n_ele=5, n_samples=40, T=320, xyz_min=0, xyz_max=10, fs=4000), 1),
     ("AVRModel_complex", dict(n_azi=10, n_ele=5, n_samples=16, T=480, fs=8000, xyz_min=-12, xyz_max=12), 2),
 ])
-def test_fused_render_vs_oracle_seeded(built_library, model_class, kw, bs):
+def test_fused_render_vs_oracle_seeded(built_library, model_class, kw, bs, dense):
     cfg = tiny_config(model_class, **kw)
     cls = field_ref.AVRModelRef if model_class == "AVRModel" else field_ref.AVRModelComplexRef
     ref_net = field_ref.trained_like_(cls(cfg["model"], seed=21), seed=22)
@@ -93,7 +95,7 @@ def test_fused_render_vs_oracle_seeded(built_library, model_class, kw, bs):
     G = torch.randn(bs, kw["T"] // 2 + 1, 2, generator=gen)
     ref_out = render_ref.RenderRef(ref_net, **r)(rx, tx, dtx, azi_rand=azi)
     (ref_out * G).sum().backward()
-    ren = avr_b200.AVRRender(native, **r)
+    ren = avr_b200.AVRRender(native, **r, dense=dense)
     out = ren(rx.to(DEV), tx.to(DEV), dtx.to(DEV) if dtx is not None else None, azi_rand=azi)
     assert float(ref_out.abs().max()) > 0
     assert rel_l2(out, ref_out) < TOL

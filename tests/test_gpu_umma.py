@@ -11,8 +11,8 @@ DEV = "cuda:0"
 TOL = 2e-5        # ~2^-17 per product, random signs
 
 
-def _pp(x, ld=None):
-    out = PlanePair.empty(x.shape[0], x.shape[1], DEV, ld)
+def _pp(x, ld=None, n=2):
+    out = PlanePair.empty(x.shape[0], x.shape[1], DEV, ld, n)
     return ops.planes_split(x.to(DEV).contiguous(), out)
 
 
@@ -65,6 +65,28 @@ def test_umma_nt_epilogues(built_library):
     assert rel_l2(m[:, 128:128 + N], ref) < TOL and float(m[:, :128].abs().max()) == 0 and float(m[:, 384:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 128, 48), (4099, 512, 512), (300, 16, 128), (777, 208, 128), (130, 512, 208)])
+def test_umma_nt_six_products_fp32_grade(built_library, M, N, K):
+    """3 planes x 3 planes (forward pass): operands carry 24 bits; what remains is the tensor core's own
+    accumulation rounding (one truncation per tcgen05.mma into TMEM: ~7e-9 * K relative, measured)."""
+    g = torch.Generator().manual_seed(M * N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    a, b = _pp(A, n=3), _pp(B, n=3)
+    assert float((ops.planes_merge(a).cpu() - A).abs().max()) <= 2 ** -23 * float(A.abs().max())
+    ref = A.double() @ B.double().t()
+    c = PlanePair.empty(M, N, DEV, n=3)
+    ops.umma_nt(a, b, ops.UMMA_RELU, c)
+    bound = 1e-8 * K + 5e-7
+    err = rel_l2(ops.planes_merge(c), ref.clamp_min(0))
+    assert err < bound, (err, bound)
+    c2 = PlanePair.empty(M, N, DEV, n=2)
+    ops.umma_nt(_pp(A), _pp(B), ops.UMMA_RELU, c2)
+    assert err < rel_l2(ops.planes_merge(c2), ref.clamp_min(0))          # strictly better than the 3-product mode
+    c32 = torch.empty(M, N, device=DEV)
+    ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c32)
+    assert rel_l2(c32, ref) < bound
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (512, 512, 20000), (16, 128, 5000), (128, 48, 3001), (512, 208, 7777),
                                    (1600, 512, 4100), (128, 80, 64)])
 def test_umma_tn_weight_grad(built_library, M, N, K):
@@ -80,3 +102,43 @@ def test_umma_tn_weight_grad(built_library, M, N, K):
     assert torch.equal(outs[0], outs[1])                     # deterministic split-K
     assert rel_l2(outs[0][:, :N], dY.double().t() @ X.double()) < TOL
     assert float(outs[0][:, N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("bs,R,S,T,W", [(2, 37, 5, 200, 64), (1, 300, 7, 400, 512), (3, 66, 4, 240, 136)])
+def test_collapse_matches_literal_output_layer(built_library, bs, R, S, T, W):
+    """y, d_H, d_w, d_W_out of the collapsed output layer == literal GEMM + masked ray reduction (float64)."""
+    g = torch.Generator().manual_seed(R + T)
+    n = bs * R * S
+    H = torch.randn(n, W, generator=g).clamp_min(0)                      # post-ReLU hidden activation
+    Wout = torch.randn(T, W, generator=g) / W ** 0.5
+    w = torch.rand(bs, R, S, generator=g)
+    delay = torch.randint(0, T // 3, (bs, R, S), generator=g, dtype=torch.int32) + torch.arange(S, dtype=torch.int32) * 11
+    delay[0, :, 0] = 7                                                    # one (b,s) where every ray shares a delay
+    dy = torch.randn(bs, S, T, generator=g)
+    geom = ops.RenderGeom(bs, R, S, T, -10.0, 20.0, 16000.0, 343.8)
+    hp = PlanePair.empty(n, W, DEV)
+    ops.planes_split(H.to(DEV), hp)
+    Hq = ops.planes_merge(hp).cpu().double()                              # the values the kernels actually see
+    Hq.requires_grad_()
+    Wd = Wout.double().requires_grad_()
+    wd = w.double().requires_grad_()
+    sig = (Hq @ Wd.t()).view(bs, R, S, T)
+    mask = (torch.arange(T)[None, None, None, :] >= delay[..., None]).double()
+    y_ref = (sig * mask * wd[..., None]).sum(1)
+    (y_ref * dy.double()).sum().backward()
+    sort = ops.delay_sort(geom, delay.to(DEV), w.to(DEV))
+    sd = sort[1].cpu()
+    assert bool((sd[..., 1:] >= sd[..., :-1]).all())                      # sortedness
+    assert torch.equal(torch.sort(sort[0].cpu(), dim=-1).values, torch.arange(R, dtype=torch.int32).expand(bs, S, R))
+    y = ops.collapse_fwd(geom, hp, sort, Wout.to(DEV))
+    assert rel_l2(y, y_ref) < 2e-6
+    dH = PlanePair.empty(n, W, DEV)
+    d_w = ops.collapse_bwd_data(geom, hp, sort, Wout.to(DEV), dy.to(DEV), dH)
+    assert rel_l2(d_w, wd.grad) < 2e-6
+    assert rel_l2(ops.planes_merge(dH), Hq.grad * (Hq.detach() > 0)) < 2e-5
+    dW = torch.zeros(T, W + 8, device=DEV)
+    ops.collapse_bwd_weight(geom, hp, sort, dy.to(DEV), dW[:, :W], tspan=T)
+    assert rel_l2(dW[:, :W], Wd.grad) < 2e-6 and float(dW[:, W:].abs().max()) == 0
+    dW2 = torch.zeros(T, W, device=DEV)
+    ops.collapse_bwd_weight(geom, hp, sort, dy.to(DEV), dW2, tspan=3)     # violated bound must poison, not corrupt
+    assert bool(torch.isnan(dW2).any())
