@@ -292,6 +292,12 @@ def run_native(args, cfg):
                 kernels[name] = {"bound": "hbm", "achieved": rate / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": rate / 1e9 / pk["hbm"], "launches_per_step": d["n"] / args.steps,
                                  "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / ms}
+        if os.environ.get("AVR_BENCH_DETAIL"):
+            per_step = len(prof) // args.steps
+            for name, work, unit, s0, e0 in prof[-per_step:]:
+                t = s0.elapsed_time(e0)
+                rate = work / (t * 1e-3) / (1e12 if unit == "flop" else 1e9)
+                sys.stderr.write(f"DETAIL {name:22s} {t:8.3f} ms  work {work:.3e} {unit}  {rate:8.1f} {'TFLOP/s' if unit == 'flop' else 'GB/s'}\n")
         dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
         roof = dict(kernels[dominant]) if dominant else {}
         roof.update({"kernel": dominant, "traffic": None, "peak_source": pk["src"],

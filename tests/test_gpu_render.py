@@ -187,3 +187,39 @@ def test_full_size_simu_properties(built_library):
         grads.append([p.grad.clone() for p in native.parameters()])
     for a, b in zip(*grads):
         assert torch.equal(a, b) and bool(torch.isfinite(a).all())
+
+
+@pytest.mark.parametrize("name,bs", [("meshrir", 1), ("raf_furnished", 2), ("real_exp_ch_emb_1", 1)])
+def test_full_size_other_configs(built_library, name, bs):
+    """BASELINE configs[2..4] shapes at full size: finite, deterministic, linear in the signal head."""
+    cfg = get_config(name)
+    cls = avr_b200.AVRModel if cfg["model_class"] == "AVRModel" else avr_b200.AVRModel_complex
+    native = cls(cfg["model"]).to(DEV)
+    with torch.no_grad():
+        for m in native.modules():
+            if isinstance(m, avr_b200.Encoding):
+                m.params.normal_(0, 0.1)
+    r = cfg["render"]
+    ren = avr_b200.AVRRender(native, **r)
+    gen = torch.Generator().manual_seed(3)
+    c = (r["xyz_min"] + r["xyz_max"]) / 2
+    rx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 1.5).to(DEV)
+    tx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 1.5).to(DEV)
+    dtx = torch.nn.functional.normalize(torch.randn(bs, 3, generator=gen), dim=-1).to(DEV) if cfg["model_class"] != "AVRModel" else None
+    ch = torch.arange(bs, device=DEV) % 8
+    azi = torch.rand(r["n_azi"], generator=gen)
+    T = cfg["model"]["signal_output_dim"]
+    grads = []
+    for _ in range(2):
+        native.zero_grad(set_to_none=True)
+        out = ren(rx, tx, dtx, ch_idx=ch, azi_rand=azi)
+        assert out.shape == (bs, T // 2 + 1, 2) and bool(torch.isfinite(out).all()) and float(out.abs().max()) > 0
+        out.square().sum().backward()
+        grads.append([p.grad.clone() for p in native.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b) and bool(torch.isfinite(a).all())
+    o, i = native._model_signal.shapes[-1]
+    with torch.no_grad():
+        native._model_signal.params[-o * i:] *= -0.5
+        out2 = ren(rx, tx, dtx, ch_idx=ch, azi_rand=azi)
+    assert rel_l2(out2, -0.5 * out) < 1e-5
