@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libavr_b200
 
 GEMM_RELU, GEMM_ACCUM, GEMM_MASK, GEMM_RELU_A, GEMM_RELU_B = 1, 2, 4, 8, 16
 K_CONTIG, I_CONTIG = 0, 1
-UMMA_RELU, UMMA_ACCUM, UMMA_MASK, UMMA_OUT_F32, UMMA_DUAL_RELU = 1, 2, 4, 8, 16
+UMMA_RELU, UMMA_ACCUM, UMMA_MASK, UMMA_OUT_F32, UMMA_DUAL_RELU, UMMA_BITS = 1, 2, 4, 8, 16, 32
 
 
 class AVRLibraryError(RuntimeError):
@@ -56,7 +56,7 @@ SIGNATURES = {
     "avr_planes_split": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.c_int, _P, _I64,
-                                   _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int, _P]),
+                                   _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_tn_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P, _I64,
                                    C.c_int, _P]),

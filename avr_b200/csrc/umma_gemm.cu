@@ -25,7 +25,7 @@
 
 namespace avr {
 
-enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16 };
+enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32 };
 
 struct UmmaParams {
     int M, N, K;            // K-major: rows, cols, reduction.  MN-major: A extent, B extent, reduction (points)
@@ -36,7 +36,8 @@ struct UmmaParams {
     int flags;
     __nv_bfloat16* c; long long ldc, c_plane;          // plane-pair output
     __nv_bfloat16* c2; long long ldc2, c2_plane;       // second (ReLU'd) plane-pair output
-    const __nv_bfloat16* mask; long long ldmask;       // hi plane of the activation whose sign gates the result
+    const uint32_t* mask; long long ldmask;            // ReLU bitmask of the gating activation: bit (col % 32) of word [row][col / 32]
+    uint32_t* bits; long long ldbits;                  // bitmask (value > 0) written by the forward epilogue (UF_BITS)
     float* c32; long long ldc32;                       // fp32 output / split-K partials
 };
 
@@ -72,6 +73,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -131,10 +140,41 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* base, long long pla
     if (nplanes == 3) *reinterpret_cast<uint4*>(base + 2 * plane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+constexpr int EPI_COLS = 32;                              // columns per staged chunk (64-byte rows, SWIZZLE_64B)
+constexpr uint32_t EPI_PLANE_BYTES = 32 * EPI_COLS * 2;   // 32 rows x 64 B = 2 KB per plane per warp
+
+// Split 32 fp32 values of one row into nplanes bf16 planes and write them into the warp's staging tiles
+// ([plane][32 rows][64 B], 64-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)).
+__device__ __forceinline__ void stage_planes32(uint32_t stage, int lane, const float* v, bool relu, int nplanes) {
+    const uint32_t row_base = stage + (uint32_t)lane * 64u;
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t h[4], m[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a = v[8 * q + 2 * i], b = v[8 * q + 2 * i + 1];
+            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+            const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+            const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
+            h[i] = pack2(ah, bh);
+            m[i] = pack2(am, bm);
+            l[i] = pack2(__float2bfloat16_rn(ar - __bfloat162float(am)), __float2bfloat16_rn(br - __bfloat162float(bm)));
+        }
+        const uint32_t off = row_base + (((uint32_t)q ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off + EPI_PLANE_BYTES), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
+        if (nplanes == 3)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off + 2 * EPI_PLANE_BYTES), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool MN_MAJOR>
 __global__ void __launch_bounds__(UTHREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,6 +188,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
     const uint32_t smem_base = smem_u32(smem);
+    // epilogue staging: 4 warps x 3 planes x 2 KB, 1024-byte aligned, after the barrier block
+    const uint32_t epi_base = (smem_base + (uint32_t)p.stages * stage_bytes + 256u + 1023u) & ~1023u;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -263,16 +305,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long row = m0 + lane_grp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
             const bool row_ok = row < p.M;
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);                                       // warp-collective: outside the row guard
-                if (!row_ok) continue;
+            if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
+                // fp32 outputs (split-K partials, the 16-wide density head): direct stores
+                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);                                   // warp-collective: outside the row guard
+                    if (!row_ok) continue;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const long long col = n0 + c0 + 8 * h;
-                    if (col >= p.N) continue;
-                    float* x = v + 8 * h;
-                    if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
+                    for (int h = 0; h < 2; ++h) {
+                        const long long col = n0 + c0 + 8 * h;
+                        if (col >= p.N) continue;
+                        float* x = v + 8 * h;
                         float* dst = MN_MAJOR ? p.c32 + ((long long)split * p.M + row) * p.N + col : p.c32 + row * p.ldc32 + col;
                         if (!MN_MAJOR && (p.flags & UF_ACCUM)) {
                             const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
@@ -284,37 +327,88 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                        continue;
+                    }
+                }
+            } else {
+                // plane outputs: registers -> swizzled smem staging -> TMA bulk tensor store (full lines, rows and
+                // columns outside the output window are clipped by the tensor map)
+                const uint32_t stage = epi_base + (uint32_t)lane_grp * (3u * EPI_PLANE_BYTES);
+                // ReLU gating: one 32-bit word per 32-column chunk, all words of the tile row fetched up front
+                uint32_t mw[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    mw[j] = 0xffffffffu;
+                    const long long col = n0 + 32 * j;
+                    if ((p.flags & UF_MASK) && row_ok && 32 * j < p.BN && col < p.N) mw[j] = __ldg(p.mask + row * p.ldmask + (col >> 5));
+                }
+                for (int c0 = 0; c0 < p.BN && n0 + c0 < p.N; c0 += EPI_COLS) {
+                    float v[32];
+                    {
+                        float t0[16], t1[16];
+                        tmem_ld16(taddr + c0, t0);
+                        if (c0 + 16 < p.BN) {
+                            tmem_ld16(taddr + c0 + 16, t1);
+                        } else {                                                // ragged last chunk (single-tile N only):
+#pragma unroll                                                                  // the missing columns lie outside the
+                            for (int i = 0; i < 16; ++i) t1[i] = 0.f;           // output window and are clipped by TMA
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
                     }
                     if (p.flags & UF_MASK) {
-                        const uint4 m = *reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col);
-                        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                        uint32_t word = 0;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (!(bf_lo(mw[i]) > 0.f)) x[2 * i] = 0.f;
-                            if (!(bf_hi(mw[i]) > 0.f)) x[2 * i + 1] = 0.f;
-                        }
+                        for (int j = 0; j < 8; ++j) word = (c0 >> 5) == j ? mw[j] : word;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = (word >> i) & 1u ? v[i] : 0.f;
                     }
-                    __nv_bfloat16* dst = p.c + row * p.ldc + col;
+                    if (p.flags & UF_BITS) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) word |= (v[i] > 0.f ? 1u : 0u) << i;
+                        if (row_ok) p.bits[row * p.ldbits + ((n0 + c0) >> 5)] = word;
+                    }
                     if (p.flags & UF_ACCUM) {
-                        const uint4 oh = *reinterpret_cast<const uint4*>(dst), ol = *reinterpret_cast<const uint4*>(dst + p.c_plane);
-                        uint4 o3 = make_uint4(0u, 0u, 0u, 0u);
-                        if (p.nc == 3) o3 = *reinterpret_cast<const uint4*>(dst + 2 * p.c_plane);
-                        const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
-                        const uint32_t tw[4] = {o3.x, o3.y, o3.z, o3.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            x[2 * i] += bf_lo(hw[i]) + (bf_lo(lw[i]) + bf_lo(tw[i]));
-                            x[2 * i + 1] += bf_hi(hw[i]) + (bf_hi(lw[i]) + bf_hi(tw[i]));
+                        for (int q = 0; q < 4; ++q) {
+                            const long long col = n0 + c0 + 8 * q;
+                            float* x = v + 8 * q;
+                            if (!row_ok || col >= p.N) continue;
+                            {
+                                const __nv_bfloat16* dst = p.c + row * p.ldc + col;
+                                const uint4 oh = *reinterpret_cast<const uint4*>(dst), ol = *reinterpret_cast<const uint4*>(dst + p.c_plane);
+                                uint4 o3 = make_uint4(0u, 0u, 0u, 0u);
+                                if (p.nc == 3) o3 = *reinterpret_cast<const uint4*>(dst + 2 * p.c_plane);
+                                const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
+                                const uint32_t tw[4] = {o3.x, o3.y, o3.z, o3.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    x[2 * i] += bf_lo(hw[i]) + (bf_lo(lw[i]) + bf_lo(tw[i]));
+                                    x[2 * i + 1] += bf_hi(hw[i]) + (bf_hi(lw[i]) + bf_hi(tw[i]));
+                                }
+                            }
                         }
                     }
-                    store_planes8(dst, p.c_plane, x, (p.flags & UF_RELU) != 0, p.nc);
-                    if (p.flags & UF_DUAL_RELU) store_planes8(p.c2 + row * p.ldc2 + col, p.c2_plane, x, true, p.nc);
+                    const int n_out = (p.flags & UF_DUAL_RELU) ? 2 : 1;
+                    for (int o = 0; o < n_out; ++o) {
+                        if (lane == 0) tma_store_wait_read();                   // staging tiles free again?
+                        __syncwarp();
+                        stage_planes32(stage, lane, v, o == 1 || (p.flags & UF_RELU), p.nc);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const CUtensorMap* map = o == 0 ? &tmC : &tmC2;
+                            for (int pl = 0; pl < p.nc; ++pl)
+                                tma_store_3d(map, stage + pl * EPI_PLANE_BYTES, n0 + c0, m0 + lane_grp * 32, pl);
+                            tma_store_commit();
+                        }
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (lane == 0) tma_store_wait_all();                                   // smem must outlive the bulk stores
     }
     tc_fence_before();
     __syncthreads();
@@ -351,15 +445,31 @@ __global__ void planes_merge_kernel(const __nv_bfloat16* __restrict__ in, long l
     out[r * ld + c] = __bfloat162float(in[r * ldp + c]) + tail;
 }
 
-// dW[m, n] (+)= sum over splits of partial[split][m][n]   (fixed order)
-__global__ void umma_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, long long N,
-                                          float* __restrict__ C, long long ldc, int accumulate) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * N) return;
-    const long long r = i / N, c = i - r * N;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[((long long)z * M + r) * N + c];
-    C[r * ldc + c] = accumulate ? C[r * ldc + c] + s : s;
+// dW[m, n] (+)= sum over splits of partial[split][m][n].  One warp per float4 of the output: lane l adds the
+// splits l, l+32, ... in order, then a fixed butterfly combines the lanes -> deterministic and latency-tolerant.
+__global__ void __launch_bounds__(256)
+umma_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, long long N, float* __restrict__ C,
+                          long long ldc, int accumulate) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nq = N / 4;
+    if (q >= M * nq) return;
+    const long long r = q / nq, c = (q - r * nq) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = lane; z < splits; z += 32) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + ((long long)z * M + r) * N + c));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+    }
+    if (lane == 0) {
+        float* dst = C + r * ldc + c;
+        if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(dst); s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+        *reinterpret_cast<float4*>(dst) = s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -382,7 +492,7 @@ static EncodeTiledFn encode_fn() {
 
 // plane-pair tensor [2][rows][ld] of bf16, logical width `cols`; box = (64 cols, box_rows, 2 planes), 128B swizzle
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
-                    int box_rows, int nplanes) {
+                    int box_rows, int nplanes, bool store_map = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(AVR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld * 2) % 16 || (plane * 2) % 16)
@@ -390,9 +500,11 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nplanes};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)nplanes};
+    if (store_map) { box[0] = EPI_COLS; box[1] = 32; box[2] = 1; }          // epilogue staging tile: 32 rows x 64 B
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, store_map ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     store_map ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(AVR_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
     return AVR_OK;
@@ -405,7 +517,7 @@ static int pick_bn(long long N, int max_bn = 256) {
     // e.g. 1600: prefer the multiple of 16 <= max_bn that wastes least
     int best = max_bn;
     long long best_waste = ceil_div(N, max_bn) * max_bn - N;
-    for (int bn = max_bn - 16; bn >= max_bn / 2; bn -= 16) {
+    for (int bn = max_bn - 32; bn >= max_bn / 2; bn -= 32) {      // multiples of 32: staged epilogue chunks never straddle tiles
         long long waste = ceil_div(N, bn) * bn - N;
         if (waste < best_waste) { best = bn; best_waste = waste; }
     }
@@ -459,8 +571,8 @@ AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
-                             int64_t c2_plane, const void* mask_hi, int64_t ldmask, float* c_f32, int64_t ldc32,
-                             int device, void* stream) {
+                             int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
+                             int64_t ldbits, float* c_f32, int64_t ldc32, int device, void* stream) {
     AVR_REQUIRE(a_planes && b_planes, "null operand");
     AVR_REQUIRE((a_nplanes == 2 || a_nplanes == 3) && (b_nplanes == 2 || b_nplanes == 3) && (c_nplanes == 2 || c_nplanes == 3),
                 "plane counts must be 2 or 3");
@@ -470,7 +582,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     AVR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension overflow");
     if (flags & UF_OUT_F32) AVR_REQUIRE(c_f32 && ldc32 % 4 == 0 && aligned16(c_f32), "fp32 output must be 16-byte aligned");
     else AVR_REQUIRE(c_planes && ldc % 8 == 0 && c_plane % 8 == 0 && aligned16(c_planes), "plane output must be 16-byte aligned");
-    if (flags & UF_MASK) AVR_REQUIRE(mask_hi && ldmask % 8 == 0 && aligned16(mask_hi), "mask must be 16-byte aligned");
+    if (flags & UF_MASK) AVR_REQUIRE(mask_bits && ldmask * 32 >= N, "MASK needs a bitmask with >= N/32 words per row");
+    if (flags & UF_BITS) AVR_REQUIRE(bits_out && ldbits * 32 >= N && !(flags & UF_OUT_F32), "BITS needs a bitmask output");
     if (flags & UF_DUAL_RELU) AVR_REQUIRE(c2_planes && ldc2 % 8 == 0 && c2_plane % 8 == 0 && aligned16(c2_planes), "second output misaligned");
     AVR_ENTER(device);
     if (M == 0) return AVR_OK;
@@ -484,20 +597,29 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.flags = flags;
     p.c = (__nv_bfloat16*)c_planes; p.ldc = ldc; p.c_plane = c_plane;
     p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
-    p.mask = (const __nv_bfloat16*)mask_hi; p.ldmask = ldmask;
+    p.mask = mask_bits; p.ldmask = ldmask;
+    p.bits = bits_out; p.ldbits = ldbits;
     p.c32 = c_f32; p.ldc32 = ldc32;
     const uint32_t stage_bytes = (uint32_t)p.na * A_PLANE_BYTES + (uint32_t)p.nb * (uint32_t)p.BN * 128u;
-    p.stages = (int)((220 * 1024) / stage_bytes);
+    const uint32_t epi_bytes = 4u * 3u * EPI_PLANE_BYTES + 1024u;
+    p.stages = (int)((226 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-    CUtensorMap ta, tb;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + epi_bytes;
+    CUtensorMap ta, tb, tc, tc2;
     if (int rc = make_map(&ta, a_planes, M, K, lda, a_plane, UM, p.na)) return rc;
     if (int rc = make_map(&tb, b_planes, N, K, ldb, b_plane, p.BN, p.nb)) return rc;
+    tc = ta; tc2 = ta;
+    if (!(flags & UF_OUT_F32)) {
+        if (int rc = make_map(&tc, c_planes, M, N, ldc, c_plane, 32, p.nc, true)) return rc;
+        tc2 = tc;
+        if (flags & UF_DUAL_RELU)
+            if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, p.nc, true)) return rc;
+    }
     AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
-    umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, p);
+    umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, tc, tc2, p);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
@@ -506,7 +628,7 @@ AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     const int bn = pick_bn(N);
     const int64_t tiles = ceil_div(M, UM) * ceil_div(N, bn);
-    int64_t splits = ceil_div(2 * 148, tiles);
+    int64_t splits = 148 / tiles;                  // one wave: tiles * splits <= number of SMs
     const int64_t max_by_k = ceil_div(K, 1024);
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
@@ -542,7 +664,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.stages = (int)((220 * 1024) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + 2048;
     cudaStream_t st = (cudaStream_t)stream;
     if (K > 0) {
         CUtensorMap ta, tb;
@@ -551,13 +673,14 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
         AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
-        umma_gemm_kernel<true><<<grid, UTHREADS, smem, st>>>(ta, tb, p);
+        umma_gemm_kernel<true><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, p);
         AVR_LAUNCH_CHECK();
     } else {
         p.k_splits = 0;
     }
-    umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>((const float*)workspace, p.k_splits, M, N, c,
-                                                                            ldc, accumulate);
+    AVR_REQUIRE(ldc % 4 == 0 && aligned16(c), "C must be 16-byte aligned");
+    umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * (N / 4) * 32, 256), 256, 0, st>>>((const float*)workspace, p.k_splits, M,
+                                                                                       N, c, ldc, accumulate);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

@@ -83,29 +83,34 @@ class FusedRenderTC(torch.autograd.Function):
         if delay_slot:
             _, _, _, delay = ops.sample_points(geom, rays_o, pos_tx, dirs, d_vals, want_pts=False)
         w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_PLANES)
-        acts_enc, h = [], x0
+        acts_enc, bits_enc, h = [], [], x0
         for li in range(len(w_enc) - 1):
             y = PlanePair.empty(n_rows, w_enc[li].rows, dev, n=FWD_PLANES)
-            ops.umma_nt(h, w_enc[li], ops.UMMA_RELU, y)
+            bits = ops.relu_bits_empty(n_rows, y.cols, dev)
+            ops.umma_nt(h, w_enc[li], ops.UMMA_RELU, y, bits_out=bits)
             acts_enc.append(y)
+            bits_enc.append(bits)
             h = y
         # sigma_feat lands directly in the signal network's input buffer (no concat)
         sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev, n=FWD_PLANES)
         feat_win = sig_in.window(0, feat_dim)
+        bits_feat = ops.relu_bits_empty(n_rows, feat_dim, dev)               # (sigma_feat > 0)
         if plan["sig_relu_feat"]:
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win)               # both consumers read relu(feat)
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat)        # both consumers read relu(feat)
             dec_in = feat_win
         else:
             dec_in = PlanePair.empty(n_rows, feat_dim, dev, n=FWD_PLANES)
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_in)  # raw feat + relu(feat)
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_in, bits_out=bits_feat)   # raw feat + relu(feat)
 
         # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
         w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_PLANES)
-        acts_dec, h = [], dec_in
+        acts_dec, bits_dec, h = [], [], dec_in
         for li in range(len(w_dec) - 1):
             y = PlanePair.empty(n_rows, w_dec[li].rows, dev, n=FWD_PLANES)
-            ops.umma_nt(h, w_dec[li], ops.UMMA_RELU, y)
+            bits = ops.relu_bits_empty(n_rows, y.cols, dev)
+            ops.umma_nt(h, w_dec[li], ops.UMMA_RELU, y, bits_out=bits)
             acts_dec.append(y)
+            bits_dec.append(bits)
             h = y
         dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
         ops.umma_nt(h, w_dec[-1], ops.UMMA_OUT_F32, c_f32=dec_out)
@@ -116,11 +121,13 @@ class FusedRenderTC(torch.autograd.Function):
                   params_of, [])
         sig_mats = sig_net.matrices(params_of(sig_net))
         w_sig = _weight_planes(sig_net, params_of(sig_net), False, FWD_PLANES)[:-1]
-        acts_sig, h = [], sig_in
+        acts_sig, bits_sig, h = [], [], sig_in
         for li in range(len(w_sig)):
             y = PlanePair.empty(n_rows, w_sig[li].rows, dev, n=FWD_PLANES)
-            ops.umma_nt(h, w_sig[li], ops.UMMA_RELU, y)
+            bits = ops.relu_bits_empty(n_rows, y.cols, dev) if li < len(w_sig) - 1 else None   # last one is read by collapse
+            ops.umma_nt(h, w_sig[li], ops.UMMA_RELU, y, bits_out=bits)
             acts_sig.append(y)
+            bits_sig.append(bits)
             h = y
         sort = ops.delay_sort(geom, delay, w)
         y_t = ops.collapse_fwd(geom, h, sort, sig_mats[-1])
@@ -130,7 +137,8 @@ class FusedRenderTC(torch.autograd.Function):
             ctx.plan, ctx.geom, ctx.tables, ctx.tspan = plan, geom, tables, tspan
             ctx.small_in = small_in
             ctx.bufs = dict(x0=x0, acts_enc=acts_enc, sig_in=sig_in, dec_in=dec_in, acts_dec=acts_dec, dec_out=dec_out,
-                            acts_sig=acts_sig, sort=sort)
+                            acts_sig=acts_sig, sort=sort, bits_enc=bits_enc, bits_dec=bits_dec, bits_sig=bits_sig,
+                            bits_feat=bits_feat)
             ctx.save_for_backward(rays_o, dirs, *params)
         return out
 
@@ -149,7 +157,7 @@ class FusedRenderTC(torch.autograd.Function):
         ws_bytes = max(ops.umma_tn_workspace_bytes(o, i, n_rows) for n in (enc_net, dec_net, sig_net) for (o, i) in n.shapes)
         ws = torch.empty(max(4, ws_bytes // 4), device=dev)
 
-        def hidden_backward(net, g, acts, first_input, g_flat):
+        def hidden_backward(net, g, acts, bits, first_input, g_flat):
             """Back-propagate through layers len(acts)..1 of ``net`` given g = d(pre-activation of the last
             hidden layer); fills the weight gradients of layers >= 1 and of layer 0; returns g at layer 0."""
             wt = _weight_planes(net, pmap[id(net)], True, BWD_PLANES)
@@ -158,7 +166,7 @@ class FusedRenderTC(torch.autograd.Function):
                 x = acts[li - 1]
                 ops.umma_tn(g, x, d_mats[li], ws)
                 gx = PlanePair.empty(n_rows, x.cols, dev)
-                ops.umma_nt(g, wt[li], ops.UMMA_MASK, gx, mask=x)
+                ops.umma_nt(g, wt[li], ops.UMMA_MASK, gx, mask=bits[li - 1])
                 g = gx
             ops.umma_tn(g, first_input, d_mats[0], ws)
             return g, wt, d_mats
@@ -175,12 +183,12 @@ class FusedRenderTC(torch.autograd.Function):
 
         # ---- signal network hidden layers ----------------------------------------------------------------
         sig_in, dec_in = B["sig_in"], B["dec_in"]
-        g, wt_sig, _ = hidden_backward(sig_net, g, B["acts_sig"], sig_in, g_sig)
+        g, wt_sig, _ = hidden_backward(sig_net, g, B["acts_sig"], B["bits_sig"], sig_in, g_sig)
         grads[id(sig_net)] = g_sig
         d_feat = PlanePair.empty(n_rows, feat_dim, dev)
         wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
         if plan["sig_relu_feat"]:
-            ops.umma_nt(g, wt0.row_window(0, feat_dim), ops.UMMA_MASK, d_feat, mask=dec_in)
+            ops.umma_nt(g, wt0.row_window(0, feat_dim), ops.UMMA_MASK, d_feat, mask=B["bits_feat"])
         else:
             ops.umma_nt(g, wt0.row_window(0, feat_dim), 0, d_feat)
         tail_w = sig_net.in_pad - feat_dim
@@ -203,10 +211,10 @@ class FusedRenderTC(torch.autograd.Function):
             x = acts_dec[li - 1]
             ops.umma_tn(g, x, d_dec_mats[li], ws)
             gx = PlanePair.empty(n_rows, x.cols, dev)
-            ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=x)
+            ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=B["bits_dec"][li - 1])
             g = gx
         ops.umma_tn(g, dec_in, d_dec_mats[0], ws)
-        ops.umma_nt(g, wt_dec[0], ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=dec_in)      # d_feat += relu'(feat) * ...
+        ops.umma_nt(g, wt_dec[0], ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=B["bits_feat"])   # d_feat += relu'(feat) * ...
         grads[id(dec_net)] = g_dec
 
         # ---- sigma encoder -----------------------------------------------------------------------------------
@@ -219,7 +227,7 @@ class FusedRenderTC(torch.autograd.Function):
             x = acts_enc[li - 1]
             ops.umma_tn(g, x, d_enc_mats[li], ws)
             gx = PlanePair.empty(n_rows, x.cols, dev)
-            ops.umma_nt(g, wt_enc[li], ops.UMMA_MASK, gx, mask=x)
+            ops.umma_nt(g, wt_enc[li], ops.UMMA_MASK, gx, mask=B["bits_enc"][li - 1])
             g = gx
         x0 = B["x0"]
         ops.umma_tn(g, x0, d_enc_mats[0], ws)

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import (GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG,  # noqa: F401
-                   UMMA_ACCUM, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta, RenderGeom)
+                   UMMA_ACCUM, UMMA_BITS, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta, RenderGeom)
 
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream ----------------------
 PROFILE = None          # set to a list to collect (name, work, unit, start_event, end_event)
@@ -301,20 +301,33 @@ def planes_merge(pp: PlanePair):
     return out
 
 
-def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask: PlanePair = None,
-            c_f32=None):
-    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane pair or (UMMA_OUT_F32) an fp32 tensor."""
+def relu_bits_empty(rows, cols, device):
+    """Storage of a ReLU bitmask: int32 ``[rows, ceil(cols/32) rounded up to 4 words]``."""
+    words = ((cols + 31) // 32 + 3) // 4 * 4
+    return torch.empty(rows, words, dtype=torch.int32, device=device)
+
+
+def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask=None, c_f32=None,
+            bits_out=None):
+    """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane set or (UMMA_OUT_F32) an fp32 tensor.
+
+    ``mask`` (with UMMA_MASK): int32 bitmask ``[M, words]`` gating the product (ReLU backward);
+    ``bits_out``: if given, the bitmask ``(C > 0)`` is written (forward ReLU layers).
+    """
     dev, st = _ctx(a)
     M, K, N = a.rows, a.cols, b.rows
     assert b.cols == K, (b.cols, K)
     none = C.c_void_p(None)
+    if bits_out is not None:
+        flags |= UMMA_BITS
     with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
         _lib.check(_lib.load().avr_umma_gemm_nt(
             M, N, K, a.ptr, a.ld, a.plane, a.n, b.ptr, b.ld, b.plane, b.n, flags,
             c.ptr if c is not None else none, c.ld if c is not None else 0, c.plane if c is not None else 0,
             c.n if c is not None else 2,
             c2.ptr if c2 is not None else none, c2.ld if c2 is not None else 0, c2.plane if c2 is not None else 0,
-            mask.ptr if mask is not None else none, mask.ld if mask is not None else 0,
+            _p(mask, torch.int32), mask.stride(0) if mask is not None else 0,
+            _p(bits_out, torch.int32), bits_out.stride(0) if bits_out is not None else 0,
             _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0, dev, st), "avr_umma_gemm_nt")
 
 

@@ -155,9 +155,10 @@ AVR_API int avr_gemm(int layout_a, int layout_b, int64_t M, int64_t N, int64_t K
 enum {
     AVR_UMMA_RELU = 1,        /* out = max(out, 0)                                                   */
     AVR_UMMA_ACCUM = 2,       /* out += previous contents of the output                              */
-    AVR_UMMA_MASK = 4,        /* product *= (mask_hi[i,j] > 0)   (ReLU backward; before ACCUM)       */
+    AVR_UMMA_MASK = 4,        /* product *= bit (j % 32) of mask_bits[i][j / 32]  (ReLU backward; before ACCUM) */
     AVR_UMMA_OUT_F32 = 8,     /* write fp32 c_f32 instead of a plane pair                            */
-    AVR_UMMA_DUAL_RELU = 16   /* additionally write max(out,0) as a second plane pair (c2)           */
+    AVR_UMMA_DUAL_RELU = 16,  /* additionally write max(out,0) as a second plane pair (c2)           */
+    AVR_UMMA_BITS = 32        /* additionally write the bitmask (out > 0) to bits_out (1 bit / element) */
 };
 /* fp32 [rows, cols] (ld) <-> plane pair; transpose != 0 writes planes[c, r] = x[r, c]; relu != 0 clamps */
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
@@ -169,8 +170,8 @@ AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
-                             int64_t c2_plane, const void* mask_hi, int64_t ldmask, float* c_f32, int64_t ldc32,
-                             int device, void* stream);
+                             int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
+                             int64_t ldbits, float* c_f32, int64_t ldc32, int device, void* stream);
 /* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane pairs; weight gradients).
  * fp32 output; deterministic split-K over the points through `workspace`. */
 AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);

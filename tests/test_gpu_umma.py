@@ -41,16 +41,28 @@ def test_umma_nt_plain(built_library, M, N, K):
     assert rel_l2(c32, ref) < TOL
 
 
+def _pack_bits(pos):
+    """bool [M, N] -> int32 bitmask [M, words] (bit j%32 of word j//32), as the forward epilogue writes it."""
+    M, N = pos.shape
+    words = ((N + 31) // 32 + 3) // 4 * 4
+    padded = torch.zeros(M, words * 32, dtype=torch.int64)
+    padded[:, :N] = pos.long()
+    w = (padded.view(M, words, 32) << torch.arange(32)).sum(-1)
+    return (w - ((w >> 31) << 32)).to(torch.int32).to(DEV)
+
+
 def test_umma_nt_epilogues(built_library):
     g = torch.Generator().manual_seed(5)
     M, N, K = 1500, 256, 128
     A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
     act, old = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
-    a, b, mask = _pp(A), _pp(B), _pp(act)
+    a, b, mask = _pp(A), _pp(B), _pack_bits(act > 0)
     ref = A.double() @ B.double().t()
     c = PlanePair.empty(M, N, DEV)
-    ops.umma_nt(a, b, ops.UMMA_RELU, c)
+    bits = ops.relu_bits_empty(M, N, DEV)
+    ops.umma_nt(a, b, ops.UMMA_RELU, c, bits_out=bits)
     assert rel_l2(ops.planes_merge(c), ref.clamp_min(0)) < TOL
+    assert torch.equal(bits[:, : N // 32].cpu(), _pack_bits(ops.planes_merge(c).cpu() > 0)[:, : N // 32].cpu())
     c, c2 = PlanePair.empty(M, N, DEV), PlanePair.empty(M, N, DEV)
     ops.umma_nt(a, b, ops.UMMA_DUAL_RELU, c, c2)
     assert rel_l2(ops.planes_merge(c), ref) < TOL and rel_l2(ops.planes_merge(c2), ref.clamp_min(0)) < TOL
