@@ -61,12 +61,11 @@ SIGNATURES = {
     "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P, _I64,
                                    C.c_int, _P]),
     "avr_delay_sort": (C.c_int, [_G, _P, _P, _P, _P, _P, C.c_int, _P]),
-    "avr_collapse_fwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, C.c_int, _P]),
-    "avr_collapse_bwd_data": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _P,
-                                        C.c_int, _P]),
-    "avr_collapse_bwd_weight_workspace_bytes": (_I64, [_G, _I32, _I32]),
-    "avr_collapse_bwd_weight": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _I64, C.c_int, _I32, _P, _I64,
-                                          C.c_int, _P]),
+    "avr_collapse_prefix_bytes": (_I64, [_G, _I32, _I32]),
+    "avr_collapse_suffix_bytes": (_I64, [_G, _I32, _I32]),
+    "avr_collapse_fwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _I32, _P, _I64, _P, C.c_int, _P]),
+    "avr_collapse_bwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _I64, _P, _I64, _I64,
+                                   _P, _P, _I64, C.c_int, C.c_int, _P]),
     "avr_rows_broadcast": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I64, _I64, _I32, _I32, C.c_int, _P]),
     "avr_rows_reduce_workspace_bytes": (_I64, [_G, _I32, C.c_int]),
     "avr_rows_reduce": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, C.c_int, _P, _P, _I64, C.c_int, _P]),

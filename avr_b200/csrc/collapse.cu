@@ -1,40 +1,40 @@
 // Output layer of the signal network fused with the time-domain ray reduction ("collapse").
 //
-// Reference: signal = H @ W_out^T (model.py:231, the 512 -> T layer, 215 GFLOP / receiver at simu), then
+// Reference: signal = H @ W_out^T (model.py:231, the width -> T layer, 215 GFLOP / receiver at simu), then
 // renderer.py:86-90,115-118 masks every row with (t >= delay) and sums the rays with the compositing weights:
 //
 //      y[b,s,t] = sum_r w[b,r,s] * [t >= delay[b,r,s]] * ( H[b,r,s,:] . W_out[t,:] )
 //
-// Sorting the rays of one (b,s) by delay makes the masked sum a PREFIX sum:
+// Sorting the rays of one cell (b,s) by delay makes the masked sum a PREFIX sum:
 //
 //      G[b,s,t,:] = sum_{r : delay <= t} w * H[b,r,s,:]          y[b,s,t] = G[b,s,t,:] . W_out[t,:]
 //
 // i.e. S*T*width MACs per receiver instead of R*S*T*width (R = 2050 x fewer), and the [bs,R,S,T] signal
 // tensor (0.84 GB / receiver) and its gradient never exist.  Exact in real arithmetic; in fp32 only the
-// summation order differs from the reference.  The backward uses the mirrored SUFFIX sum
-//      g[b,s,d,:] = sum_{t >= d} d_y[b,s,t] * W_out[t,:]         d_H = w * g[delay],   d_w = H . g[delay]
-// and  d_W_out[t,:] = sum_{b,s} d_y[b,s,t] * G[b,s,t,:].
+// summation order differs from the reference.  G only changes for t in [dmin, dmax) of the cell -- at most
+// `tspan` <= 2*far*fs/speed steps -- so its snapshots fit in a small workspace, which the backward reuses:
+//      d_W_out[t,:] = sum_cells d_y[t] * G[t,:]
+//      g[d,:]       = sum_{t >= d} d_y[t] * W_out[t,:]      (suffix sum)      d_H = w * g[delay],  d_w = H . g[delay]
 //
-// One CTA per (b,s); each thread owns 4 hidden columns; the delay-sorted ray list lives in shared memory;
-// activation rows (bf16 hi/lo plane pairs) are fetched 8 rays at a time to keep loads in flight.
+// Kernels
+//   delay_sort      stable counting sort of the rays of every cell by delay (one warp per cell)
+//   prefix_walk     one CTA per cell walks its sorted rays; activation rows (bf16 hi/mid planes) are prefetched
+//                   32 rays deep with cp.async; every thread owns 4 hidden columns; snapshots of G are written
+//                   whenever t advances (stores only: no load latency on the critical path)
+//   prefix_dot      y = G . W_out rows, one warp per (cell, t)
+//   suffix_walk     g snapshots for d in [dmin, dmax], thread per 4 columns, W_out rows streamed with unrolled loads
+//   ray_backward    parallel over the sorted rays: d_H planes and d_w
+//   dwout_reduce    d_W_out from the saved G snapshots, fixed summation order over the cells
 #include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace avr {
-
-constexpr int COL_PER_THREAD = 4;
-constexpr int RAY_BATCH = 8;
 
 struct Planes {
     const __nv_bfloat16* p;
     long long ld, plane;
 };
 
-__device__ __forceinline__ void ld_row4(const Planes& a, long long row, int c, uint2& hi, uint2& lo) {
-    const __nv_bfloat16* q = a.p + row * a.ld + c;
-    hi = __ldg(reinterpret_cast<const uint2*>(q));
-    lo = __ldg(reinterpret_cast<const uint2*>(q + a.plane));
-}
 __device__ __forceinline__ void unpack4(uint2 hi, uint2 lo, float (&x)[4]) {
     x[0] = __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
     x[1] = __uint_as_float(hi.x & 0xFFFF0000u) + __uint_as_float(lo.x & 0xFFFF0000u);
@@ -46,6 +46,26 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b, uint32_t& lo_out)
     const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
     lo_out = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
     return (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// workspace kept from forward to backward: G snapshots [cells][tspan][width], G_tot [cells][width], range [cells][2]
+struct PrefixWs {
+    float* gp;
+    float* gtot;
+    int* range;
+};
+__host__ __device__ inline PrefixWs carve_prefix(void* ws, long long cells, int tspan, int width) {
+    PrefixWs w;
+    w.gp = reinterpret_cast<float*>(ws);
+    w.gtot = w.gp + cells * tspan * width;
+    w.range = reinterpret_cast<int*>(w.gtot + cells * width);
+    return w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -101,133 +121,135 @@ delay_sort_kernel(const Geom geo, const int* __restrict__ delay, const float* __
     }
 }
 
-// shared-memory staging of one (b,s)'s sorted ray list
-struct RayList {
-    int* ord;
-    int* del;
-    float* wgt;
-};
-__device__ __forceinline__ RayList stage_rays(unsigned char* smem, int R, long long base, const int* order, const int* sdelay,
-                                              const float* sw) {
-    RayList L;
-    L.ord = reinterpret_cast<int*>(smem);
-    L.del = L.ord + R;
-    L.wgt = reinterpret_cast<float*>(L.del + R);
-    for (int k = threadIdx.x; k < R; k += blockDim.x) {
-        L.ord[k] = __ldg(order + base + k);
-        L.del[k] = __ldg(sdelay + base + k);
-        L.wgt[k] = __ldg(sw + base + k);
-    }
-    return L;
-}
+// ------------------------------------------------------------------------------------------------
+// prefix walk: G snapshots of one cell
+// ------------------------------------------------------------------------------------------------
+constexpr int PW_GROUP = 4;        // rays per cp.async group
+constexpr int PW_NGROUPS = 8;      // groups in flight  -> 32 rays deep
+constexpr int PW_MAX_THREADS = 256;
 
-// ------------------------------------------------------------------------------------------------
-// forward: y[b,s,t] = G[b,s,t,:] . W_out[t,:]
-// MODE 0: write y.   MODE 1 (weight gradient, first pass): write P[t - dmin, :] = d_y[t] * G[t,:] for
-// t in [dmin, dmax), G_tot and the (dmin, dmax) range instead.
-// ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256)
-collapse_fwd_kernel(const Geom geo, const Planes act, int width, const int* __restrict__ order,
-                    const int* __restrict__ sdelay, const float* __restrict__ sw, const float* __restrict__ w_out,
-                    long long ldw, float* __restrict__ y, const float* __restrict__ d_y, float* __restrict__ P,
-                    float* __restrict__ gtot, int* __restrict__ range, int tspan) {
+__global__ void __launch_bounds__(PW_MAX_THREADS)
+prefix_walk_kernel(const Geom geo, const Planes act, int width, const int* __restrict__ order,
+                   const int* __restrict__ sdelay, const float* __restrict__ sw, PrefixWs ws, int tspan) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int bsi = blockIdx.x, b = bsi / geo.S, s = bsi - b * geo.S;
-    const int R = geo.R, T = geo.T;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int c = threadIdx.x * COL_PER_THREAD;
+    const int cell = blockIdx.x, b = cell / geo.S, s = cell - b * geo.S;
+    const int R = geo.R;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int c = tid * 4;
     const bool col_ok = c < width;
-    RayList L = stage_rays(smem, R, (long long)bsi * R, order, sdelay, sw);
-    float* partial = reinterpret_cast<float*>(smem + (size_t)R * 12);       // MODE 0: [n_warps][T]
-    float* dy_s = partial;                                                   // MODE 1: [T]
-    if (MODE == 0) {
-        for (int i = threadIdx.x; i < n_warps * T; i += blockDim.x) partial[i] = 0.f;
-    } else {
-        for (int i = threadIdx.x; i < T; i += blockDim.x) dy_s[i] = __ldg(d_y + (long long)bsi * T + i);
+    int* l_ord = reinterpret_cast<int*>(smem);
+    int* l_del = l_ord + R;
+    float* l_w = reinterpret_cast<float*>(l_del + R);
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem + (((size_t)R * 12 + 15) & ~(size_t)15));
+    const long long lbase = (long long)cell * R;
+    for (int k = tid; k < R; k += nthr) {
+        l_ord[k] = __ldg(order + lbase + k);
+        l_del[k] = __ldg(sdelay + lbase + k);
+        l_w[k] = __ldg(sw + lbase + k);
     }
     __syncthreads();
-    const int dmin = L.del[0], dmax = L.del[R - 1];
+    const int dmin = l_del[0], dmax = l_del[R - 1];
+    const bool overflow = (dmax - dmin) > tspan;
+    const int n_groups = (R + PW_GROUP - 1) / PW_GROUP;
+
+    auto issue = [&](int g) {
+        if (g < n_groups && col_ok) {
+#pragma unroll
+            for (int j = 0; j < PW_GROUP; ++j) {
+                const int k = g * PW_GROUP + j;
+                if (k < R) {
+                    const long long row = ((long long)b * R + l_ord[k]) * geo.S + s;
+                    const __nv_bfloat16* q = act.p + row * act.ld + c;
+                    const uint32_t dst = ring + (uint32_t)((((g % PW_NGROUPS) * PW_GROUP + j) * nthr + tid) * 16);
+                    cp_async8(dst, q);
+                    cp_async8(dst + 8, q + act.plane);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    for (int g = 0; g < PW_NGROUPS; ++g) issue(g);
+
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int t = dmin;
-    bool overflow = false;
-    if (MODE == 1) overflow = (dmax - dmin) > tspan;
-
-    auto emit = [&](int tt) {
-        if (MODE == 0) {
-            float p = 0.f;
-            if (col_ok) {
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(w_out + (long long)tt * ldw + c));
-                p = acc[0] * wv.x + acc[1] * wv.y + acc[2] * wv.z + acc[3] * wv.w;
+    float* gp_cell = ws.gp + (long long)cell * tspan * width;
+    for (int g = 0; g < n_groups; ++g) {
+        cp_async_wait<PW_NGROUPS - 1>();
+#pragma unroll
+        for (int j = 0; j < PW_GROUP; ++j) {
+            const int k = g * PW_GROUP + j;
+            if (k >= R) break;
+            const int d = l_del[k];
+            while (t < d) {                                    // snapshot G(t) for every t the prefix is constant over
+                if (col_ok && !overflow)
+                    *reinterpret_cast<float4*>(gp_cell + (long long)(t - dmin) * width + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                ++t;
             }
-            p = warp_sum(p);
-            if (lane == 0) partial[warp * T + tt] = p;
-        } else if (col_ok && !overflow) {
-            const float g = dy_s[tt];
-            *reinterpret_cast<float4*>(P + ((long long)bsi * tspan + (tt - dmin)) * width + c) =
-                make_float4(g * acc[0], g * acc[1], g * acc[2], g * acc[3]);
-        }
-    };
-
-    for (int k0 = 0; k0 < R; k0 += RAY_BATCH) {
-        uint2 hi[RAY_BATCH], lo[RAY_BATCH];
+            if (col_ok) {
+                const uint32_t src = ring + (uint32_t)((((g % PW_NGROUPS) * PW_GROUP + j) * nthr + tid) * 16);
+                uint2 hi, lo;
+                asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "r"(src));
+                asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "r"(src + 8));
+                float x[4];
+                unpack4(hi, lo, x);
+                const float wk = l_w[k];
 #pragma unroll
-        for (int j = 0; j < RAY_BATCH; ++j) {
-            hi[j] = make_uint2(0u, 0u); lo[j] = make_uint2(0u, 0u);
-            if (k0 + j < R && col_ok) ld_row4(act, ((long long)b * R + L.ord[k0 + j]) * geo.S + s, c, hi[j], lo[j]);
+                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wk, x[i], acc[i]);
+            }
         }
-#pragma unroll
-        for (int j = 0; j < RAY_BATCH; ++j) {
-            if (k0 + j >= R) break;
-            const int d = L.del[k0 + j];
-            while (t < d) { emit(t); ++t; }
-            float x[4];
-            unpack4(hi[j], lo[j], x);
-            const float wk = L.wgt[k0 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fmaf(wk, x[i], acc[i]);
-        }
+        issue(g + PW_NGROUPS);
     }
-    if (MODE == 0) {
-        for (; t < T; ++t) emit(t);                                          // t >= dmax: every ray contributes
-        __syncthreads();
-        for (int i = threadIdx.x; i < T; i += blockDim.x) {
-            float v = 0.f;
-            for (int wq = 0; wq < n_warps; ++wq) v += partial[wq * T + i];
-            y[(long long)bsi * T + i] = v;
+    cp_async_wait<0>();
+    if (col_ok) {
+        const float poison = overflow ? __uint_as_float(0x7fc00000u) : 0.f;
+        *reinterpret_cast<float4*>(ws.gtot + (long long)cell * width + c) =
+            make_float4(acc[0] + poison, acc[1] + poison, acc[2] + poison, acc[3] + poison);
+    }
+    if (tid == 0) { ws.range[2 * cell] = dmin; ws.range[2 * cell + 1] = dmax; }
+}
+
+// y[cell, t] = G(cell, t) . W_out[t, :]      grid (cells, t-chunks), one warp per t
+__global__ void __launch_bounds__(128)
+prefix_dot_kernel(const Geom geo, int width, PrefixWs ws, int tspan, const float* __restrict__ w_out, long long ldw,
+                  float* __restrict__ y, int t_per_block) {
+    const int cell = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int dmin = ws.range[2 * cell], dmax = ws.range[2 * cell + 1];
+    const int t_beg = blockIdx.y * t_per_block, t_end = min(geo.T, t_beg + t_per_block);
+    const float* gp_cell = ws.gp + (long long)cell * tspan * width;
+    const float* gt = ws.gtot + (long long)cell * width;
+    for (int t = t_beg + warp; t < t_end; t += n_warps) {
+        float p = 0.f;
+        if (t >= dmin) {
+            const float* g = t < dmax ? gp_cell + (long long)(t - dmin) * width : gt;
+            const float* wr = w_out + (long long)t * ldw;
+            for (int c = lane * 4; c < width; c += 128) {
+                const float4 a = *reinterpret_cast<const float4*>(g + c);
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
+                p = fmaf(a.x, wv.x, p); p = fmaf(a.y, wv.y, p); p = fmaf(a.z, wv.z, p); p = fmaf(a.w, wv.w, p);
+            }
         }
-    } else {
-        if (col_ok) {
-            const float poison = overflow ? __uint_as_float(0x7fc00000u) : 0.f;
-            *reinterpret_cast<float4*>(gtot + (long long)bsi * width + c) =
-                make_float4(acc[0] + poison, acc[1] + poison, acc[2] + poison, acc[3] + poison);
-        }
-        if (threadIdx.x == 0) { range[2 * bsi] = dmin; range[2 * bsi + 1] = dmax; }
+        p = warp_sum(p);
+        if (lane == 0) y[(long long)cell * geo.T + t] = p;
     }
 }
 
-// d_W_out[t, c] (+)= sum_{b,s} ( t < dmin ? 0 : t < dmax ? P[b,s,t-dmin,c] : d_y[b,s,t] * G_tot[b,s,c] )
-__global__ void collapse_dw_reduce_kernel(const Geom geo, int width, const float* __restrict__ d_y, const float* __restrict__ P,
-                                          const float* __restrict__ gtot, const int* __restrict__ range, int tspan,
-                                          float* __restrict__ d_wout, long long ldw, int accumulate) {
+// d_W_out[t, c] (+)= sum_cells d_y[cell, t] * G(cell, t)[c]      (fixed order over the cells)
+__global__ void dwout_reduce_kernel(const Geom geo, int width, const float* __restrict__ d_y, PrefixWs ws, int tspan,
+                                    float* __restrict__ d_wout, long long ldw, int accumulate) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int wq = width / 4;
     if (q >= geo.T * wq) return;
     const int t = q / wq, c = (q - t * wq) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n = geo.bs * geo.S;
-    for (int i = 0; i < n; ++i) {                                            // fixed order: deterministic
-        const int dmin = __ldg(range + 2 * i), dmax = __ldg(range + 2 * i + 1);
+    for (int i = 0; i < n; ++i) {
+        const int dmin = __ldg(ws.range + 2 * i), dmax = __ldg(ws.range + 2 * i + 1);
         if (t < dmin) continue;
-        float4 a;
-        if (t < dmax) {
-            a = *reinterpret_cast<const float4*>(P + ((long long)i * tspan + (t - dmin)) * width + c);
-        } else {
-            const float g = __ldg(d_y + (long long)i * geo.T + t);
-            const float4 gt = *reinterpret_cast<const float4*>(gtot + (long long)i * width + c);
-            a = make_float4(g * gt.x, g * gt.y, g * gt.z, g * gt.w);
-        }
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        const float g = __ldg(d_y + (long long)i * geo.T + t);
+        const float* src = t < dmax ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c : ws.gtot + (long long)i * width + c;
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        v.x = fmaf(g, a.x, v.x); v.y = fmaf(g, a.y, v.y); v.z = fmaf(g, a.z, v.z); v.w = fmaf(g, a.w, v.w);
     }
     float* dst = d_wout + (long long)t * ldw + c;
     if (accumulate) {
@@ -237,82 +259,103 @@ __global__ void collapse_dw_reduce_kernel(const Geom geo, int width, const float
     *reinterpret_cast<float4*>(dst) = v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// backward (data): d_H[row,:] = (H > 0) * w * g[delay],  d_w = H . g[delay],  g = suffix sum over t
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-collapse_bwd_data_kernel(const Geom geo, const Planes act, int width, const int* __restrict__ order,
-                         const int* __restrict__ sdelay, const float* __restrict__ sw, const float* __restrict__ w_out,
-                         long long ldw, const float* __restrict__ d_y, __nv_bfloat16* __restrict__ d_act, long long ld_d,
-                         long long d_plane, float* __restrict__ d_w) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int bsi = blockIdx.x, b = bsi / geo.S, s = bsi - b * geo.S;
-    const int R = geo.R, T = geo.T;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int c = threadIdx.x * COL_PER_THREAD;
-    const bool col_ok = c < width;
-    RayList L = stage_rays(smem, R, (long long)bsi * R, order, sdelay, sw);
-    float* dy_s = reinterpret_cast<float*>(smem + (size_t)R * 12);          // [T]
-    float* dwp = dy_s + T;                                                   // [n_warps][R]
-    for (int i = threadIdx.x; i < T; i += blockDim.x) dy_s[i] = __ldg(d_y + (long long)bsi * T + i);
-    __syncthreads();
+// g snapshots: gs[cell][d - dmin][c] = sum_{t >= d} d_y[cell, t] * W_out[t, c],  d in [dmin, dmax]
+// grid (cells, column groups of 128), 32 threads x 4 columns
+__global__ void __launch_bounds__(32)
+suffix_walk_kernel(const Geom geo, int width, const int* __restrict__ range, int tspan, const float* __restrict__ w_out,
+                   long long ldw, const float* __restrict__ d_y, float* __restrict__ gs) {
+    extern __shared__ float dy_s[];
+    const int cell = blockIdx.x;
+    const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
+    const int T = geo.T;
+    for (int i = threadIdx.x; i < T; i += 32) dy_s[i] = __ldg(d_y + (long long)cell * T + i);
+    __syncwarp();
+    if (c >= width) return;
+    const int dmin = range[2 * cell], dmax = range[2 * cell + 1];
+    if (dmax - dmin > tspan) return;                           // poisoned in the forward pass already
     float g[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wc = w_out + c;
     int t = T - 1;
-    for (int k1 = R; k1 > 0; k1 -= RAY_BATCH) {
-        uint2 hi[RAY_BATCH], lo[RAY_BATCH];
-#pragma unroll
-        for (int j = 0; j < RAY_BATCH; ++j) {
-            const int k = k1 - 1 - j;
-            hi[j] = make_uint2(0u, 0u); lo[j] = make_uint2(0u, 0u);
-            if (k >= 0 && col_ok) ld_row4(act, ((long long)b * R + L.ord[k]) * geo.S + s, c, hi[j], lo[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < RAY_BATCH; ++j) {
-            const int k = k1 - 1 - j;
-            if (k < 0) break;
-            const int d = L.del[k];
-            while (t >= d) {                                                 // include every t >= delay
-                if (col_ok) {
-                    const float gy = dy_s[t];
-                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w_out + (long long)t * ldw + c));
-                    g[0] = fmaf(gy, wv.x, g[0]); g[1] = fmaf(gy, wv.y, g[1]);
-                    g[2] = fmaf(gy, wv.z, g[2]); g[3] = fmaf(gy, wv.w, g[3]);
-                }
-                --t;
+#pragma unroll 8
+    for (; t > dmax; --t) {
+        const float gy = dy_s[t];
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wc + (long long)t * ldw));
+        g[0] = fmaf(gy, wv.x, g[0]); g[1] = fmaf(gy, wv.y, g[1]); g[2] = fmaf(gy, wv.z, g[2]); g[3] = fmaf(gy, wv.w, g[3]);
+    }
+    float* gs_cell = gs + (long long)cell * (tspan + 1) * width + c;
+#pragma unroll 4
+    for (; t >= dmin; --t) {
+        const float gy = dy_s[t];
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wc + (long long)t * ldw));
+        g[0] = fmaf(gy, wv.x, g[0]); g[1] = fmaf(gy, wv.y, g[1]); g[2] = fmaf(gy, wv.z, g[2]); g[3] = fmaf(gy, wv.w, g[3]);
+        *reinterpret_cast<float4*>(gs_cell + (long long)(t - dmin) * width) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+}
+
+// d_H[row,:] = (H > 0) * w * g[delay],  d_w[row] = H[row,:] . g[delay]; one warp per 32 consecutive sorted rays
+constexpr int RB_RAYS = 32;
+__global__ void __launch_bounds__(128)
+ray_backward_kernel(const Geom geo, const Planes act, int width, const int* __restrict__ order,
+                    const int* __restrict__ sdelay, const float* __restrict__ sw, const int* __restrict__ range, int tspan,
+                    const float* __restrict__ gs, __nv_bfloat16* __restrict__ d_act, long long ld_d, long long d_plane,
+                    float* __restrict__ d_w) {
+    const int cell = blockIdx.x, b = cell / geo.S, s = cell - b * geo.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = (blockIdx.y * (blockDim.x >> 5) + warp) * RB_RAYS;
+    const int R = geo.R;
+    if (k0 >= R) return;
+    const int dmin = range[2 * cell];
+    const bool poisoned = (range[2 * cell + 1] - dmin) > tspan;
+    const long long lbase = (long long)cell * R;
+    const int my_k = k0 + lane;
+    const int my_ord = my_k < R ? __ldg(order + lbase + my_k) : 0;
+    const int my_del = my_k < R ? __ldg(sdelay + lbase + my_k) : 0;
+    const float my_w = my_k < R ? __ldg(sw + lbase + my_k) : 0.f;
+    const float* gs_cell = gs + (long long)cell * (tspan + 1) * width;
+    const int n_here = min(RB_RAYS, R - k0);
+    for (int c0 = 0; c0 < width; c0 += 128) {                  // 128 columns per pass: 4 per lane
+        const int c = c0 + lane * 4;
+        const bool col_ok = c < width;
+        int d_prev = -1;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < n_here; ++j) {
+            const int r = __shfl_sync(0xffffffffu, my_ord, j);
+            const int d = __shfl_sync(0xffffffffu, my_del, j);
+            const float wk = __shfl_sync(0xffffffffu, my_w, j);
+            if (d != d_prev && col_ok) {
+                g = poisoned ? make_float4(__uint_as_float(0x7fc00000u), 0.f, 0.f, 0.f)
+                             : *reinterpret_cast<const float4*>(gs_cell + (long long)(d - dmin) * width + c);
+                d_prev = d;
             }
-            float x[4];
-            unpack4(hi[j], lo[j], x);
-            const float wk = L.wgt[k];
-            float dot = x[0] * g[0] + x[1] * g[1] + x[2] * g[2] + x[3] * g[3];
-            dot = warp_sum(dot);
-            if (lane == 0) dwp[warp * R + k] = dot;
+            const long long row = ((long long)b * R + r) * geo.S + s;
+            float dot = 0.f;
             if (col_ok) {
-                const long long row = ((long long)b * R + L.ord[k]) * geo.S + s;
+                const __nv_bfloat16* q = act.p + row * act.ld + c;
+                const uint2 hi = __ldg(reinterpret_cast<const uint2*>(q)), lo = __ldg(reinterpret_cast<const uint2*>(q + act.plane));
+                float x[4];
+                unpack4(hi, lo, x);
+                dot = x[0] * g.x + x[1] * g.y + x[2] * g.z + x[3] * g.w;
                 uint32_t l0, l1;
-                const uint32_t h0 = pack_bf2(x[0] > 0.f ? wk * g[0] : 0.f, x[1] > 0.f ? wk * g[1] : 0.f, l0);
-                const uint32_t h1 = pack_bf2(x[2] > 0.f ? wk * g[2] : 0.f, x[3] > 0.f ? wk * g[3] : 0.f, l1);
+                const uint32_t h0 = pack_bf2(x[0] > 0.f ? wk * g.x : 0.f, x[1] > 0.f ? wk * g.y : 0.f, l0);
+                const uint32_t h1 = pack_bf2(x[2] > 0.f ? wk * g.z : 0.f, x[3] > 0.f ? wk * g.w : 0.f, l1);
                 *reinterpret_cast<uint2*>(d_act + row * ld_d + c) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(d_act + row * ld_d + c + d_plane) = make_uint2(l0, l1);
             }
+            dot = warp_sum(dot);
+            if (lane == 0) {
+                if (c0 == 0) d_w[row] = dot;
+                else d_w[row] += dot;                          // same thread, fixed order: deterministic
+            }
         }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < R; k += blockDim.x) {
-        float v = 0.f;
-        for (int wq = 0; wq < n_warps; ++wq) v += dwp[wq * R + k];
-        d_w[((long long)b * R + L.ord[k]) * geo.S + s] = v;
-    }
-}
-
-static int collapse_threads(int width) {
-    int th = (width / COL_PER_THREAD + 31) / 32 * 32;
-    return th < 32 ? 32 : th;
 }
 
 static int check_collapse(const Geom& geo, int width, const void* act, long long ld, long long plane) {
-    if (width % 8 != 0 || width <= 0 || width > 1024) return fail(AVR_ERR_UNSUPPORTED, "collapse: hidden width %d must be a multiple of 8 and <= 1024", width);
+    if (width % 8 != 0 || width <= 0 || width > 4 * PW_MAX_THREADS)
+        return fail(AVR_ERR_UNSUPPORTED, "collapse: hidden width %d must be a multiple of 8 and <= %d", width, 4 * PW_MAX_THREADS);
     if (geo.R < 1 || geo.T < 1) return fail(AVR_ERR_INVALID, "collapse: empty geometry");
-    if (!act || ld % 4 != 0 || plane % 4 != 0 || (reinterpret_cast<uintptr_t>(act) & 7u)) return fail(AVR_ERR_INVALID, "collapse: activation planes must be 8-byte aligned");
+    if (!act || ld % 4 != 0 || plane % 4 != 0 || (reinterpret_cast<uintptr_t>(act) & 7u))
+        return fail(AVR_ERR_INVALID, "collapse: activation planes must be 8-byte aligned");
     return AVR_OK;
 }
 
@@ -336,81 +379,76 @@ AVR_API int avr_delay_sort(const avr_render_geom* geom, const int32_t* delay, co
     return AVR_OK;
 }
 
-AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
-                             const float* w_out, int64_t ldw, float* y, int device, void* stream) {
-    AVR_REQUIRE(geom && order && sdelay && sw && w_out && y, "null pointer");
-    AVR_ENTER(device);
-    const Geom geo = make_geom(geom);
-    if (int rc = check_collapse(geo, width, act_planes, ld_act, act_plane)) return rc;
-    AVR_REQUIRE(ldw % 4 == 0 && aligned16(w_out), "W_out must be 16-byte aligned");
-    const int n = geo.bs * geo.S;
-    if (n == 0) return AVR_OK;
-    const int threads = collapse_threads(width);
-    const size_t smem = (size_t)geo.R * 12 + (size_t)(threads / 32) * geo.T * sizeof(float);
-    AVR_CUDA(cudaFuncSetAttribute(collapse_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane};
-    collapse_fwd_kernel<0><<<n, threads, smem, (cudaStream_t)stream>>>(geo, act, width, order, sdelay, sw, w_out, ldw, y,
-                                                                     nullptr, nullptr, nullptr, nullptr, 0);
-    AVR_LAUNCH_CHECK();
-    return AVR_OK;
-}
-
-AVR_API int avr_collapse_bwd_data(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                                  int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
-                                  const float* w_out, int64_t ldw, const float* d_y, void* d_act_planes, int64_t ld_d,
-                                  int64_t d_plane, float* d_w, int device, void* stream) {
-    AVR_REQUIRE(geom && order && sdelay && sw && w_out && d_y && d_act_planes && d_w, "null pointer");
-    AVR_ENTER(device);
-    const Geom geo = make_geom(geom);
-    if (int rc = check_collapse(geo, width, act_planes, ld_act, act_plane)) return rc;
-    AVR_REQUIRE(ldw % 4 == 0 && aligned16(w_out), "W_out must be 16-byte aligned");
-    AVR_REQUIRE(ld_d % 4 == 0 && d_plane % 4 == 0 && (reinterpret_cast<uintptr_t>(d_act_planes) & 7u) == 0, "d_act misaligned");
-    const int n = geo.bs * geo.S;
-    if (n == 0) return AVR_OK;
-    const int threads = collapse_threads(width);
-    const size_t smem = (size_t)geo.R * 12 + (size_t)geo.T * 4 + (size_t)(threads / 32) * geo.R * 4;
-    AVR_CUDA(cudaFuncSetAttribute(collapse_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane};
-    collapse_bwd_data_kernel<<<n, threads, smem, (cudaStream_t)stream>>>(geo, act, width, order, sdelay, sw, w_out, ldw, d_y,
-                                                                       (__nv_bfloat16*)d_act_planes, ld_d, d_plane, d_w);
-    AVR_LAUNCH_CHECK();
-    return AVR_OK;
-}
-
-AVR_API int64_t avr_collapse_bwd_weight_workspace_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan) {
+AVR_API int64_t avr_collapse_prefix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan) {
     if (!geom) return 0;
     const int64_t n = (int64_t)geom->bs * geom->S;
     return (n * tspan * width + n * width) * (int64_t)sizeof(float) + n * 2 * (int64_t)sizeof(int) + 64;
 }
 
-// tspan: static bound on (max delay - min delay) within one (b,s); a violation poisons the result with NaN.
-AVR_API int avr_collapse_bwd_weight(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                                    int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
-                                    const float* d_y, float* d_wout, int64_t ldw, int accumulate, int32_t tspan,
-                                    void* workspace, int64_t workspace_bytes, int device, void* stream) {
-    AVR_REQUIRE(geom && order && sdelay && sw && d_y && d_wout && workspace, "null pointer");
+AVR_API int64_t avr_collapse_suffix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan) {
+    if (!geom) return 0;
+    return (int64_t)geom->bs * geom->S * (tspan + 1) * width * (int64_t)sizeof(float) + 64;
+}
+
+// y[bs,S,T] and the prefix workspace (kept by the caller for the backward pass).
+// tspan: static bound on (max delay - min delay) within one (b,s); a violation poisons the results with NaN.
+AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
+                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             const float* w_out, int64_t ldw, int32_t tspan, void* prefix_ws, int64_t prefix_bytes, float* y,
+                             int device, void* stream) {
+    AVR_REQUIRE(geom && order && sdelay && sw && w_out && y && prefix_ws, "null pointer");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     if (int rc = check_collapse(geo, width, act_planes, ld_act, act_plane)) return rc;
-    AVR_REQUIRE(tspan > 0 && workspace_bytes >= avr_collapse_bwd_weight_workspace_bytes(geom, width, tspan), "workspace too small");
-    AVR_REQUIRE(ldw % 4 == 0 && aligned16(d_wout) && aligned16(workspace), "buffers must be 16-byte aligned");
-    const int64_t n = (int64_t)geo.bs * geo.S;
-    if (n == 0) return AVR_OK;
-    float* P = (float*)workspace;
-    float* gtot = P + n * tspan * width;
-    int* range = (int*)(gtot + n * width);
-    const int threads = collapse_threads(width);
-    const size_t smem = (size_t)geo.R * 12 + (size_t)geo.T * 4;
+    AVR_REQUIRE(ldw % 4 == 0 && aligned16(w_out) && aligned16(prefix_ws), "W_out / workspace must be 16-byte aligned");
+    AVR_REQUIRE(tspan > 0 && prefix_bytes >= avr_collapse_prefix_bytes(geom, width, tspan), "prefix workspace too small");
+    const int cells = geo.bs * geo.S;
+    if (cells == 0) return AVR_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    AVR_CUDA(cudaFuncSetAttribute(collapse_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const PrefixWs ws = carve_prefix(prefix_ws, cells, tspan, width);
+    const int threads = ((width / 4 + 31) / 32) * 32;
+    const size_t smem = (((size_t)geo.R * 12 + 15) & ~(size_t)15) + (size_t)PW_GROUP * PW_NGROUPS * threads * 16;
+    AVR_CUDA(cudaFuncSetAttribute(prefix_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane};
-    collapse_fwd_kernel<1><<<(unsigned)n, threads, smem, st>>>(geo, act, width, order, sdelay, sw, nullptr, 0, nullptr, d_y, P,
-                                                             gtot, range, tspan);
+    prefix_walk_kernel<<<cells, threads, smem, st>>>(geo, act, width, order, sdelay, sw, ws, tspan);
     AVR_LAUNCH_CHECK();
+    const int t_chunks = 8;
+    const int t_per_block = (int)ceil_div(geo.T, t_chunks);
+    prefix_dot_kernel<<<dim3(cells, t_chunks), 128, 0, st>>>(geo, width, ws, tspan, w_out, ldw, y, t_per_block);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+// d_act (plane pair, gradient w.r.t. the pre-activation), d_w[bs,R,S] and d_W_out[T,width] (+)=
+AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
+                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             const float* w_out, int64_t ldw, const float* d_y, int32_t tspan, const void* prefix_ws,
+                             void* suffix_ws, int64_t suffix_bytes, void* d_act_planes, int64_t ld_d, int64_t d_plane,
+                             float* d_w, float* d_wout, int64_t ld_dw, int accumulate, int device, void* stream) {
+    AVR_REQUIRE(geom && order && sdelay && sw && w_out && d_y && prefix_ws && suffix_ws && d_act_planes && d_w && d_wout,
+                "null pointer");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    if (int rc = check_collapse(geo, width, act_planes, ld_act, act_plane)) return rc;
+    AVR_REQUIRE(ldw % 4 == 0 && ld_dw % 4 == 0 && aligned16(w_out) && aligned16(d_wout) && aligned16(suffix_ws), "16-byte alignment");
+    AVR_REQUIRE(ld_d % 4 == 0 && d_plane % 4 == 0 && (reinterpret_cast<uintptr_t>(d_act_planes) & 7u) == 0, "d_act misaligned");
+    AVR_REQUIRE(tspan > 0 && suffix_bytes >= avr_collapse_suffix_bytes(geom, width, tspan), "suffix workspace too small");
+    const int cells = geo.bs * geo.S;
+    if (cells == 0) return AVR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const PrefixWs ws = carve_prefix(const_cast<void*>(prefix_ws), cells, tspan, width);
+    float* gs = (float*)suffix_ws;
     const int total = geo.T * (width / 4);
-    collapse_dw_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(geo, width, d_y, P, gtot, range, tspan, d_wout, ldw,
-                                                                 accumulate);
+    dwout_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(geo, width, d_y, ws, tspan, d_wout, ld_dw, accumulate);
+    AVR_LAUNCH_CHECK();
+    const size_t smem = (size_t)geo.T * sizeof(float);
+    AVR_CUDA(cudaFuncSetAttribute(suffix_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    suffix_walk_kernel<<<dim3(cells, (unsigned)ceil_div(width, 128)), 32, smem, st>>>(geo, width, ws.range, tspan, w_out, ldw, d_y, gs);
+    AVR_LAUNCH_CHECK();
+    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane};
+    const int rays_per_block = 4 * RB_RAYS;
+    ray_backward_kernel<<<dim3(cells, (unsigned)ceil_div(geo.R, rays_per_block)), 128, 0, st>>>(
+        geo, act, width, order, sdelay, sw, ws.range, tspan, gs, (__nv_bfloat16*)d_act_planes, ld_d, d_plane, d_w);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

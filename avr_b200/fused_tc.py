@@ -130,14 +130,14 @@ class FusedRenderTC(torch.autograd.Function):
             bits_sig.append(bits)
             h = y
         sort = ops.delay_sort(geom, delay, w)
-        y_t = ops.collapse_fwd(geom, h, sort, sig_mats[-1])
+        y_t, prefix = ops.collapse_fwd(geom, h, sort, sig_mats[-1], tspan)
         out = ops.spectrum_fwd(geom, y_t, tables)
 
         if any(ctx.needs_input_grad[8:]):
             ctx.plan, ctx.geom, ctx.tables, ctx.tspan = plan, geom, tables, tspan
             ctx.small_in = small_in
             ctx.bufs = dict(x0=x0, acts_enc=acts_enc, sig_in=sig_in, dec_in=dec_in, acts_dec=acts_dec, dec_out=dec_out,
-                            acts_sig=acts_sig, sort=sort, bits_enc=bits_enc, bits_dec=bits_dec, bits_sig=bits_sig,
+                            acts_sig=acts_sig, sort=sort, prefix=prefix, bits_enc=bits_enc, bits_dec=bits_dec, bits_sig=bits_sig,
                             bits_feat=bits_feat)
             ctx.save_for_backward(rays_o, dirs, *params)
         return out
@@ -178,8 +178,8 @@ class FusedRenderTC(torch.autograd.Function):
         d_sig_mats = sig_net.matrices(g_sig)
         h_last = B["acts_sig"][-1]
         g = PlanePair.empty(n_rows, h_last.cols, dev)
-        d_w = ops.collapse_bwd_data(geom, h_last, B["sort"], sig_mats[-1], d_y, g)
-        ops.collapse_bwd_weight(geom, h_last, B["sort"], d_y, d_sig_mats[-1], ctx.tspan)
+        d_w = ops.collapse_bwd(geom, h_last, B["sort"], sig_mats[-1], d_y, ctx.tspan, B["prefix"], g, d_sig_mats[-1])
+        B["prefix"] = None
 
         # ---- signal network hidden layers ----------------------------------------------------------------
         sig_in, dec_in = B["sig_in"], B["dec_in"]

@@ -23,10 +23,11 @@ PROFILE = None          # set to a list to collect (name, work, unit, start_even
 
 
 class _timed:
-    __slots__ = ("name", "work", "unit", "start")
+    __slots__ = ("name", "work", "unit", "start", "executed")
 
-    def __init__(self, name, work, unit):
+    def __init__(self, name, work, unit, executed=None):
         self.name, self.work, self.unit, self.start = name, work, unit, None
+        self.executed = work if executed is None else executed      # e.g. tensor-pipe flops incl. the 3 / 6 products
 
     def __enter__(self):
         if PROFILE is not None:
@@ -38,7 +39,7 @@ class _timed:
         if self.start is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            PROFILE.append((self.name, self.work, self.unit, self.start, end))
+            PROFILE.append((self.name, self.work, self.unit, self.start, end, self.executed))
         return False
 
 
@@ -320,7 +321,8 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
     none = C.c_void_p(None)
     if bits_out is not None:
         flags |= UMMA_BITS
-    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
+    products = 6 if (a.n == 3 and b.n == 3) else 3
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * products):
         _lib.check(_lib.load().avr_umma_gemm_nt(
             M, N, K, a.ptr, a.ld, a.plane, a.n, b.ptr, b.ld, b.plane, b.n, flags,
             c.ptr if c is not None else none, c.ld if c is not None else 0, c.plane if c is not None else 0,
@@ -340,7 +342,7 @@ def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
     dev, st = _ctx(a)
     K, M, N = a.rows, a.cols, b.cols
     assert b.rows == K
-    with _timed("umma_gemm", 2.0 * M * N * K, "flop"):
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop", 6.0 * M * N * K):
         _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, _p(c_f32),
                                                 c_f32.stride(0), 1 if accumulate else 0,
                                                 C.c_void_p(workspace.data_ptr()),
@@ -451,40 +453,33 @@ def collapse_tspan(render_cfg) -> int:
     return int(math.ceil(2.0 * float(render_cfg["far"]) * float(render_cfg["fs"]) / float(render_cfg["speed"]))) + 4
 
 
-def collapse_fwd(g, act: PlanePair, sort, w_out):
+def collapse_fwd(g, act: PlanePair, sort, w_out, tspan):
+    """-> (y[bs,S,T], prefix workspace to hand to ``collapse_bwd``)."""
     dev, st = _ctx(act)
     order, sdelay, sw = sort
     y = torch.empty(g.bs, g.S, g.T, device=act.device)
+    nbytes = int(_lib.load().avr_collapse_prefix_bytes(C.byref(g), act.cols, tspan))
+    prefix = torch.empty((nbytes + 3) // 4, device=act.device)
     n_pts = g.bs * g.R * g.S
     with _timed("collapse_fwd", float(n_pts) * act.cols * 4 + float(g.bs * g.S) * g.T * act.cols * 4, "byte"):
         _lib.check(_lib.load().avr_collapse_fwd(C.byref(g), act.ptr, act.ld, act.plane, act.cols, _p(order, torch.int32),
-                                                _p(sdelay, torch.int32), _p(sw), _p(w_out), w_out.stride(0), _p(y), dev, st),
-                   "avr_collapse_fwd")
-    return y
+                                                _p(sdelay, torch.int32), _p(sw), _p(w_out), w_out.stride(0), tspan,
+                                                _p(prefix), prefix.numel() * 4, _p(y), dev, st), "avr_collapse_fwd")
+    return y, prefix
 
 
-def collapse_bwd_data(g, act: PlanePair, sort, w_out, d_y, d_act: PlanePair):
+def collapse_bwd(g, act: PlanePair, sort, w_out, d_y, tspan, prefix, d_act: PlanePair, d_wout, accumulate=False):
+    """Fills ``d_act`` (plane pair) and ``d_wout`` (fp32 ``[T, width]`` view); returns ``d_w[bs,R,S]``."""
     dev, st = _ctx(act)
     order, sdelay, sw = sort
     d_w = torch.empty(g.bs, g.R, g.S, device=act.device)
+    nbytes = int(_lib.load().avr_collapse_suffix_bytes(C.byref(g), act.cols, tspan))
+    suffix = torch.empty((nbytes + 3) // 4, device=act.device)
     n_pts = g.bs * g.R * g.S
-    with _timed("collapse_bwd_data", float(n_pts) * act.cols * 8 + float(g.bs * g.S) * g.T * act.cols * 4, "byte"):
-        _lib.check(_lib.load().avr_collapse_bwd_data(C.byref(g), act.ptr, act.ld, act.plane, act.cols,
-                                                     _p(order, torch.int32), _p(sdelay, torch.int32), _p(sw), _p(w_out),
-                                                     w_out.stride(0), _p(_dense(d_y)), d_act.ptr, d_act.ld, d_act.plane,
-                                                     _p(d_w), dev, st), "avr_collapse_bwd_data")
+    with _timed("collapse_bwd", float(n_pts) * act.cols * 8 + 2.0 * g.bs * g.S * g.T * act.cols * 4, "byte"):
+        _lib.check(_lib.load().avr_collapse_bwd(C.byref(g), act.ptr, act.ld, act.plane, act.cols, _p(order, torch.int32),
+                                                _p(sdelay, torch.int32), _p(sw), _p(w_out), w_out.stride(0),
+                                                _p(_dense(d_y)), tspan, _p(prefix), _p(suffix), suffix.numel() * 4,
+                                                d_act.ptr, d_act.ld, d_act.plane, _p(d_w), _p(d_wout), d_wout.stride(0),
+                                                1 if accumulate else 0, dev, st), "avr_collapse_bwd")
     return d_w
-
-
-def collapse_bwd_weight(g, act: PlanePair, sort, d_y, d_wout, tspan, accumulate=False):
-    dev, st = _ctx(act)
-    order, sdelay, sw = sort
-    nbytes = int(_lib.load().avr_collapse_bwd_weight_workspace_bytes(C.byref(g), act.cols, tspan))
-    ws = torch.empty((nbytes + 3) // 4, device=act.device)
-    n_pts = g.bs * g.R * g.S
-    with _timed("collapse_bwd_weight", float(n_pts) * act.cols * 4 + 2.0 * g.bs * g.S * tspan * act.cols * 4, "byte"):
-        _lib.check(_lib.load().avr_collapse_bwd_weight(C.byref(g), act.ptr, act.ld, act.plane, act.cols,
-                                                       _p(order, torch.int32), _p(sdelay, torch.int32), _p(sw),
-                                                       _p(_dense(d_y)), _p(d_wout), d_wout.stride(0),
-                                                       1 if accumulate else 0, tspan, C.c_void_p(ws.data_ptr()),
-                                                       ws.numel() * 4, dev, st), "avr_collapse_bwd_weight")

@@ -278,31 +278,34 @@ def run_native(args, cfg):
     if rank == 0:
         pk = peaks()
         per = {}
-        for name, work, unit, s, e in prof:
-            d = per.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0, "unit": unit})
-            d["ms"] += s.elapsed_time(e); d["work"] += work; d["n"] += 1
+        for name, work, unit, s, e, executed in prof:
+            d = per.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0, "unit": unit, "executed": 0.0})
+            d["ms"] += s.elapsed_time(e); d["work"] += work; d["n"] += 1; d["executed"] += executed
         kernels = {}
         for name, d in per.items():
             rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
             if d["unit"] == "flop":
                 kernels[name] = {"bound": "tensor", "achieved": rate / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
                                  "frac": rate / 1e12 / pk["tensor"], "launches_per_step": d["n"] / args.steps,
-                                 "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / ms}
+                                 "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / ms,
+                                 "tensor_pipe_tflops": d["executed"] / (d["ms"] * 1e-3) / 1e12,
+                                 "tensor_pipe_frac": d["executed"] / (d["ms"] * 1e-3) / 1e12 / pk["tensor"]}
             else:
                 kernels[name] = {"bound": "hbm", "achieved": rate / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": rate / 1e9 / pk["hbm"], "launches_per_step": d["n"] / args.steps,
                                  "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / ms}
         if os.environ.get("AVR_BENCH_DETAIL"):
             per_step = len(prof) // args.steps
-            for name, work, unit, s0, e0 in prof[-per_step:]:
+            for name, work, unit, s0, e0, _ex in prof[-per_step:]:
                 t = s0.elapsed_time(e0)
                 rate = work / (t * 1e-3) / (1e12 if unit == "flop" else 1e9)
                 sys.stderr.write(f"DETAIL {name:22s} {t:8.3f} ms  work {work:.3e} {unit}  {rate:8.1f} {'TFLOP/s' if unit == 'flop' else 'GB/s'}\n")
         dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
         roof = dict(kernels[dominant]) if dominant else {}
         roof.update({"kernel": dominant, "traffic": None, "peak_source": pk["src"],
-                     "note": "achieved = algorithmic flops (2MNK) or bytes (SURVEY 8d) of the timed launches / their "
-                             "CUDA-event time inside the timed region"})
+                     "note": "achieved = algorithmic flops (2MNK of the fp32-grade product) or bytes (SURVEY 8d) of the timed "
+                             "launches / their CUDA-event time inside the timed region; each algorithmic product costs 3 "
+                             "(backward) or 6 (forward) bf16 tcgen05 products, see tensor_pipe_*"})
         cpu = None
         if not args.no_cpu_baseline:
             v, dt, desc = time_cpu_oracle(cfg, steps=1, warmup=1, ray_div=(4, 2))

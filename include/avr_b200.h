@@ -186,20 +186,22 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
  *   avr_delay_sort: stable counting sort by delay -> order / sdelay / sw, each [bs,S,R]. */
 AVR_API int avr_delay_sort(const avr_render_geom* geom, const int32_t* delay, const float* w, int32_t* order,
                            int32_t* sdelay, float* sw, int device, void* stream);
+/* tspan: static bound on (max delay - min delay) inside one (b,s) (<= 2*far*fs/speed); a violation poisons the
+ * results with NaN instead of corrupting them.  The prefix workspace written by avr_collapse_fwd holds the
+ * G snapshots and is handed back to avr_collapse_bwd. */
+AVR_API int64_t avr_collapse_prefix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan);
+AVR_API int64_t avr_collapse_suffix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan);
 AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
                              int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
-                             const float* w_out, int64_t ldw, float* y, int device, void* stream);
-/* d_act = (H > 0) * w * g[delay] as a plane pair (gradient w.r.t. the pre-activation), d_w[bs,R,S] = H . g[delay] */
-AVR_API int avr_collapse_bwd_data(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                                  int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
-                                  const float* w_out, int64_t ldw, const float* d_y, void* d_act_planes, int64_t ld_d,
-                                  int64_t d_plane, float* d_w, int device, void* stream);
-/* d_W_out[T, width] (+)= sum_{b,s} d_y[b,s,t] G[b,s,t,:]; tspan >= max over (b,s) of (max delay - min delay) */
-AVR_API int64_t avr_collapse_bwd_weight_workspace_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan);
-AVR_API int avr_collapse_bwd_weight(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                                    int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
-                                    const float* d_y, float* d_wout, int64_t ldw, int accumulate, int32_t tspan,
-                                    void* workspace, int64_t workspace_bytes, int device, void* stream);
+                             const float* w_out, int64_t ldw, int32_t tspan, void* prefix_ws, int64_t prefix_bytes, float* y,
+                             int device, void* stream);
+/* d_act = (H > 0) * w * g[delay] as a plane pair (gradient w.r.t. the pre-activation), d_w[bs,R,S] = H . g[delay],
+ * d_W_out[T, width] (+)= sum_{b,s} d_y[b,s,t] G[b,s,t,:] */
+AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
+                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             const float* w_out, int64_t ldw, const float* d_y, int32_t tspan, const void* prefix_ws,
+                             void* suffix_ws, int64_t suffix_bytes, void* d_act_planes, int64_t ld_d, int64_t d_plane,
+                             float* d_w, float* d_wout, int64_t ld_dw, int accumulate, int device, void* stream);
 
 /* ---- broadcast inputs of the signal network (renderer.py:59-60; model.py:219-221) ------------
  * dst[n, col0:col0+w] = src[row(n), 0:w] with row(n) = r (per_receiver=0) or b (per_receiver=1). */

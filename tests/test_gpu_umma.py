@@ -142,15 +142,13 @@ def test_collapse_matches_literal_output_layer(built_library, bs, R, S, T, W):
     sd = sort[1].cpu()
     assert bool((sd[..., 1:] >= sd[..., :-1]).all())                      # sortedness
     assert torch.equal(torch.sort(sort[0].cpu(), dim=-1).values, torch.arange(R, dtype=torch.int32).expand(bs, S, R))
-    y = ops.collapse_fwd(geom, hp, sort, Wout.to(DEV))
+    y, prefix = ops.collapse_fwd(geom, hp, sort, Wout.to(DEV), tspan=T)
     assert rel_l2(y, y_ref) < 2e-6
     dH = PlanePair.empty(n, W, DEV)
-    d_w = ops.collapse_bwd_data(geom, hp, sort, Wout.to(DEV), dy.to(DEV), dH)
+    dW = torch.zeros(T, W + 8, device=DEV)
+    d_w = ops.collapse_bwd(geom, hp, sort, Wout.to(DEV), dy.to(DEV), T, prefix, dH, dW[:, :W])
     assert rel_l2(d_w, wd.grad) < 2e-6
     assert rel_l2(ops.planes_merge(dH), Hq.grad * (Hq.detach() > 0)) < 2e-5
-    dW = torch.zeros(T, W + 8, device=DEV)
-    ops.collapse_bwd_weight(geom, hp, sort, dy.to(DEV), dW[:, :W], tspan=T)
     assert rel_l2(dW[:, :W], Wd.grad) < 2e-6 and float(dW[:, W:].abs().max()) == 0
-    dW2 = torch.zeros(T, W, device=DEV)
-    ops.collapse_bwd_weight(geom, hp, sort, dy.to(DEV), dW2, tspan=3)     # violated bound must poison, not corrupt
-    assert bool(torch.isnan(dW2).any())
+    y2, prefix2 = ops.collapse_fwd(geom, hp, sort, Wout.to(DEV), tspan=3)     # violated bound must poison, not corrupt
+    assert bool(torch.isnan(y2).any())
