@@ -33,6 +33,7 @@ struct UmmaParams {
     int tiles_m, tiles_n, k_splits, k_per_split;
     int stages, tmem_cols;
     int na, nb, nc;         // planes used of A / B (2: hi,mid  3: hi,mid,lo) and written to C
+    int b_resident, nkb;    // K-major, single column tile, short K: the whole B operand stays in shared memory
     int flags;
     __nv_bfloat16* c; long long ldc, c_plane;          // plane-pair output
     __nv_bfloat16* c2; long long ldc2, c2_plane;       // second (ReLU'd) plane-pair output
@@ -182,18 +183,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
     const uint32_t a_tile_bytes = MN_MAJOR ? A_TILE_BYTES : (uint32_t)p.na * A_PLANE_BYTES;
     const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)bn_rows * 256u : (uint32_t)p.nb * b_plane_bytes;
-    const uint32_t stage_bytes = a_tile_bytes + b_tile_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const bool bres = !MN_MAJOR && p.b_resident;
+    const uint32_t bres_bytes = bres ? (uint32_t)p.nkb * b_tile_bytes : 0u;    // resident B: [k-block][plane][rows][128 B]
+    const uint32_t stage_bytes = bres ? a_tile_bytes : a_tile_bytes + b_tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bres_bytes + (size_t)p.stages * stage_bytes);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.stages;
-    const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16, bar_bres = bar_tempty + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+    const uint32_t bres_base = smem_u32(smem);
+    const uint32_t smem_base = bres_base + bres_bytes;
     // epilogue staging: 4 warps x 3 planes x 2 KB, 1024-byte aligned, after the barrier block
     const uint32_t epi_base = (smem_base + (uint32_t)p.stages * stage_bytes + 256u + 1023u) & ~1023u;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        mbar_init(bar_bres, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -213,20 +218,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if (bres && (int)blockIdx.x < n_tiles) {                          // B is the same for every tile of this CTA
+                mbar_expect_tx(bar_bres, bres_bytes);
+                for (int kb = 0; kb < p.nkb; ++kb) tma_load_3d(bres_base + kb * b_tile_bytes, &tmB, bar_bres, kb * UBK, 0, 0);
+            }
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int split = tile % p.k_splits;
                 const int mn = tile / p.k_splits;
                 const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
-                const int k_beg = split * p.k_per_split;
-                const int k_end = min(p.K, k_beg + p.k_per_split);
-                for (int k0 = k_beg; k0 < k_end; k0 += UBK) {
+                // split-K slices are interleaved (k-block j of slice s is block j*k_splits + s) so that the CTAs
+                // sharing operand columns walk the same rows at the same time and the re-reads hit L2
+                for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_tile_bytes;
                     mbar_expect_tx(full, stage_bytes);
                     if (!MN_MAJOR) {
                         tma_load_3d(sa, &tmA, full, k0, m0, 0);
-                        tma_load_3d(sb, &tmB, full, k0, n0, 0);
+                        if (!bres) tma_load_3d(sb, &tmB, full, k0, n0, 0);
                     } else {
                         tma_load_3d(sa, &tmA, full, m0, k0, 0);
                         tma_load_3d(sa + 16384, &tmA, full, m0 + 64, k0, 0);
@@ -243,19 +252,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (MN_MAJOR) idesc |= (1u << 15) | (1u << 16);
             int stage = 0, iter = 0;
             uint32_t phase = 0;
+            if (bres && (int)blockIdx.x < n_tiles) mbar_wait(bar_bres, 0);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
                 const int split = tile % p.k_splits;
-                const int k_beg = split * p.k_per_split;
-                const int k_end = min(p.K, k_beg + p.k_per_split);
                 const int acc = iter & 1;
                 mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 uint32_t accumulate = 0;
-                for (int k0 = k_beg; k0 < k_end; k0 += UBK) {
+                for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_tile_bytes;
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t sb = bres ? bres_base + (uint32_t)(k0 / UBK) * b_tile_bytes : sa + a_tile_bytes;
 #pragma unroll
                     for (int j = 0; j < UBK / 16; ++j) {
                         uint64_t a_hi, a_lo, b_hi, b_lo;
@@ -600,12 +609,17 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.mask = mask_bits; p.ldmask = ldmask;
     p.bits = bits_out; p.ldbits = ldbits;
     p.c32 = c_f32; p.ldc32 = ldc32;
-    const uint32_t stage_bytes = (uint32_t)p.na * A_PLANE_BYTES + (uint32_t)p.nb * (uint32_t)p.BN * 128u;
+    const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
     const uint32_t epi_bytes = 4u * 3u * EPI_PLANE_BYTES + 1024u;
-    p.stages = (int)((226 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
+    const uint32_t budget = 226 * 1024 - 1024 - 256 - epi_bytes;
+    p.nkb = (int)ceil_div(K, UBK);
+    p.b_resident = (p.tiles_n == 1 && p.tiles_m > 1 && (uint64_t)p.nkb * b_tile + 2ull * a_tile <= budget) ? 1 : 0;
+    const uint32_t bres_total = p.b_resident ? (uint32_t)p.nkb * b_tile : 0u;
+    const uint32_t stage_bytes = p.b_resident ? a_tile : a_tile + b_tile;
+    p.stages = (int)((budget - bres_total) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + epi_bytes;
+    const size_t smem = (size_t)bres_total + (size_t)p.stages * stage_bytes + 1024 + 256 + epi_bytes;
     CUtensorMap ta, tb, tc, tc2;
     if (int rc = make_map(&ta, a_planes, M, K, lda, a_plane, UM, p.na)) return rc;
     if (int rc = make_map(&tb, b_planes, N, K, ldb, b_plane, p.BN, p.nb)) return rc;
