@@ -76,6 +76,9 @@ SIGNATURES = {
     "avr_composite_bwd": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_spectrum_fwd": (C.c_int, [_G, _P, _P, _P, _P, _I64, _P, _P, _P, C.c_int, _P]),
     "avr_spectrum_bwd": (C.c_int, [_G, _P, _P, _P, _P, _I64, _P, _P, C.c_int, _P]),
+    "avr_spectrum_gain": (C.c_int, [_G, _P, _P, _P, _I64, _I64, _I32, C.c_int, _P]),
+    "avr_spectrum_phase_sum": (C.c_int, [_G, _P, _I64, _P, _P, C.c_int, _P]),
+    "avr_spectrum_phase_bwd": (C.c_int, [_G, _P, _P, _P, _I64, _I64, _I32, C.c_int, _P]),
 }
 
 _lib = None

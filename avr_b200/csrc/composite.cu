@@ -244,6 +244,25 @@ composite_bwd_kernel(const Geom geo, const float* __restrict__ sig, const float*
 // spectrum helpers
 // ------------------------------------------------------------------------------------------------
 // z[row, t] = y[row, t] * gain[row % S, t]
+__device__ __forceinline__ void split3_store(__nv_bfloat16* dst, int64_t plane, int np, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    dst[0] = hi;
+    dst[plane] = mid;
+    if (np == 3) dst[2 * plane] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
+// z = y * gain written as a bf16 plane set (operand of the tensor-core DFT)
+__global__ void gain_planes_kernel(const float* __restrict__ y, const float* __restrict__ gain, int64_t n_rows, int T, int S,
+                                   __nv_bfloat16* __restrict__ z, int64_t ldz, int64_t plane, int np) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * T) return;
+    const int64_t row = i / T;
+    const int t = (int)(i - row * T);
+    split3_store(z + row * ldz + t, plane, np, y[i] * __ldg(gain + (int64_t)(row % S) * T + t));
+}
+
 __global__ void gain_kernel(const float* y, const float* __restrict__ gain, int64_t n_rows, int T, int S, float* z) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int TQ = T >> 2;
@@ -273,9 +292,9 @@ __global__ void phase_sum_kernel(const float* __restrict__ x, int64_t ldx, const
     out[2 * i + 1] = im;
 }
 
-// d_X[b,s,f] = d_out[b,f] * conj(phase[s,f]) ; pad columns [2F, ldx) are zeroed
+// d_X[b,s,f] = d_out[b,f] * conj(phase[s,f]) ; pad columns [2F, ldx) are zeroed.  dx: fp32 or bf16 plane set.
 __global__ void phase_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ phase, int bs, int S, int F,
-                                 int64_t ldx, float* __restrict__ dx) {
+                                 int64_t ldx, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxp, int64_t plane, int np) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t half = ldx / 2;
     if (i >= (int64_t)bs * S * half) return;
@@ -289,7 +308,12 @@ __global__ void phase_bwd_kernel(const float* __restrict__ d_out, const float* _
         o.x = fmaf(g.x, p.x, g.y * p.y);
         o.y = fmaf(g.y, p.x, -g.x * p.y);
     }
-    *reinterpret_cast<float2*>(dx + row * ldx + 2 * f) = o;
+    if (dxp) {
+        split3_store(dxp + row * ldx + 2 * f, plane, np, o.x);
+        split3_store(dxp + row * ldx + 2 * f + 1, plane, np, o.y);
+    } else {
+        *reinterpret_cast<float2*>(dx + row * ldx + 2 * f) = o;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -511,7 +535,8 @@ extern "C" int avr_spectrum_bwd(const avr_render_geom* geom, const float* d_out,
     const int64_t rows = (int64_t)geo.bs * geo.S;
     if (rows == 0) return AVR_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    phase_bwd_kernel<<<(unsigned)ceil_div(rows * (ldd / 2), 256), 256, 0, st>>>(d_out, phase, geo.bs, geo.S, F, ldd, xbuf);
+    phase_bwd_kernel<<<(unsigned)ceil_div(rows * (ldd / 2), 256), 256, 0, st>>>(d_out, phase, geo.bs, geo.S, F, ldd, xbuf,
+                                                                              nullptr, 0, 0);
     AVR_LAUNCH_CHECK();
     if (int rc = gemm_impl(AVR_K_CONTIG, AVR_K_CONTIG, rows, geo.T, ldd, xbuf, ldd, dft, ldd, d_y, geo.T, 0, nullptr, 0,
                            nullptr, 0, st))
@@ -564,6 +589,58 @@ extern "C" int avr_rows_reduce(const avr_render_geom* geom, const void* d_dst, i
                                                                              per_receiver, ipc, workspace);
     AVR_LAUNCH_CHECK();
     rows_reduce_final_kernel<<<(unsigned)ceil_div((int64_t)rows * w, 256), 256, 0, st>>>(workspace, rows, chunks, w, d_src);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+
+// ---- pieces of the spectrum stage for the tensor-core DFT (the GEMM itself is avr_umma_gemm_nt) -------------
+extern "C" int avr_spectrum_gain(const avr_render_geom* geom, const float* y, const float* gain, void* z, int64_t ldz,
+                                 int64_t z_plane, int32_t z_nplanes, int device, void* stream) {
+    AVR_REQUIRE(geom && y && gain && z, "null pointer");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int64_t rows = (int64_t)geo.bs * geo.S;
+    if (rows == 0) return AVR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (z_plane == 0) {
+        AVR_REQUIRE(geo.T % 4 == 0 && ldz == geo.T, "fp32 gain output must be dense with T % 4 == 0");
+        gain_kernel<<<(unsigned)ceil_div(rows * (geo.T / 4), 256), 256, 0, st>>>(y, gain, rows, geo.T, geo.S, (float*)z);
+    } else {
+        AVR_REQUIRE(z_nplanes == 2 || z_nplanes == 3, "plane count must be 2 or 3");
+        gain_planes_kernel<<<(unsigned)ceil_div(rows * geo.T, 256), 256, 0, st>>>(y, gain, rows, geo.T, geo.S, (__nv_bfloat16*)z,
+                                                                               ldz, z_plane, z_nplanes);
+    }
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+extern "C" int avr_spectrum_phase_sum(const avr_render_geom* geom, const float* x, int64_t ldx, const float* phase, float* out,
+                                      int device, void* stream) {
+    AVR_REQUIRE(geom && x && phase && out, "null pointer");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int F = geo.T / 2 + 1;
+    AVR_REQUIRE(ldx >= 2 * F && ldx % 2 == 0, "ldx must be even and >= 2F");
+    if (geo.bs == 0) return AVR_OK;
+    phase_sum_kernel<<<(unsigned)ceil_div((int64_t)geo.bs * F, 128), 128, 0, (cudaStream_t)stream>>>(x, ldx, phase, geo.bs, geo.S, F, out);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+extern "C" int avr_spectrum_phase_bwd(const avr_render_geom* geom, const float* d_out, const float* phase, void* dx, int64_t ldx,
+                                      int64_t dx_plane, int32_t dx_nplanes, int device, void* stream) {
+    AVR_REQUIRE(geom && d_out && phase && dx, "null pointer");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int F = geo.T / 2 + 1;
+    AVR_REQUIRE(ldx >= 2 * F && ldx % 2 == 0, "ldx must be even and >= 2F");
+    const int64_t rows = (int64_t)geo.bs * geo.S;
+    if (rows == 0) return AVR_OK;
+    if (dx_plane) AVR_REQUIRE(dx_nplanes == 2 || dx_nplanes == 3, "plane count must be 2 or 3");
+    phase_bwd_kernel<<<(unsigned)ceil_div(rows * (ldx / 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        d_out, phase, geo.bs, geo.S, F, ldx, dx_plane ? nullptr : (float*)dx, dx_plane ? (__nv_bfloat16*)dx : nullptr, dx_plane,
+        dx_nplanes);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

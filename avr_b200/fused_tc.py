@@ -131,7 +131,7 @@ class FusedRenderTC(torch.autograd.Function):
             h = y
         sort = ops.delay_sort(geom, delay, w)
         y_t, prefix = ops.collapse_fwd(geom, h, sort, sig_mats[-1], tspan)
-        out = ops.spectrum_fwd(geom, y_t, tables)
+        out = ops.spectrum_fwd_tc(geom, y_t, tables)
 
         if any(ctx.needs_input_grad[8:]):
             ctx.plan, ctx.geom, ctx.tables, ctx.tspan = plan, geom, tables, tspan
@@ -172,7 +172,7 @@ class FusedRenderTC(torch.autograd.Function):
             return g, wt, d_mats
 
         # ---- spectrum, collapsed output layer --------------------------------------------------------
-        d_y = ops.spectrum_bwd(geom, d_out.contiguous().float(), tables)
+        d_y = ops.spectrum_bwd_tc(geom, d_out.contiguous().float(), tables)
         sig_mats = sig_net.matrices(pmap[id(sig_net)])
         g_sig = torch.empty_like(pmap[id(sig_net)])
         d_sig_mats = sig_net.matrices(g_sig)

@@ -483,3 +483,47 @@ def collapse_bwd(g, act: PlanePair, sort, w_out, d_y, tspan, prefix, d_act: Plan
                                                 d_act.ptr, d_act.ld, d_act.plane, _p(d_w), _p(d_wout), d_wout.stride(0),
                                                 1 if accumulate else 0, dev, st), "avr_collapse_bwd")
     return d_w
+
+
+# ---- spectrum stage with the DFT on the tensor cores ---------------------------------------------------------
+def dft_planes(tables):
+    """Plane sets of the DFT matrix, built once per table set: dft^T [ldd, T] and dft [T, ldd], 3 planes each.
+
+    The adjoint DFT also runs with six products: d_y feeds d_w = H . g, and the density gradient that follows
+    (d_alpha = d_w*Tr - (sum_{k>s} d_w_k w_k)/q) is a difference of nearly equal terms that amplifies its error."""
+    if "dftT_p3" not in tables:
+        dft = tables["dft"]
+        T, ldd = dft.shape
+        tables["dftT_p3"] = planes_split(dft, PlanePair.empty(ldd, T, dft.device, n=3), transpose=True)
+        tables["dft_p3"] = planes_split(dft, PlanePair.empty(T, ldd, dft.device, n=3))
+    return tables["dftT_p3"], tables["dft_p3"]
+
+
+def spectrum_fwd_tc(g, y, tables):
+    """out[bs,F,2] = sum_s phase * DFT(y * gain), DFT as a six-product tcgen05 GEMM (fp32-grade)."""
+    dev, st = _ctx(y)
+    dft_t, _ = dft_planes(tables)
+    rows, ldd = g.bs * g.S, dft_t.rows
+    z = PlanePair.empty(rows, g.T, y.device, n=3)
+    _lib.check(_lib.load().avr_spectrum_gain(C.byref(g), _p(_dense(y)), _p(tables["gain"]), z.ptr, z.ld, z.plane, z.n, dev, st),
+               "avr_spectrum_gain")
+    xbuf = torch.empty(rows, ldd, device=y.device)
+    umma_nt(z, dft_t, UMMA_OUT_F32, c_f32=xbuf)
+    out = torch.empty(g.bs, g.T // 2 + 1, 2, device=y.device)
+    _lib.check(_lib.load().avr_spectrum_phase_sum(C.byref(g), _p(xbuf), ldd, _p(tables["phase"]), _p(out), dev, st),
+               "avr_spectrum_phase_sum")
+    return out
+
+
+def spectrum_bwd_tc(g, d_out, tables):
+    dev, st = _ctx(d_out)
+    _, dft = dft_planes(tables)
+    rows, ldd = g.bs * g.S, dft.cols
+    q = PlanePair.empty(rows, ldd, d_out.device, n=3)
+    _lib.check(_lib.load().avr_spectrum_phase_bwd(C.byref(g), _p(_dense(d_out)), _p(tables["phase"]), q.ptr, q.ld, q.plane,
+                                                  q.n, dev, st), "avr_spectrum_phase_bwd")
+    d_y = torch.empty(g.bs, g.S, g.T, device=d_out.device)
+    umma_nt(q, dft, UMMA_OUT_F32, c_f32=d_y.view(rows, g.T))
+    _lib.check(_lib.load().avr_spectrum_gain(C.byref(g), _p(d_y), _p(tables["gain"]), C.c_void_p(d_y.data_ptr()), g.T, 0, 0,
+                                             dev, st), "avr_spectrum_gain")
+    return d_y

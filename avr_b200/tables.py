@@ -36,12 +36,12 @@ def direction_table(n_azi: int, n_ele: int, azi_rand: torch.Tensor | None = None
 
 
 def dft_matrix(T: int) -> torch.Tensor:
-    """``[T, ldd]`` real-DFT matrix, columns (cos, -sin)(2 pi f t / T) interleaved, ``ldd = ceil4(2F)``.
+    """``[T, ldd]`` real-DFT matrix, columns (cos, -sin)(2 pi f t / T) interleaved, ``ldd = ceil8(2F)``.
 
     Angles are reduced exactly (``f*t mod T`` in integers) and evaluated in float64 before rounding.
     """
     F = T // 2 + 1
-    ldd = (2 * F + 3) // 4 * 4
+    ldd = (2 * F + 7) // 8 * 8
     k = (torch.arange(T, dtype=torch.int64)[:, None] * torch.arange(F, dtype=torch.int64)[None, :]) % T
     ang = k.double() * (2.0 * np.pi / T)
     m = torch.zeros(T, ldd, dtype=torch.float64)

@@ -249,6 +249,16 @@ AVR_API int avr_spectrum_fwd(const avr_render_geom* geom, const float* y, const 
 AVR_API int avr_spectrum_bwd(const avr_render_geom* geom, const float* d_out, const float* gain, const float* phase,
                      const float* dft, int64_t ldd, float* xbuf, float* d_y, int device, void* stream);
 
+/* The three elementwise pieces of the spectrum stage, for running the DFT on the tensor cores
+ * (avr_umma_gemm_nt against a plane set of the DFT matrix): z = y*gain, the phase-weighted sum over samples,
+ * and its adjoint.  z / dx: fp32 (plane == 0) or bf16 plane set. */
+AVR_API int avr_spectrum_gain(const avr_render_geom* geom, const float* y, const float* gain, void* z, int64_t ldz,
+                              int64_t z_plane, int32_t z_nplanes, int device, void* stream);
+AVR_API int avr_spectrum_phase_sum(const avr_render_geom* geom, const float* x, int64_t ldx, const float* phase, float* out,
+                                   int device, void* stream);
+AVR_API int avr_spectrum_phase_bwd(const avr_render_geom* geom, const float* d_out, const float* phase, void* dx, int64_t ldx,
+                                   int64_t dx_plane, int32_t dx_nplanes, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
