@@ -6,6 +6,7 @@ Public surface (mirrors the reference's ``renderer.py`` / ``model.py``):
 * ``AVRModel(cfg)`` / ``AVRModel_complex(cfg)``   <- model.py:63 / :238
 * ``Encoding`` / ``Network``                      <- tcnn.Encoding / tcnn.Network as used by model.py
 * ``GradArena``                                   <- the DDP gradient all-reduce of avr_runner_ddp.py:98,257
+* ``FusedAdam``                                   <- clip / NaN scrub / Adam of avr_runner.py:192-200
 
 The compute path is hand-written CUDA behind the C-ABI of ``include/avr_b200.h``
 (``avr_b200/libavr_b200.so``); there is no CPU or PyTorch fallback.
@@ -15,3 +16,4 @@ __version__ = "0.1.0"
 from .model import AVRModel, AVRModel_complex, Encoding, Network      # noqa: E402,F401
 from .renderer import AVRRender                                       # noqa: E402,F401
 from .ddp import GradArena                                            # noqa: E402,F401
+from .optim import FusedAdam                                          # noqa: E402,F401

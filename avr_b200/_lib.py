@@ -76,6 +76,8 @@ SIGNATURES = {
     "avr_composite_bwd": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_spectrum_fwd": (C.c_int, [_G, _P, _P, _P, _P, _I64, _P, _P, _P, C.c_int, _P]),
     "avr_spectrum_bwd": (C.c_int, [_G, _P, _P, _P, _P, _I64, _P, _P, C.c_int, _P]),
+    "avr_adam_workspace_bytes": (_I64, []),
+    "avr_fused_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _I64, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "avr_spectrum_gain": (C.c_int, [_G, _P, _P, _P, _I64, _I64, _I32, C.c_int, _P]),
     "avr_spectrum_phase_sum": (C.c_int, [_G, _P, _I64, _P, _P, C.c_int, _P]),
     "avr_spectrum_phase_bwd": (C.c_int, [_G, _P, _P, _P, _I64, _I64, _I32, C.c_int, _P]),

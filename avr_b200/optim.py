@@ -1,0 +1,63 @@
+"""Fused training update over the flat arenas: clip-norm -> NaN/Inf scrub -> Adam in one pass.
+
+Replaces ``avr_runner.py:192-200`` (``clip_grad_norm_(params, max_norm=1)``, the in-place NaN/Inf scrub loop over
+every ``.grad`` and ``torch.optim.Adam.step()``).  Parameters are re-homed into one contiguous fp32 buffer (their
+``nn.Parameter`` objects become views of it, so ``state_dict`` / the renderer keep working) next to the
+``GradArena`` gradient buffer, and the whole update is one kernel of 28 bytes of HBM traffic per parameter.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .ddp import GradArena
+
+
+class FusedAdam:
+    """``torch.optim.Adam`` semantics (lr, betas, eps, weight_decay as L2) + the reference's clipping and scrubbing."""
+
+    def __init__(self, parameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0,
+                 arena: GradArena | None = None):
+        params = [p for p in parameters if p.requires_grad]
+        self.arena = arena if arena is not None else GradArena(params)
+        if [id(p) for p in self.arena.params] != [id(p) for p in params]:
+            raise ValueError("arena and optimiser must cover the same parameters in the same order")
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.step_count = 0
+        flat = self.arena.flat
+        if not flat.is_cuda:
+            raise _lib.AVRLibraryError("FusedAdam needs CUDA parameters (no CPU fallback)")
+        self.flat_params = torch.zeros_like(flat)
+        with torch.no_grad():
+            for p, off in zip(self.arena.params, self.arena.offsets):       # re-home the parameters
+                view = self.flat_params[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.norm = torch.zeros(2, device=flat.device)
+        self._ws = torch.empty(int(_lib.load().avr_adam_workspace_bytes()) // 4 + 4, device=flat.device)
+
+    def zero_grad(self):
+        self.arena.zero_()
+
+    @torch.no_grad()
+    def step(self, lr=None, write_back_grad=False):
+        """Apply one update; ``lr`` overrides the stored rate (cosine schedule is host-side, avr_runner.py:71,200)."""
+        self.step_count += 1
+        flat = self.arena.flat
+        dev = flat.device.index if flat.device.index is not None else torch.cuda.current_device()
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        p = C.c_void_p
+        _lib.check(_lib.load().avr_fused_adam_step(
+            p(self.flat_params.data_ptr()), p(flat.data_ptr()), p(self.exp_avg.data_ptr()), p(self.exp_avg_sq.data_ptr()),
+            flat.numel(), float(self.lr if lr is None else lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+            float(self.weight_decay), float(self.max_norm if self.max_norm else 0.0), self.step_count,
+            1 if write_back_grad else 0, p(self.norm.data_ptr()), p(self._ws.data_ptr()), self._ws.numel() * 4, dev, st),
+            "avr_fused_adam_step")
+
+    def grad_norm(self) -> torch.Tensor:
+        """Total gradient norm of the last step (device scalar; no sync)."""
+        return self.norm[0]

@@ -259,6 +259,15 @@ AVR_API int avr_spectrum_phase_sum(const avr_render_geom* geom, const float* x, 
 AVR_API int avr_spectrum_phase_bwd(const avr_render_geom* geom, const float* d_out, const float* phase, void* dx, int64_t ldx,
                                    int64_t dx_plane, int32_t dx_nplanes, int device, void* stream);
 
+/* ---- fused optimiser step over flat fp32 arenas (avr_runner.py:192-200: clip_grad_norm_ -> NaN/Inf scrub -> Adam) ----
+ * norm_out[0] = total gradient L2 norm (before clipping), norm_out[1] = clip coefficient.  max_norm <= 0: no
+ * clipping.  step is the 1-based Adam step.  write_back_grad != 0 stores the clipped / scrubbed gradient. */
+AVR_API int64_t avr_adam_workspace_bytes(void);
+AVR_API int avr_fused_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, float max_norm, int64_t step,
+                                int write_back_grad, float* norm_out, void* workspace, int64_t workspace_bytes, int device,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif
