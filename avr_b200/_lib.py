@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libavr_b200
 
 GEMM_RELU, GEMM_ACCUM, GEMM_MASK, GEMM_RELU_A, GEMM_RELU_B = 1, 2, 4, 8, 16
 K_CONTIG, I_CONTIG = 0, 1
-UMMA_RELU, UMMA_ACCUM, UMMA_MASK, UMMA_OUT_F32, UMMA_DUAL_RELU, UMMA_BITS = 1, 2, 4, 8, 16, 32
+UMMA_RELU, UMMA_ACCUM, UMMA_MASK, UMMA_OUT_F32, UMMA_DUAL_RELU, UMMA_BITS, UMMA_BIAS = 1, 2, 4, 8, 16, 32, 64
 
 
 class AVRLibraryError(RuntimeError):
@@ -56,7 +56,8 @@ SIGNATURES = {
     "avr_planes_split": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.c_int, _P, _I64,
-                                   _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, C.c_int, _P]),
+                                   _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _I64,
+                                   C.c_int, _P]),
     "avr_umma_gemm_tn_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P, _I64,
                                    C.c_int, _P]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "avr_collapse_bwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _I64, _P, _I64, _I64,
                                    _P, _P, _I64, C.c_int, C.c_int, _P]),
     "avr_rows_broadcast": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I64, _I64, _I32, _I32, C.c_int, _P]),
+    "avr_rows_block_sum": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, C.c_int, _P]),
     "avr_rows_reduce_workspace_bytes": (_I64, [_G, _I32, C.c_int]),
     "avr_rows_reduce": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "avr_ray_weights_fwd": (C.c_int, [_G, _P, _I64, _P, _F, _P, _P, C.c_int, _P]),

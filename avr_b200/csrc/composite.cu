@@ -644,3 +644,49 @@ extern "C" int avr_spectrum_phase_bwd(const avr_render_geom* geom, const float* 
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
+
+
+// partial[(b*R + r), c] = sum_s x[(b*R + r)*S + s, c]   (x: fp32 or bf16 plane set, first two planes)
+__global__ void __launch_bounds__(256)
+rows_block_sum_kernel(const Geom geo, const void* __restrict__ x_v, int64_t ldx, int64_t plane, int w, float* __restrict__ partial) {
+    const int64_t blk = blockIdx.x;                        // (b, r)
+    const int c = threadIdx.x * 4;
+    if (c >= w) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t row0 = blk * geo.S;
+    if (plane == 0) {
+        const float* x = reinterpret_cast<const float*>(x_v);
+        for (int s = 0; s < geo.S; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + (row0 + s) * ldx + c));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    } else {
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_v);
+#pragma unroll 4
+        for (int s = 0; s < geo.S; ++s) {
+            const __nv_bfloat16* q = x + (row0 + s) * ldx + c;
+            const uint2 hi = __ldg(reinterpret_cast<const uint2*>(q)), lo = __ldg(reinterpret_cast<const uint2*>(q + plane));
+            acc.x += __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
+            acc.y += __uint_as_float(hi.x & 0xFFFF0000u) + __uint_as_float(lo.x & 0xFFFF0000u);
+            acc.z += __uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16);
+            acc.w += __uint_as_float(hi.y & 0xFFFF0000u) + __uint_as_float(lo.y & 0xFFFF0000u);
+        }
+    }
+    *reinterpret_cast<float4*>(partial + blk * w + c) = acc;
+}
+
+// Sum of the S consecutive sample rows of every (receiver, ray): the adjoint of adding a per-ray / per-receiver
+// row to every sample point.  partial: fp32 [bs*R, w] dense.
+extern "C" int avr_rows_block_sum(const avr_render_geom* geom, const void* x, int64_t ldx, int64_t x_plane, int32_t w,
+                                  float* partial, int device, void* stream) {
+    AVR_REQUIRE(geom && x && partial, "null pointer");
+    AVR_REQUIRE(w > 0 && w % 4 == 0 && w <= 1024 && ldx % 4 == 0, "width must be a multiple of 4 and <= 1024");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int64_t blocks = (int64_t)geo.bs * geo.R;
+    if (blocks == 0 || geo.S == 0) return AVR_OK;
+    const int threads = ((w / 4 + 31) / 32) * 32;
+    rows_block_sum_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(geo, x, ldx, x_plane, w, partial);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}

@@ -21,11 +21,12 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <mutex>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace avr {
 
-enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32 };
+enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32, UF_BIAS = 64, UF_DEBUG_NOWAIT = 128 };
 
 struct UmmaParams {
     int M, N, K;            // K-major: rows, cols, reduction.  MN-major: A extent, B extent, reduction (points)
@@ -39,6 +40,9 @@ struct UmmaParams {
     __nv_bfloat16* c2; long long ldc2, c2_plane;       // second (ReLU'd) plane-pair output
     const uint32_t* mask; long long ldmask;            // ReLU bitmask of the gating activation: bit (col % 32) of word [row][col / 32]
     uint32_t* bits; long long ldbits;                  // bitmask (value > 0) written by the forward epilogue (UF_BITS)
+    const float* bias_ray; const float* bias_rcv;      // UF_BIAS: out[row,:] += bias_ray[ray(row),:] + bias_rcv[receiver(row),:]
+    long long ld_bias_ray, ld_bias_rcv;
+    int geo_R, geo_S;                                  // row = (b*R + r)*S + s
     float* c32; long long ldc32;                       // fp32 output / split-K partials
 };
 
@@ -119,6 +123,12 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
+// two fp32 -> packed bf16x2 (round to nearest even); low half = first argument
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -156,12 +166,12 @@ __device__ __forceinline__ void stage_planes32(uint32_t stage, int lane, const f
         for (int i = 0; i < 4; ++i) {
             float a = v[8 * q + 2 * i], b = v[8 * q + 2 * i + 1];
             if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-            const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
-            const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
-            h[i] = pack2(ah, bh);
-            m[i] = pack2(am, bm);
-            l[i] = pack2(__float2bfloat16_rn(ar - __bfloat162float(am)), __float2bfloat16_rn(br - __bfloat162float(bm)));
+            // packed conversions (cvt.rn.bf16x2.f32): one instruction per pair and per plane; the epilogue is bound by the
+            // issue rate of its four warps, so instruction count is what matters here
+            h[i] = cvt_bf16x2(a, b);
+            const float ar = a - bf_lo(h[i]), br = b - bf_hi(h[i]);
+            m[i] = cvt_bf16x2(ar, br);
+            l[i] = nplanes == 3 ? cvt_bf16x2(ar - bf_lo(m[i]), br - bf_hi(m[i])) : 0u;
         }
         const uint32_t off = row_base + (((uint32_t)q ^ sw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
@@ -309,11 +319,43 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int mn = tile / p.k_splits;
             const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
             const int acc = iter & 1;
+            const long long row = m0 + lane_grp * 32 + lane;
+            const bool row_ok = row < p.M;
+            // per-tile operands of the epilogue are fetched BEFORE waiting for the accumulator, so that their
+            // (row-strided / L2) load latency overlaps the tile's MMAs:
+            //   mw[j]   ReLU gating word of columns [32j, 32j+32) of this row            (UF_MASK)
+            //   bt*[j]  value of column 32j + lane of the warp's shared bias row           (UF_BIAS, uniform case)
+            uint32_t mw[8];
+            int ray_row = 0, rcv_row = 0, ray_uniform = 0, rcv_uniform = 0;
+            const uint32_t bias_s = epi_base + 4u * 3u * EPI_PLANE_BYTES + (uint32_t)lane_grp * 1024u;   // 256 floats: ray + receiver rows summed
+            if (!MN_MAJOR && !(p.flags & UF_OUT_F32)) {
+                if (p.flags & UF_BIAS) {
+                    const long long rrow = row_ok ? row : (long long)p.M - 1;
+                    ray_row = (int)((rrow / p.geo_S) % p.geo_R);
+                    rcv_row = (int)(rrow / ((long long)p.geo_R * p.geo_S));
+                    __match_all_sync(0xffffffffu, ray_row, &ray_uniform);
+                    __match_all_sync(0xffffffffu, rcv_row, &rcv_uniform);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    mw[j] = 0xffffffffu;
+                    const long long col = n0 + 32 * j;
+                    if (32 * j >= p.BN || col >= p.N) continue;
+                    if ((p.flags & UF_MASK) && row_ok) mw[j] = __ldg(p.mask + row * p.ldmask + (col >> 5));
+                    if (p.flags & UF_BIAS) {                                     // the warp's bias row segment -> smem
+                        float tr = 0.f, tb = 0.f;
+                        if (col + lane < p.N) {
+                            if (p.bias_ray && ray_uniform) tr = __ldg(p.bias_ray + (long long)ray_row * p.ld_bias_ray + col + lane);
+                            if (p.bias_rcv && rcv_uniform) tb = __ldg(p.bias_rcv + (long long)rcv_row * p.ld_bias_rcv + col + lane);
+                        }
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (uint32_t)(32 * j + lane) * 4u), "f"(tr + tb) : "memory");
+                    }
+                }
+                if (p.flags & UF_BIAS) __syncwarp();
+            }
             mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
             tc_fence_after();
-            const long long row = m0 + lane_grp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
-            const bool row_ok = row < p.M;
             if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
                 // fp32 outputs (split-K partials, the 16-wide density head): direct stores
                 for (int c0 = 0; c0 < p.BN; c0 += 16) {
@@ -325,7 +367,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const long long col = n0 + c0 + 8 * h;
                         if (col >= p.N) continue;
                         float* x = v + 8 * h;
-                        float* dst = MN_MAJOR ? p.c32 + ((long long)split * p.M + row) * p.N + col : p.c32 + row * p.ldc32 + col;
+                        float* dst = MN_MAJOR ? p.c32 + ((long long)split * p.M + row) * p.ldc32 + col : p.c32 + row * p.ldc32 + col;
                         if (!MN_MAJOR && (p.flags & UF_ACCUM)) {
                             const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
                             x[0] += o0.x; x[1] += o0.y; x[2] += o0.z; x[3] += o0.w; x[4] += o1.x; x[5] += o1.y; x[6] += o1.z; x[7] += o1.w;
@@ -342,14 +384,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // plane outputs: registers -> swizzled smem staging -> TMA bulk tensor store (full lines, rows and
                 // columns outside the output window are clipped by the tensor map)
                 const uint32_t stage = epi_base + (uint32_t)lane_grp * (3u * EPI_PLANE_BYTES);
-                // ReLU gating: one 32-bit word per 32-column chunk, all words of the tile row fetched up front
-                uint32_t mw[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    mw[j] = 0xffffffffu;
-                    const long long col = n0 + 32 * j;
-                    if ((p.flags & UF_MASK) && row_ok && 32 * j < p.BN && col < p.N) mw[j] = __ldg(p.mask + row * p.ldmask + (col >> 5));
-                }
                 for (int c0 = 0; c0 < p.BN && n0 + c0 < p.N; c0 += EPI_COLS) {
                     float v[32];
                     {
@@ -363,6 +397,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
+                    }
+                    if (p.flags & UF_BIAS) {
+                        // per-ray / per-receiver additive terms of the first signal layer (the broadcast inputs of
+                        // renderer.py:59-60 folded through W0).  The 32 rows of a warp almost always share their ray and
+                        // receiver: the prefetched lane value is then broadcast with shuffles.
+                        // (uniform tables were summed into the warp's smem row above: broadcast reads, no shuffles)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 t;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                         : "r"(bias_s + (uint32_t)(c0 + 4 * q) * 4u));
+                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                        }
+#pragma unroll
+                        for (int tsel = 0; tsel < 2; ++tsel) {                   // rare: rows of the warp straddle rays / receivers
+                            const float* tab = tsel == 0 ? p.bias_ray : p.bias_rcv;
+                            if (tab == nullptr || (tsel == 0 ? ray_uniform : rcv_uniform)) continue;
+                            const long long ldt = tsel == 0 ? p.ld_bias_ray : p.ld_bias_rcv;
+                            const int my = tsel == 0 ? ray_row : rcv_row;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + c0 + i < p.N) v[i] += __ldg(tab + (long long)my * ldt + n0 + c0 + i);
+                        }
                     }
                     if (p.flags & UF_MASK) {
                         uint32_t word = 0;
@@ -400,7 +457,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     const int n_out = (p.flags & UF_DUAL_RELU) ? 2 : 1;
                     for (int o = 0; o < n_out; ++o) {
-                        if (lane == 0) tma_store_wait_read();                   // staging tiles free again?
+                        if (lane == 0 && !(p.flags & UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
                         __syncwarp();
                         stage_planes32(stage, lane, v, o == 1 || (p.flags & UF_RELU), p.nc);
                         fence_async_smem();
@@ -457,8 +514,8 @@ __global__ void planes_merge_kernel(const __nv_bfloat16* __restrict__ in, long l
 // dW[m, n] (+)= sum over splits of partial[split][m][n].  One warp per float4 of the output: lane l adds the
 // splits l, l+32, ... in order, then a fixed butterfly combines the lanes -> deterministic and latency-tolerant.
 __global__ void __launch_bounds__(256)
-umma_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, long long N, float* __restrict__ C,
-                          long long ldc, int accumulate) {
+umma_splitk_reduce_kernel(const float* __restrict__ partial, long long ldp, int splits, long long M, long long N,
+                          float* __restrict__ C, long long ldc, int accumulate) {
     const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long nq = N / 4;
@@ -466,7 +523,7 @@ umma_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long lo
     const long long r = q / nq, c = (q - r * nq) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int z = lane; z < splits; z += 32) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + ((long long)z * M + r) * N + c));
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + ((long long)z * M + r) * ldp + c));
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
 #pragma unroll
@@ -581,13 +638,15 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
                              int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
-                             int64_t ldbits, float* c_f32, int64_t ldc32, int device, void* stream) {
+                             int64_t ldbits, const float* bias_ray, int64_t ld_bias_ray, const float* bias_rcv,
+                             int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32, int device,
+                             void* stream) {
     AVR_REQUIRE(a_planes && b_planes, "null operand");
     AVR_REQUIRE((a_nplanes == 2 || a_nplanes == 3) && (b_nplanes == 2 || b_nplanes == 3) && (c_nplanes == 2 || c_nplanes == 3),
                 "plane counts must be 2 or 3");
     if (!(a_nplanes == 3 && b_nplanes == 3)) a_nplanes = b_nplanes = 2;     // six products need 24 bits on both sides
     AVR_REQUIRE(M >= 0 && N > 0 && K > 0, "bad dimensions");
-    AVR_REQUIRE(N % 8 == 0, "N must be a multiple of 8");
+    AVR_REQUIRE((flags & UF_OUT_F32) ? N % 8 == 0 : N % 4 == 0, "N must be a multiple of 8 (fp32 output) / 4 (plane output)");
     AVR_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "dimension overflow");
     if (flags & UF_OUT_F32) AVR_REQUIRE(c_f32 && ldc32 % 4 == 0 && aligned16(c_f32), "fp32 output must be 16-byte aligned");
     else AVR_REQUIRE(c_planes && ldc % 8 == 0 && c_plane % 8 == 0 && aligned16(c_planes), "plane output must be 16-byte aligned");
@@ -608,9 +667,17 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
     p.mask = mask_bits; p.ldmask = ldmask;
     p.bits = bits_out; p.ldbits = ldbits;
+    if (flags & UF_BIAS) {
+        AVR_REQUIRE((bias_ray || bias_rcv) && geo_R > 0 && geo_S > 0 && !(flags & UF_OUT_F32), "BIAS needs a table and the ray geometry");
+        AVR_REQUIRE((!bias_ray || (aligned16(bias_ray) && ld_bias_ray % 4 == 0)) && (!bias_rcv || (aligned16(bias_rcv) && ld_bias_rcv % 4 == 0)),
+                    "bias tables must be 16-byte aligned");
+    }
+    p.bias_ray = bias_ray; p.bias_rcv = bias_rcv; p.ld_bias_ray = ld_bias_ray; p.ld_bias_rcv = ld_bias_rcv;
+    p.geo_R = geo_R; p.geo_S = geo_S;
+    if (getenv("AVR_UMMA_NOWAIT")) p.flags |= UF_DEBUG_NOWAIT;       // timing experiment only: results are garbage
     p.c32 = c_f32; p.ldc32 = ldc32;
     const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
-    const uint32_t epi_bytes = 4u * 3u * EPI_PLANE_BYTES + 1024u;
+    const uint32_t epi_bytes = 4u * 3u * EPI_PLANE_BYTES + 4u * 1024u + 1024u;    // staging tiles + per-warp bias rows
     const uint32_t budget = 226 * 1024 - 1024 - 256 - epi_bytes;
     p.nkb = (int)ceil_div(K, UBK);
     p.b_resident = (p.tiles_n == 1 && p.tiles_m > 1 && (uint64_t)p.nkb * b_tile + 2ull * a_tile <= budget) ? 1 : 0;
@@ -646,7 +713,7 @@ AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K
     const int64_t max_by_k = ceil_div(K, 1024);
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
-    return splits * M * N * (int64_t)sizeof(float);
+    return splits * M * (ceil_div(N, 8) * 8) * (int64_t)sizeof(float);
 }
 
 // C[M,N] (+)= sum_k A[k,M] * B[k,N] on plane pairs stored [K, M] and [K, N] (both MN-major); fp32 output,
@@ -656,7 +723,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
                              void* workspace, int64_t workspace_bytes, int device, void* stream) {
     AVR_REQUIRE(a_planes && b_planes && c && workspace, "null pointer");
     AVR_REQUIRE(M > 0 && N > 0 && K >= 0, "bad dimensions");
-    AVR_REQUIRE(M % 8 == 0 && N % 8 == 0, "M and N must be multiples of 8");
+    AVR_REQUIRE(M % 4 == 0 && N % 4 == 0, "M and N must be multiples of 4");
     AVR_REQUIRE(K < (1ll << 31), "dimension overflow");
     AVR_ENTER(device);
     UmmaParams p = {};
@@ -666,13 +733,14 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     const int64_t need = avr_umma_gemm_tn_workspace_bytes(M, N, K);
     AVR_REQUIRE(workspace_bytes >= need && aligned16(workspace), "workspace too small or misaligned");
-    int64_t splits = need / (M * N * (int64_t)sizeof(float));
+    const int64_t ldp = ceil_div(N, 8) * 8;                    // partial rows padded to whole 8-column store groups
+    int64_t splits = need / (M * ldp * (int64_t)sizeof(float));
     if (splits < 1) splits = 1;
     p.k_per_split = (int)(ceil_div(ceil_div(K, splits), UBK) * UBK);
     if (p.k_per_split < UBK) p.k_per_split = UBK;
     p.k_splits = (int)(K > 0 ? ceil_div(K, p.k_per_split) : 1);
     p.tmem_cols = tmem_cols_for(p.BN);
-    p.c32 = (float*)workspace;
+    p.c32 = (float*)workspace; p.ldc32 = ldp;
     const int bn_rows = (p.BN + 63) / 64 * 64;
     const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)bn_rows * 256u;
     p.stages = (int)((220 * 1024) / stage_bytes);
@@ -693,8 +761,8 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
         p.k_splits = 0;
     }
     AVR_REQUIRE(ldc % 4 == 0 && aligned16(c), "C must be 16-byte aligned");
-    umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * (N / 4) * 32, 256), 256, 0, st>>>((const float*)workspace, p.k_splits, M,
-                                                                                       N, c, ldc, accumulate);
+    umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * (N / 4) * 32, 256), 256, 0, st>>>((const float*)workspace, ldp, p.k_splits,
+                                                                                       M, N, c, ldc, accumulate);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

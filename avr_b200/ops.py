@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import (GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG,  # noqa: F401
-                   UMMA_ACCUM, UMMA_BITS, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta, RenderGeom)
+                   UMMA_ACCUM, UMMA_BIAS, UMMA_BITS, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta, RenderGeom)
 
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream ----------------------
 PROFILE = None          # set to a list to collect (name, work, unit, start_event, end_event)
@@ -309,11 +309,12 @@ def relu_bits_empty(rows, cols, device):
 
 
 def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask=None, c_f32=None,
-            bits_out=None):
+            bits_out=None, bias_ray=None, bias_rcv=None, geom=None):
     """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane set or (UMMA_OUT_F32) an fp32 tensor.
 
     ``mask`` (with UMMA_MASK): int32 bitmask ``[M, words]`` gating the product (ReLU backward);
     ``bits_out``: if given, the bitmask ``(C > 0)`` is written (forward ReLU layers).
+    ``bias_ray[R,N]`` / ``bias_rcv[bs,N]`` (fp32, with ``geom``): rows added to every sample point of a ray / receiver.
     """
     dev, st = _ctx(a)
     M, K, N = a.rows, a.cols, b.rows
@@ -321,6 +322,8 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
     none = C.c_void_p(None)
     if bits_out is not None:
         flags |= UMMA_BITS
+    if bias_ray is not None or bias_rcv is not None:
+        flags |= UMMA_BIAS
     products = 6 if (a.n == 3 and b.n == 3) else 3
     with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * products):
         _lib.check(_lib.load().avr_umma_gemm_nt(
@@ -330,6 +333,9 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
             c2.ptr if c2 is not None else none, c2.ld if c2 is not None else 0, c2.plane if c2 is not None else 0,
             _p(mask, torch.int32), mask.stride(0) if mask is not None else 0,
             _p(bits_out, torch.int32), bits_out.stride(0) if bits_out is not None else 0,
+            _p(bias_ray), bias_ray.stride(0) if bias_ray is not None else 0,
+            _p(bias_rcv), bias_rcv.stride(0) if bias_rcv is not None else 0,
+            geom.R if geom is not None else 0, geom.S if geom is not None else 0,
             _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0, dev, st), "avr_umma_gemm_nt")
 
 
@@ -355,6 +361,16 @@ def rows_broadcast(g, src, per_receiver, dst, col0):
     ptr, ld, plane = _mat(dst)
     _lib.check(_lib.load().avr_rows_broadcast(C.byref(g), _p(_dense(src)), src.shape[1], 1 if per_receiver else 0,
                                               ptr, ld, plane, _np(dst), col0, dev, st), "avr_rows_broadcast")
+
+
+def rows_block_sum(g, x):
+    """-> fp32 ``[bs*R, w]``: sum over the S sample rows of every (receiver, ray) of ``x`` (fp32 2-D or PlanePair)."""
+    dev, st = _ctx(x)
+    ptr, ld, plane = _mat(x)
+    w = x.cols if isinstance(x, PlanePair) else x.shape[1]
+    out = torch.empty(g.bs * g.R, w, device=x.device)
+    _lib.check(_lib.load().avr_rows_block_sum(C.byref(g), ptr, ld, plane, w, _p(out), dev, st), "avr_rows_block_sum")
+    return out
 
 
 def rows_reduce(g, d_dst, col0, w, per_receiver):

@@ -158,7 +158,8 @@ enum {
     AVR_UMMA_MASK = 4,        /* product *= bit (j % 32) of mask_bits[i][j / 32]  (ReLU backward; before ACCUM) */
     AVR_UMMA_OUT_F32 = 8,     /* write fp32 c_f32 instead of a plane pair                            */
     AVR_UMMA_DUAL_RELU = 16,  /* additionally write max(out,0) as a second plane pair (c2)           */
-    AVR_UMMA_BITS = 32        /* additionally write the bitmask (out > 0) to bits_out (1 bit / element) */
+    AVR_UMMA_BITS = 32,       /* additionally write the bitmask (out > 0) to bits_out (1 bit / element) */
+    AVR_UMMA_BIAS = 64        /* out[row,:] += bias_ray[ray(row),:] + bias_rcv[receiver(row),:], row = (b*R + r)*S + s */
 };
 /* fp32 [rows, cols] (ld) <-> plane pair; transpose != 0 writes planes[c, r] = x[r, c]; relu != 0 clamps */
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
@@ -171,7 +172,9 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
                              int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
-                             int64_t ldbits, float* c_f32, int64_t ldc32, int device, void* stream);
+                             int64_t ldbits, const float* bias_ray, int64_t ld_bias_ray, const float* bias_rcv,
+                             int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32, int device,
+                             void* stream);
 /* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane pairs; weight gradients).
  * fp32 output; deterministic split-K over the points through `workspace`. */
 AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
@@ -209,6 +212,9 @@ AVR_API int avr_rows_broadcast(const avr_render_geom* geom, const float* src, in
                        void* dst, int64_t ld_dst, int64_t dst_plane, int32_t dst_nplanes, int32_t col0, int device,
                        void* stream);
 /* transpose of the above: d_src[row, :] = sum over the points mapped to `row` (fixed order). */
+/* partial[(b*R + r), 0:w] = sum over the S sample rows of (b, r) of x (fp32, or plane set: first two planes) */
+AVR_API int avr_rows_block_sum(const avr_render_geom* geom, const void* x, int64_t ldx, int64_t x_plane, int32_t w,
+                               float* partial, int device, void* stream);
 AVR_API int64_t avr_rows_reduce_workspace_bytes(const avr_render_geom* geom, int32_t w, int per_receiver);
 AVR_API int avr_rows_reduce(const avr_render_geom* geom, const void* d_dst, int64_t ld_dst, int64_t d_plane, int32_t col0,
                     int32_t w, int per_receiver, float* d_src, float* workspace, int64_t workspace_bytes,

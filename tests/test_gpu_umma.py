@@ -152,3 +152,24 @@ def test_collapse_matches_literal_output_layer(built_library, bs, R, S, T, W):
     assert rel_l2(dW[:, :W], Wd.grad) < 2e-6 and float(dW[:, W:].abs().max()) == 0
     y2, prefix2 = ops.collapse_fwd(geom, hp, sort, Wout.to(DEV), tspan=3)     # violated bound must poison, not corrupt
     assert bool(torch.isnan(y2).any())
+
+
+def test_umma_bias_epilogue_and_block_sum(built_library):
+    """Per-ray / per-receiver rows added in the GEMM epilogue and the adjoint block sum."""
+    g = torch.Generator().manual_seed(9)
+    bs, R, S, K, N = 3, 10, 64, 128, 256                       # S = 64: warps share their ray; also a ragged case below
+    for S_ in (S, 24):
+        M = bs * R * S_
+        geom = ops.RenderGeom(bs, R, S_, 200, -10.0, 20.0, 16000.0, 343.8)
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+        t_ray, t_rcv = torch.randn(R, N, generator=g), torch.randn(bs, N, generator=g)
+        rows = torch.arange(M)
+        ref = A.double() @ B.double().t() + t_ray[(rows // S_) % R].double() + t_rcv[rows // (R * S_)].double()
+        c = PlanePair.empty(M, N, DEV, n=3)
+        ops.umma_nt(_pp(A, n=3), _pp(B, n=3), ops.UMMA_RELU, c, bias_ray=t_ray.to(DEV), bias_rcv=t_rcv.to(DEV), geom=geom)
+        assert rel_l2(ops.planes_merge(c), ref.clamp_min(0)) < 2e-6
+        x = torch.randn(M, 72, generator=g)
+        part = ops.rows_block_sum(geom, x[:, :64].contiguous().to(DEV))
+        assert rel_l2(part, x[:, :64].double().view(bs * R, S_, 64).sum(1)) < 1e-6
+        part_p = ops.rows_block_sum(geom, _pp(x[:, :64].contiguous()))
+        assert rel_l2(part_p, x[:, :64].double().view(bs * R, S_, 64).sum(1)) < 1e-5
