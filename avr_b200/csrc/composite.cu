@@ -342,6 +342,75 @@ __global__ void rows_broadcast_kernel(const Geom geo, const float* __restrict__ 
     }
 }
 
+// plane-set destination, 8 columns (one 16-byte store per plane) per thread
+__global__ void rows_broadcast_planes8_kernel(const Geom geo, const float* __restrict__ src, int w, int per_receiver,
+                                              __nv_bfloat16* __restrict__ db, int64_t ld_dst, int64_t dst_plane, int dst_np,
+                                              int col0) {
+    const int groups = w >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_pts = (int64_t)geo.bs * geo.R * geo.S;
+    if (i >= n_pts * groups) return;
+    const int64_t n = i / groups;
+    const int g = (int)(i - n * groups);
+    const int64_t row = per_receiver ? n / ((int64_t)geo.R * geo.S) : (n / geo.S) % geo.R;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + row * w + 8 * g));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + row * w + 8 * g) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        const float r0 = v[2 * k] - __low2float(hh), r1 = v[2 * k + 1] - __high2float(hh);
+        const __nv_bfloat162 mm = __floats2bfloat162_rn(r0, r1);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0 - __low2float(mm), r1 - __high2float(mm));
+        h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        m[k] = *reinterpret_cast<const uint32_t*>(&mm);
+        l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    __nv_bfloat16* o = db + n * ld_dst + col0 + 8 * g;
+    *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(o + dst_plane) = make_uint4(m[0], m[1], m[2], m[3]);
+    if (dst_np == 3) *reinterpret_cast<uint4*>(o + 2 * dst_plane) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// plane-set source, 8 columns (one 16-byte load per plane) per thread; same partial layout and a fixed summation order
+__global__ void __launch_bounds__(256)
+rows_reduce_planes8_kernel(const Geom geo, const __nv_bfloat16* __restrict__ db, int64_t ld_dst, int64_t d_plane, int col0,
+                           int w, int per_receiver, int items_per_chunk, float* __restrict__ partial) {
+    extern __shared__ float red8[];                               // [items per pass][w + 1]
+    const int row = blockIdx.x, chunk = blockIdx.y;
+    const int groups = w >> 3, ipp = 256 / groups;
+    const int g = threadIdx.x % groups, y = threadIdx.x / groups;
+    const int64_t n_items = per_receiver ? (int64_t)geo.R * geo.S : (int64_t)geo.bs * geo.S;
+    const int64_t j_beg = (int64_t)chunk * items_per_chunk;
+    const int64_t j_end = min(n_items, j_beg + items_per_chunk);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (y < ipp) {
+        for (int64_t j = j_beg + y; j < j_end; j += ipp) {
+            int64_t n;
+            if (per_receiver) n = (int64_t)row * geo.R * geo.S + j;
+            else { const int64_t b = j / geo.S, sx = j - b * geo.S; n = (b * geo.R + row) * geo.S + sx; }
+            const __nv_bfloat16* src = db + n * ld_dst + col0 + 8 * g;
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(src + d_plane));
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[2 * k] += __uint_as_float(hw[k] << 16) + __uint_as_float(mw[k] << 16);
+                acc[2 * k + 1] += __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(mw[k] & 0xffff0000u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red8[y * (w + 1) + 8 * g + k] = acc[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < w; c += 256) {
+        float t = 0.f;
+        for (int k = 0; k < ipp; ++k) t += red8[k * (w + 1) + c];
+        partial[((int64_t)row * gridDim.y + chunk) * w + c] = t;
+    }
+}
+
 // stage 1: partial[row, chunk, c] = sum over the chunk's contributing points (fixed order)
 __global__ void __launch_bounds__(256)
 rows_reduce_kernel(const Geom geo, const void* __restrict__ d_dst_v, int64_t ld_dst, int64_t d_plane, int col0, int w,
@@ -556,8 +625,12 @@ extern "C" int avr_rows_broadcast(const avr_render_geom* geom, const float* src,
     const Geom geo = make_geom(geom);
     const int64_t total = (int64_t)geo.bs * geo.R * geo.S * w;
     if (total == 0) return AVR_OK;
-    rows_broadcast_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(geo, src, w, per_receiver, dst,
-                                                                                         ld_dst, dst_plane, dst_nplanes, col0);
+    if (dst_plane != 0 && w % 8 == 0 && col0 % 8 == 0 && ld_dst % 8 == 0 && dst_plane % 8 == 0 && aligned16(dst) && aligned16(src))
+        rows_broadcast_planes8_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            geo, src, w, per_receiver, (__nv_bfloat16*)dst, ld_dst, dst_plane, dst_nplanes, col0);
+    else
+        rows_broadcast_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(geo, src, w, per_receiver, dst,
+                                                                                             ld_dst, dst_plane, dst_nplanes, col0);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
@@ -585,8 +658,15 @@ extern "C" int avr_rows_reduce(const avr_render_geom* geom, const void* d_dst, i
     const int chunks = rows_reduce_plan(geo, per_receiver, &ipc);
     AVR_REQUIRE(chunks <= 65535, "too many reduce chunks");
     cudaStream_t st = (cudaStream_t)stream;
-    rows_reduce_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, st>>>(geo, d_dst, ld_dst, d_plane, col0, w,
-                                                                             per_receiver, ipc, workspace);
+    if (d_plane != 0 && w % 8 == 0 && w <= 2048 && col0 % 8 == 0 && ld_dst % 8 == 0 && d_plane % 8 == 0 && aligned16(d_dst)) {
+        const int ipp = 256 / (w / 8);
+        const size_t smem = (size_t)ipp * (w + 1) * sizeof(float);          // <= 32 x 257 floats
+        rows_reduce_planes8_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, smem, st>>>(
+            geo, (const __nv_bfloat16*)d_dst, ld_dst, d_plane, col0, w, per_receiver, ipc, workspace);
+    } else {
+        rows_reduce_kernel<<<dim3((unsigned)rows, (unsigned)chunks), 256, 0, st>>>(geo, d_dst, ld_dst, d_plane, col0, w,
+                                                                                 per_receiver, ipc, workspace);
+    }
     AVR_LAUNCH_CHECK();
     rows_reduce_final_kernel<<<(unsigned)ceil_div((int64_t)rows * w, 256), 256, 0, st>>>(workspace, rows, chunks, w, d_src);
     AVR_LAUNCH_CHECK();

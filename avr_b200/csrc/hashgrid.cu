@@ -108,14 +108,39 @@ __device__ __forceinline__ void scatter_level(const GridDev& g, int l, float ux,
     const Cell c = locate(g.scale[l], ux, uy, uz);
     const uint32_t res = g.res[l], size = g.size[l];
     unsigned long long* base = acc + 2ull * g.offset[l];
+    // all sixteen addends first, then sixteen back-to-back reductions from distinct registers: a RED holds its
+    // source registers until the LSU has taken them, so interleaving address math with REDs serialises on that
+    uint32_t idx[8];
+    long long q0[8], q1[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        uint32_t idx = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
-        float w = corner_weight(c, k);
-        long long q0 = __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc));
-        long long q1 = __float2ll_rn(__fmul_rn(__fmul_rn(w, g1), sc));
-        if (q0 != 0) atomicAdd(base + 2ull * idx, (unsigned long long)q0);
-        if (q1 != 0) atomicAdd(base + 2ull * idx + 1, (unsigned long long)q1);
+        idx[k] = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
+        const float w = corner_weight(c, k);
+        q0[k] = __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc));
+        q1[k] = __float2ll_rn(__fmul_rn(__fmul_rn(w, g1), sc));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        unsigned long long* dst = base + 2ull * idx[k];
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(dst), "l"(q0[k]) : "memory");
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(dst + 1), "l"(q1[k]) : "memory");
+    }
+}
+
+// fp32 variant: one vector reduction per corner (both features of an entry), straight into the gradient.  The cost of
+// a RED is per instruction, not per byte (measured: 2 x u64 1.57 ms, 2 x f32 1.75 ms, 1 x v2.f32 0.92 ms per simu
+// step), so this halves the scatter -- at the price of a summation order that changes from run to run.
+__device__ __forceinline__ void scatter_level_f32(const GridDev& g, int l, float ux, float uy, float uz, float g0,
+                                                  float g1, float* __restrict__ grad) {
+    const Cell c = locate(g.scale[l], ux, uy, uz);
+    const uint32_t res = g.res[l], size = g.size[l];
+    float* base = grad + 2ull * g.offset[l];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t idx = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
+        const float w = corner_weight(c, k);
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(base + 2ull * idx), "f"(__fmul_rn(w, g0)), "f"(__fmul_rn(w, g1))
+                     : "memory");
     }
 }
 
@@ -190,17 +215,20 @@ encode_fwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
     }
 }
 
-template <bool RAYGEN>
+template <bool RAYGEN, bool F32ACC>
 __global__ void __launch_bounds__(ENC_PTS* ENC_LG)
 encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t n_pts, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ d_vals, const float* __restrict__ u_in,
                   const void* __restrict__ d_out_v, int64_t ld_out, int64_t d_plane, int col0,
                   const uint32_t* __restrict__ gmax_bits, int headroom, unsigned long long* __restrict__ acc) {
     extern __shared__ float tile[];
-    bool ok, poisoned;
-    const int e = fixed_exponent(__ldg(gmax_bits), headroom, ok, poisoned);
-    if (!ok) return;                                        // zero (or poisoned) gradient: nothing to add
-    const float sc = ldexpf(1.0f, e);
+    float sc = 1.f;
+    if (!F32ACC) {
+        bool ok, poisoned;
+        const int e = fixed_exponent(__ldg(gmax_bits), headroom, ok, poisoned);
+        if (!ok) return;                                    // zero (or poisoned) gradient: nothing to add
+        sc = ldexpf(1.0f, e);
+    }
     const int W = 2 * grid.n_levels;
     const int Wp = W | 1;
     const int p = threadIdx.x, lg = threadIdx.y;
@@ -232,7 +260,9 @@ encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
     }
     for (int l = lg; l < grid.n_levels; l += ENC_LG) {
         const float g0 = tile[p * Wp + 2 * l], g1 = tile[p * Wp + 2 * l + 1];
-        if (g0 != 0.f || g1 != 0.f) scatter_level(grid, l, ux, uy, uz, g0, g1, sc, acc);
+        if (g0 == 0.f && g1 == 0.f) continue;
+        if (F32ACC) scatter_level_f32(grid, l, ux, uy, uz, g0, g1, reinterpret_cast<float*>(acc));
+        else scatter_level(grid, l, ux, uy, uz, g0, g1, sc, acc);
     }
 }
 
@@ -393,29 +423,29 @@ extern "C" int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, in
 
 static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* grid, int64_t n_pts, const float* rays_o,
                              const float* dirs, const float* d_vals, const float* u, const void* d_out, int64_t ld_out,
-                             int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t headroom, int64_t* acc,
+                             int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t headroom, void* acc,
                              void* stream) {
     if (int rc = check_grid(grid)) return rc;
-    AVR_REQUIRE(d_out && gmax_bits && acc, "null d_out/gmax/acc");
+    const bool f32acc = headroom == AVR_GRID_GRAD_F32;
+    AVR_REQUIRE(d_out && acc && (gmax_bits || f32acc), "null d_out/gmax/acc");
     AVR_REQUIRE(col0 >= 0 && ld_out >= col0 + 2 * grid->n_levels, "bad gradient window");
-    AVR_REQUIRE(headroom >= 0 && headroom <= 56, "log2_headroom out of range");
+    AVR_REQUIRE(f32acc || (headroom >= 0 && headroom <= 56), "log2_headroom out of range");
     if (n_pts == 0) return AVR_OK;
     const GridDev gd = make_grid(grid);
     const int W = 2 * grid->n_levels;
     const size_t smem = (size_t)ENC_PTS * (W | 1) * sizeof(float);
     const dim3 block(ENC_PTS, ENC_LG);
     const unsigned blocks = (unsigned)ceil_div(n_pts, ENC_PTS);
-    if (raygen) {
-        AVR_CUDA(cudaFuncSetAttribute(encode_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        encode_bwd_kernel<true><<<blocks, block, smem, (cudaStream_t)stream>>>(
-            geo, gd, n_pts, rays_o, dirs, d_vals, nullptr, d_out, ld_out, d_plane, col0, gmax_bits, headroom,
-            (unsigned long long*)acc);
-    } else {
-        AVR_CUDA(cudaFuncSetAttribute(encode_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        encode_bwd_kernel<false><<<blocks, block, smem, (cudaStream_t)stream>>>(
-            geo, gd, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, d_plane, col0, gmax_bits, headroom,
-            (unsigned long long*)acc);
-    }
+    auto launch = [&](auto kernel) -> int {
+        AVR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<blocks, block, smem, (cudaStream_t)stream>>>(geo, gd, n_pts, rays_o, dirs, d_vals, u, d_out, ld_out, d_plane,
+                                                             col0, gmax_bits, headroom, (unsigned long long*)acc);
+        return AVR_OK;
+    };
+    int rc;
+    if (raygen) rc = f32acc ? launch(encode_bwd_kernel<true, true>) : launch(encode_bwd_kernel<true, false>);
+    else rc = f32acc ? launch(encode_bwd_kernel<false, true>) : launch(encode_bwd_kernel<false, false>);
+    if (rc) return rc;
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
@@ -423,7 +453,7 @@ static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
 extern "C" int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
                                      const float* dirs, const float* d_vals, const void* d_out, int64_t ld_out,
                                      int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
-                                     int64_t* acc, int device, void* stream) {
+                                     void* acc, int device, void* stream) {
     AVR_REQUIRE(geom && rays_o && dirs && d_vals, "null input");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
@@ -433,7 +463,7 @@ extern "C" int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid
 
 extern "C" int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const void* d_out,
                                    int64_t ld_out, int64_t d_plane, int32_t col0, const uint32_t* gmax_bits,
-                                   int32_t log2_headroom, int64_t* acc, int device, void* stream) {
+                                   int32_t log2_headroom, void* acc, int device, void* stream) {
     AVR_REQUIRE(u != nullptr || n_pts == 0, "null input");
     AVR_ENTER(device);
     Geom geo = {};

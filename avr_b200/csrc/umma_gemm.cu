@@ -26,7 +26,7 @@
 
 namespace avr {
 
-enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32, UF_BIAS = 64, UF_DEBUG_NOWAIT = 128 };
+enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32, UF_BIAS = 64, UF_DEBUG_NOWAIT = 128, UF_DEBUG_NOSTORE = 256, UF_DEBUG_NOSTAGE = 512, UF_DEBUG_NOFENCE = 1024 };
 
 struct UmmaParams {
     int M, N, K;            // K-major: rows, cols, reduction.  MN-major: A extent, B extent, reduction (points)
@@ -275,8 +275,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = bres ? bres_base + (uint32_t)(k0 / UBK) * b_tile_bytes : sa + a_tile_bytes;
+                    const int k_steps = min(UBK / 16, (p.K - k0 + 15) / 16);    // the zero-filled tail of the last block is skipped
 #pragma unroll
                     for (int j = 0; j < UBK / 16; ++j) {
+                        if (j >= k_steps) break;
                         uint64_t a_hi, a_lo, b_hi, b_lo;
                         if (!MN_MAJOR) {
                             a_hi = smem_desc(sa + 32 * j, 16, 1024);
@@ -459,10 +461,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int o = 0; o < n_out; ++o) {
                         if (lane == 0 && !(p.flags & UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
                         __syncwarp();
-                        stage_planes32(stage, lane, v, o == 1 || (p.flags & UF_RELU), p.nc);
-                        fence_async_smem();
+                        if (!(p.flags & UF_DEBUG_NOSTAGE)) stage_planes32(stage, lane, v, o == 1 || (p.flags & UF_RELU), p.nc);
+                        if (!(p.flags & UF_DEBUG_NOFENCE)) fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(p.flags & UF_DEBUG_NOSTORE)) {
                             const CUtensorMap* map = o == 0 ? &tmC : &tmC2;
                             for (int pl = 0; pl < p.nc; ++pl)
                                 tma_store_3d(map, stage + pl * EPI_PLANE_BYTES, n0 + c0, m0 + lane_grp * 32, pl);
@@ -674,7 +676,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     }
     p.bias_ray = bias_ray; p.bias_rcv = bias_rcv; p.ld_bias_ray = ld_bias_ray; p.ld_bias_rcv = ld_bias_rcv;
     p.geo_R = geo_R; p.geo_S = geo_S;
-    if (getenv("AVR_UMMA_NOWAIT")) p.flags |= UF_DEBUG_NOWAIT;       // timing experiment only: results are garbage
+    if (getenv("AVR_UMMA_NOWAIT")) p.flags |= UF_DEBUG_NOWAIT;       // timing experiments only: results are garbage
+    if (const char* dbg = getenv("AVR_UMMA_DEBUG")) p.flags |= (atoi(dbg) & (UF_DEBUG_NOWAIT | UF_DEBUG_NOSTORE | UF_DEBUG_NOSTAGE | UF_DEBUG_NOFENCE));
     p.c32 = c_f32; p.ldc32 = ldc32;
     const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
     const uint32_t epi_bytes = 4u * 3u * EPI_PLANE_BYTES + 4u * 1024u + 1024u;    // staging tiles + per-warp bias rows

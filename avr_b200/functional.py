@@ -33,7 +33,7 @@ class HashGridFunction(torch.autograd.Function):
         (u,) = ctx.saved_tensors
         enc = ctx.enc
         d_out = d_out.contiguous()
-        acc = ops.GridGradAccumulator(enc.meta, d_out.device, u.shape[0])
+        acc = ops.GridGradAccumulator(enc.meta, d_out.device, u.shape[0], None, enc.grid_grad)
         acc.observe(d_out, 0, enc.n_output_dims)
         acc.add_points(u, d_out)
         return None, acc.finalize(), None

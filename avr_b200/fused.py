@@ -128,19 +128,19 @@ class FusedRenderFunction(torch.autograd.Function):
         stacks["enc"].backward([(B["x0"], False)], B["acts_enc"], d_feat, g_enc, ws, [(d_x0, False, None)])
         grads[id(enc_net)] = g_enc
 
-        scratch = torch.empty(max(int(m.meta.total) * 2 for (m, _) in plan["x0"] + plan["tail"]), dtype=torch.int64,
-                              device=dev)
+        grids = [m for (m, _) in plan["x0"] + plan["tail"] if m.grid_grad == "deterministic"]
+        scratch = torch.empty(max(int(m.meta.total) * 2 for m in grids), dtype=torch.int64, device=dev) if grids else None
         for segments, d_buf in ((plan["x0"], d_x0), (plan["tail"], d_tail)):
             col = 0
             for mod, kind in segments:
                 wdt = mod.n_output_dims
                 if kind == "point":
-                    acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch)
+                    acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch, mod.grid_grad)
                     acc.observe(d_buf, col, wdt)
                     acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col)
                 else:
                     small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
-                    acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch)
+                    acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch, mod.grid_grad)
                     acc.observe(small, 0, wdt)
                     acc.add_points(ctx.small_in[kind], small)
                 grads[id(mod)] = acc.finalize()

@@ -60,6 +60,9 @@ class Encoding(nn.Module):
         n = self.geom["total"] * self.geom["n_feat"]
         self.params = nn.Parameter((torch.rand(n, generator=g) * 2 - 1) * 1e-4)      # tcnn: U(-1e-4, 1e-4)
         self._meta = None
+        #: how the table gradient is accumulated: "atomic" (fp32 vector reductions, fastest, run-to-run
+        #: differences in the last bits like tcnn) or "deterministic" (int64 fixed point, bit-reproducible)
+        self.grid_grad = "atomic"
 
     @property
     def meta(self):

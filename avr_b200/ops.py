@@ -201,11 +201,27 @@ def grid_encode_fwd(meta, u, table, out, col0=0, n_ones=0):
                                                _np(out), col0, n_ones, dev, st), "avr_grid_encode_fwd")
 
 
-class GridGradAccumulator:
-    """Deterministic fixed-point accumulation of hash-table gradients (see include/avr_b200.h)."""
+GRID_GRAD_F32 = -1       # include/avr_b200.h AVR_GRID_GRAD_F32
+GRID_GRAD_MODES = ("atomic", "deterministic")
 
-    def __init__(self, meta: GridMeta, device, n_points: int, scratch=None):
-        self.meta, self.n = meta, int(meta.total) * 2
+
+class GridGradAccumulator:
+    """Accumulation of hash-table gradients (see include/avr_b200.h).
+
+    ``mode="deterministic"``: 2^e-scaled int64 fixed point (bit-reproducible, two reductions per cell corner);
+    ``mode="atomic"``: fp32 vector reductions straight into the gradient (one per corner; the summation order
+    varies from run to run, as with tcnn's own atomics).
+    """
+
+    def __init__(self, meta: GridMeta, device, n_points: int, scratch=None, mode: str = "deterministic"):
+        if mode not in GRID_GRAD_MODES:
+            raise ValueError(f"grid_grad must be one of {GRID_GRAD_MODES}")
+        self.meta, self.n, self.mode = meta, int(meta.total) * 2, mode
+        if mode == "atomic":
+            self.headroom = GRID_GRAD_F32
+            self.acc = torch.zeros(self.n, dtype=torch.float32, device=device)
+            self.gmax = None
+            return
         self.headroom = headroom_bits(n_points)
         if scratch is not None and scratch.numel() >= self.n:
             self.acc = scratch[: self.n]
@@ -215,6 +231,8 @@ class GridGradAccumulator:
         self.gmax = torch.zeros(1, dtype=torch.int32, device=device)
 
     def observe(self, d_out, col0, ncols):
+        if self.mode == "atomic":
+            return
         dev, st = _ctx(d_out)
         ptr, ld, plane = _mat(d_out)
         _lib.check(_lib.load().avr_absmax_bits(ptr, _rows(d_out), ld, plane, col0, ncols, _p(self.gmax, torch.int32),
@@ -224,20 +242,25 @@ class GridGradAccumulator:
         dev, st = _ctx(d_out)
         ptr, ld, plane = _mat(d_out)
         n_pts = g.bs * g.R * g.S
-        with _timed("raygen_encode_bwd", float(n_pts) * self.meta.n_levels * 136, "byte"):   # 8 B d_out + 8 corners*16 B rmw
+        rmw = 8 if self.mode == "atomic" else 16                   # bytes read-modify-written per cell corner
+        with _timed("raygen_encode_bwd", float(n_pts) * self.meta.n_levels * (8 + 8 * rmw), "byte"):
             _lib.check(_lib.load().avr_raygen_encode_bwd(C.byref(g), C.byref(self.meta), _p(_dense(rays_o)),
                                                          _p(_dense(dirs)), _p(_dense(d_vals)), ptr, ld, plane, col0,
                                                          _p(self.gmax, torch.int32), self.headroom,
-                                                         _p(self.acc, torch.int64), dev, st), "avr_raygen_encode_bwd")
+                                                         C.c_void_p(self.acc.data_ptr()), dev, st), "avr_raygen_encode_bwd")
 
     def add_points(self, u, d_out, col0=0):
         dev, st = _ctx(d_out)
         ptr, ld, plane = _mat(d_out)
         _lib.check(_lib.load().avr_grid_encode_bwd(C.byref(self.meta), _p(_dense(u)), u.shape[0], ptr, ld, plane, col0,
                                                    _p(self.gmax, torch.int32), self.headroom,
-                                                   _p(self.acc, torch.int64), dev, st), "avr_grid_encode_bwd")
+                                                   C.c_void_p(self.acc.data_ptr()), dev, st), "avr_grid_encode_bwd")
 
     def finalize(self, grad=None, accumulate=False):
+        if self.mode == "atomic":
+            if grad is None:
+                return self.acc
+            return grad.add_(self.acc) if accumulate else grad.copy_(self.acc)
         if grad is None:
             grad = torch.empty(self.n, device=self.acc.device)
         dev, st = _ctx(grad)

@@ -50,6 +50,17 @@ class AVRRender(nn.Module):
         self.dense = kwargs.get("dense", "tc")
         if self.dense not in ("tc", "simt"):
             raise ValueError("dense must be 'tc' or 'simt'")
+        #: accumulation of the hash-table gradients, applied to every ``Encoding`` of the field when given:
+        #: "atomic" (default of ``Encoding``) or "deterministic" (bit-reproducible, ~0.7 ms/step slower on simu)
+        grid_grad = kwargs.get("grid_grad")
+        if grid_grad is not None:
+            from .model import Encoding
+            from .ops import GRID_GRAD_MODES
+            if grid_grad not in GRID_GRAD_MODES:
+                raise ValueError(f"grid_grad must be one of {GRID_GRAD_MODES}")
+            for m in networks_fn.modules():
+                if isinstance(m, Encoding):
+                    m.grid_grad = grid_grad
         self._tables = {}
 
     # -- configuration -----------------------------------------------------------------------------

@@ -111,14 +111,18 @@ AVR_API int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_me
                           void* out, int64_t ld_out, int64_t out_plane, int32_t out_nplanes, int32_t col0,
                           int32_t n_ones, int32_t* delay, int device, void* stream);
 
-/* Backward of the above w.r.t. the table (tcnn kernel_grid_backward), DETERMINISTIC:
- * contributions are accumulated as 2^e-scaled int64 (integer addition is associative), `e`
- * derived on the device from absmax(d_out) and `log2_headroom` >= log2(max contributions per
- * entry).  acc[total*2] int64 must be zeroed by the caller (or hold a previous partial sum
- * taken with the same gmax_bits); gmax_bits is a device uint32 filled by avr_absmax_bits. */
+/* Backward of the above w.r.t. the table (tcnn kernel_grid_backward).  Two accumulation modes:
+ *   log2_headroom in [0,56]  DETERMINISTIC: contributions are accumulated as 2^e-scaled int64 (integer addition is
+ *     associative), `e` derived on the device from absmax(d_out) and `log2_headroom` >= log2(max contributions
+ *     per entry).  acc[total*2] is int64, zeroed by the caller (or holding a previous partial sum taken with the
+ *     same gmax_bits); gmax_bits is a device uint32 filled by avr_absmax_bits; avr_grid_grad_finalize converts.
+ *   log2_headroom == AVR_GRID_GRAD_F32  acc[total*2] is the fp32 gradient itself (zeroed, or a partial sum); one
+ *     red.global.add.v2.f32 per cell corner (half the reductions of the int64 mode, summation order -- and
+ *     so the last bits -- vary from run to run, as in tcnn); gmax_bits is ignored and may be NULL. */
+#define AVR_GRID_GRAD_F32 (-1)
 AVR_API int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
                           const float* dirs, const float* d_vals, const void* d_out, int64_t ld_out,
-                          int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, int64_t* acc,
+                          int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, void* acc,
                           int device, void* stream);
 
 /* Encode explicit unit-cube points u[N,3] (model.py:191,219-220 on arbitrary inputs). */
@@ -127,7 +131,7 @@ AVR_API int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, int64
                         int device, void* stream);
 AVR_API int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const void* d_out,
                         int64_t ld_out, int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
-                        int64_t* acc, int device, void* stream);
+                        void* acc, int device, void* stream);
 /* gmax_bits = max(gmax_bits, bit pattern of max |x[i, col0:col0+ncols]|)  (caller zeroes it first) */
 AVR_API int avr_absmax_bits(const void* x, int64_t rows, int64_t ld, int64_t plane, int32_t col0, int32_t ncols,
                     uint32_t* gmax_bits, int device, void* stream);

@@ -104,6 +104,15 @@ def test_grid_encode_fwd_bwd_vs_oracle(built_library, which, n):
         grads.append(acc.finalize().cpu())
     assert torch.equal(grads[0], grads[1])                                        # bit-identical reruns
     assert rel_l2(grads[0], enc.params.grad) < 1e-5
+    # backward, fp32 vector reductions straight into the gradient (AVR_GRID_GRAD_F32)
+    acc = ops.GridGradAccumulator(meta, DEV, n, mode="atomic")
+    acc.observe(dbuf, 4, W)
+    acc.add_points(u.to(DEV), dbuf, col0=4)
+    fast = acc.finalize().cpu()
+    assert rel_l2(fast, enc.params.grad) < 1e-5 and rel_l2(fast, grads[0]) < 1e-5
+    again = torch.ones_like(grads[0]).to(DEV)
+    acc.finalize(again, accumulate=True)
+    assert torch.equal(again.cpu(), fast + 1.0)
 
 
 def test_grid_grad_zero_and_nan_inputs(built_library):
@@ -296,3 +305,30 @@ def test_rows_broadcast_and_reduce(built_library):
         red = ops.rows_reduce(geom, d.to(DEV), 8, 12, per_receiver)
         ref = torch.zeros(rows, 12, dtype=torch.float64).index_add_(0, row, d[:, 8:20].double())
         assert rel_l2(red, ref) < 1e-6
+
+
+@pytest.mark.parametrize("w,col0,nplanes", [(40, 8, 3), (40, 48, 2), (16, 0, 3), (12, 8, 3)])
+def test_rows_broadcast_and_reduce_plane_sets(built_library, w, col0, nplanes):
+    """bf16 plane-set windows (the signal-network input): 16-byte vector path (w, col0 multiples of 8) and scalar path."""
+    from avr_b200.ops import PlanePair
+    geom = ops.RenderGeom(3, 37, 6, 200, -10.0, 20.0, 16000.0, 343.8)
+    n = 3 * 37 * 6
+    g = torch.Generator().manual_seed(w + col0)
+    idx = torch.arange(n)
+    for per_receiver, rows in ((False, 37), (True, 3)):
+        row = idx // (37 * 6) if per_receiver else (idx // 6) % 37
+        src = torch.randn(rows, w, generator=g)
+        dst = PlanePair.empty(n, 96, DEV, n=nplanes)
+        dst.buf.zero_()
+        ops.rows_broadcast(geom, src.to(DEV), per_receiver, dst, col0)
+        got = dst.buf.float().sum(0).cpu()                       # planes add up to the fp32 value
+        tol = 2.0 ** -16 if nplanes == 2 else 2.0 ** -23
+        assert float((got[:, col0:col0 + w] - src[row]).abs().max()) <= tol * float(src.abs().max())
+        assert float(got[:, :col0].abs().max() if col0 else 0.0) == 0 and float(got[:, col0 + w:].abs().max()) == 0
+        d = PlanePair.empty(n, 96, DEV, n=nplanes)
+        d.buf.normal_(generator=torch.Generator(device=DEV).manual_seed(1))
+        red = ops.rows_reduce(geom, d, col0, w, per_receiver)
+        two = d.buf[:2].float().sum(0).cpu()                     # readers of plane sets use the first two planes
+        ref = torch.zeros(rows, w, dtype=torch.float64).index_add_(0, row, two[:, col0:col0 + w].double())
+        assert rel_l2(red, ref) < 1e-6
+        assert torch.equal(red, ops.rows_reduce(geom, d, col0, w, per_receiver))

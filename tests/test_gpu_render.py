@@ -112,7 +112,7 @@ def test_backward_is_deterministic_and_chunking_is_transparent(built_library):
     azi = torch.rand(8, generator=gen)
     runs = []
     for chunk in (8, 8, 2):
-        ren = avr_b200.AVRRender(native, **cfg["render"], max_receivers_per_pass=chunk)
+        ren = avr_b200.AVRRender(native, **cfg["render"], max_receivers_per_pass=chunk, grid_grad="deterministic")
         native.zero_grad(set_to_none=True)
         out = ren(rx, tx, azi_rand=azi)
         out.square().sum().backward()
@@ -123,6 +123,14 @@ def test_backward_is_deterministic_and_chunking_is_transparent(built_library):
     assert rel_l2(runs[2][0], runs[0][0]) < 1e-6
     for a, b in zip(runs[2][1], runs[0][1]):
         assert rel_l2(a, b) < 1e-5
+    # the default fp32-atomic table gradients agree with the fixed-point ones to rounding
+    ren = avr_b200.AVRRender(native, **cfg["render"], grid_grad="atomic")
+    native.zero_grad(set_to_none=True)
+    ren(rx, tx, azi_rand=azi).square().sum().backward()
+    for p, b in zip(native.parameters(), runs[0][1]):
+        assert rel_l2(p.grad, b) < 1e-5
+    with pytest.raises(ValueError):
+        avr_b200.AVRRender(native, **cfg["render"], grid_grad="sorted")
 
 
 def test_standalone_field_matches_oracle(built_library):
@@ -165,7 +173,7 @@ def test_full_size_simu_properties(built_library):
         for m in native.modules():
             if isinstance(m, avr_b200.Encoding):
                 m.params.normal_(0, 0.1)
-    ren = avr_b200.AVRRender(native, **cfg["render"])
+    ren = avr_b200.AVRRender(native, **cfg["render"], grid_grad="deterministic")
     rx = torch.tensor([[1.0, -2.0, 0.5]], device=DEV)
     tx = torch.tensor([[-1.5, 1.0, 0.0]], device=DEV)
     azi = torch.rand(64)
@@ -200,7 +208,7 @@ def test_full_size_other_configs(built_library, name, bs):
             if isinstance(m, avr_b200.Encoding):
                 m.params.normal_(0, 0.1)
     r = cfg["render"]
-    ren = avr_b200.AVRRender(native, **r)
+    ren = avr_b200.AVRRender(native, **r, grid_grad="deterministic")
     gen = torch.Generator().manual_seed(3)
     c = (r["xyz_min"] + r["xyz_max"]) / 2
     rx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 1.5).to(DEV)
