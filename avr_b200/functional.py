@@ -60,7 +60,7 @@ class DenseStack:
         for k, (x, relu_in) in enumerate(parts):
             w = self.mats[0][:, c0:c0 + x.shape[1]]
             last = k == len(parts) - 1
-            ops.linear_fwd(x, w, h, relu=last, relu_in=relu_in, accum=k > 0)
+            ops.linear_fwd(x, w, h, relu=last and len(self.mats) > 1, relu_in=relu_in, accum=k > 0)
             c0 += x.shape[1]
         assert c0 == self.mats[0].shape[1], "input blocks do not cover the first matrix"
         acts.append(h)

@@ -15,7 +15,9 @@ from .functional import DenseStack
 
 
 def plan_modules(plan: dict):
-    return [m for (m, _) in plan["x0"]] + [m for (m, _) in plan["tail"]] + [plan["enc"], plan["dec"], plan["sig"]]
+    """Modules whose flat ``params`` the fused step differentiates (per-receiver row blocks carry no parameters here)."""
+    segs = plan["x0"] + plan["tail"]
+    return [m for (m, kind) in segs if kind != "receiver_rows"] + [plan["enc"], plan["dec"], plan["sig"]]
 
 
 def _assemble(segments, total_width, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot):
@@ -128,7 +130,7 @@ class FusedRenderFunction(torch.autograd.Function):
         stacks["enc"].backward([(B["x0"], False)], B["acts_enc"], d_feat, g_enc, ws, [(d_x0, False, None)])
         grads[id(enc_net)] = g_enc
 
-        grids = [m for (m, _) in plan["x0"] + plan["tail"] if m.grid_grad == "deterministic"]
+        grids = [m for (m, kind) in plan["x0"] + plan["tail"] if kind != "receiver_rows" and m.grid_grad == "deterministic"]
         scratch = torch.empty(max(int(m.meta.total) * 2 for m in grids), dtype=torch.int64, device=dev) if grids else None
         for segments, d_buf in ((plan["x0"], d_x0), (plan["tail"], d_tail)):
             col = 0

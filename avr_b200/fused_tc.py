@@ -33,11 +33,14 @@ def _weight_planes(net, params, transpose, n):
     return out
 
 
-def _assemble(segments, buf: PlanePair, col, end_col, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot):
+def _assemble(segments, buf: PlanePair, col, end_col, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot,
+              rows_of=None):
     """Encode ``segments`` into columns ``[col, ...)`` of ``buf``; pad up to ``end_col`` with ones."""
     dev = rays_o.device
+    if not segments and end_col > col:
+        segments = [(None, "ones")]
     for k, (mod, kind) in enumerate(segments):
-        w = mod.n_output_dims
+        w = mod.n_output_dims if mod is not None else 0
         last = k == len(segments) - 1
         n_ones = end_col - (col + w) if last else 0
         if kind == "point":
@@ -45,10 +48,13 @@ def _assemble(segments, buf: PlanePair, col, end_col, geom, small_in, rays_o, po
             ops.raygen_encode_fwd(geom, mod.meta, rays_o, pos_tx, dirs, d_vals, params_of(mod), buf, col0=col,
                                   n_ones=n_ones, delay=delay)
         else:
-            u = small_in[kind]
-            small = torch.empty(u.shape[0], w, device=dev)
-            ops.grid_encode_fwd(mod.meta, u, params_of(mod), small)
-            ops.rows_broadcast(geom, small, kind != "ray", buf, col)
+            if kind == "receiver_rows":                                      # channel-embedding rows (model.py:201-203)
+                ops.rows_broadcast(geom, rows_of[mod.key], True, buf, col)
+            elif kind != "ones":
+                u = small_in[kind]
+                small = torch.empty(u.shape[0], w, device=dev)
+                ops.grid_encode_fwd(mod.meta, u, params_of(mod), small)
+                ops.rows_broadcast(geom, small, kind != "ray", buf, col)
             if n_ones:                                                       # tcnn pads the network input with ones
                 c0 = buf.col0 + col + w
                 buf.buf[0, :, c0:c0 + n_ones] = 1.0
@@ -63,6 +69,18 @@ class FusedRenderTC(torch.autograd.Function):
         mods = plan_modules(plan)
         pmap = {id(m): p.detach() for m, p in zip(mods, params)}
         params_of = lambda m: pmap[id(m)]                                    # noqa: E731
+        # per-receiver channel-embedding rows: biases of hidden layers / blocks of network inputs
+        roles = plan.get("extras", [])
+        extras = [t.detach().float().contiguous() for t in params[len(mods):]]
+        if len(extras) != len(roles):
+            raise ValueError("plan extras and extra tensors do not match")
+        bias_of = {(r[1], r[2]): t for r, t in zip(roles, extras) if r[0] == "bias"}
+        rows_of = {r[1]: t for r, t in zip(roles, extras) if r[0] == "rows"}
+
+        def layer_flags(net_key, li):
+            b = bias_of.get((net_key, li))
+            return (ops.UMMA_RELU | ops.UMMA_BIAS, dict(bias_rcv=b, geom=geom)) if b is not None else (ops.UMMA_RELU, {})
+
         enc_net, dec_net, sig_net = plan["enc"], plan["dec"], plan["sig"]
         feat_dim, T = plan["feat_dim"], geom.T
         if sig_net.out_pad != T or T % 8:
@@ -79,7 +97,8 @@ class FusedRenderTC(torch.autograd.Function):
 
         # ---- sigma encoder ------------------------------------------------------------------------
         x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
-        _assemble(plan["x0"], x0, 0, enc_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot)
+        _assemble(plan["x0"], x0, 0, enc_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot,
+                  rows_of)
         if delay_slot:
             _, _, _, delay = ops.sample_points(geom, rays_o, pos_tx, dirs, d_vals, want_pts=False)
         w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_PLANES)
@@ -87,7 +106,8 @@ class FusedRenderTC(torch.autograd.Function):
         for li in range(len(w_enc) - 1):
             y = PlanePair.empty(n_rows, w_enc[li].rows, dev, n=FWD_PLANES)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev)
-            ops.umma_nt(h, w_enc[li], ops.UMMA_RELU, y, bits_out=bits)
+            fl, kw = layer_flags("enc", li)
+            ops.umma_nt(h, w_enc[li], fl, y, bits_out=bits, **kw)
             acts_enc.append(y)
             bits_enc.append(bits)
             h = y
@@ -99,8 +119,14 @@ class FusedRenderTC(torch.autograd.Function):
             ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat)        # both consumers read relu(feat)
             dec_in = feat_win
         else:
-            dec_in = PlanePair.empty(n_rows, feat_dim, dev, n=FWD_PLANES)
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_in, bits_out=bits_feat)   # raw feat + relu(feat)
+            dec_buf = PlanePair.empty(n_rows, dec_net.in_pad, dev, n=FWD_PLANES)
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_buf.window(0, feat_dim), bits_out=bits_feat)   # raw feat + relu(feat)
+            if dec_net.in_pad > feat_dim:                                    # decoder input = [relu(feat), embedding row]
+                _assemble(plan.get("dec_tail", []), dec_buf, feat_dim, dec_net.in_pad, geom, small_in, rays_o, pos_tx, dirs,
+                          d_vals, params_of, [], rows_of)
+            dec_in = dec_buf
+        if dec_in.cols != dec_net.in_pad:
+            raise NotImplementedError("sigma decoder input width does not match the sigma feature width")
 
         # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
         w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_PLANES)
@@ -108,7 +134,8 @@ class FusedRenderTC(torch.autograd.Function):
         for li in range(len(w_dec) - 1):
             y = PlanePair.empty(n_rows, w_dec[li].rows, dev, n=FWD_PLANES)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev)
-            ops.umma_nt(h, w_dec[li], ops.UMMA_RELU, y, bits_out=bits)
+            fl, kw = layer_flags("dec", li)
+            ops.umma_nt(h, w_dec[li], fl, y, bits_out=bits, **kw)
             acts_dec.append(y)
             bits_dec.append(bits)
             h = y
@@ -118,14 +145,15 @@ class FusedRenderTC(torch.autograd.Function):
 
         # ---- signal network hidden layers + collapsed output layer ---------------------------------
         _assemble(plan["tail"], sig_in, feat_dim, sig_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals,
-                  params_of, [])
+                  params_of, [], rows_of)
         sig_mats = sig_net.matrices(params_of(sig_net))
         w_sig = _weight_planes(sig_net, params_of(sig_net), False, FWD_PLANES)[:-1]
         acts_sig, bits_sig, h = [], [], sig_in
         for li in range(len(w_sig)):
             y = PlanePair.empty(n_rows, w_sig[li].rows, dev, n=FWD_PLANES)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev) if li < len(w_sig) - 1 else None   # last one is read by collapse
-            ops.umma_nt(h, w_sig[li], ops.UMMA_RELU, y, bits_out=bits)
+            fl, kw = layer_flags("sig", li)
+            ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, **kw)
             acts_sig.append(y)
             bits_sig.append(bits)
             h = y
@@ -135,7 +163,7 @@ class FusedRenderTC(torch.autograd.Function):
 
         if any(ctx.needs_input_grad[8:]):
             ctx.plan, ctx.geom, ctx.tables, ctx.tspan = plan, geom, tables, tspan
-            ctx.small_in = small_in
+            ctx.small_in, ctx.roles = small_in, roles
             ctx.bufs = dict(x0=x0, acts_enc=acts_enc, sig_in=sig_in, dec_in=dec_in, acts_dec=acts_dec, dec_out=dec_out,
                             acts_sig=acts_sig, sort=sort, prefix=prefix, bits_enc=bits_enc, bits_dec=bits_dec, bits_sig=bits_sig,
                             bits_feat=bits_feat)
@@ -148,6 +176,14 @@ class FusedRenderTC(torch.autograd.Function):
         rays_o, dirs, *params = ctx.saved_tensors
         mods = plan_modules(plan)
         pmap = {id(m): p.detach() for m, p in zip(mods, params)}
+        extra_grads = {}                                                     # role -> gradient of that extra tensor
+        bias_layers = {(r[1], r[2]) for r in ctx.roles if r[0] == "bias"}
+
+        def bias_grad(net_key, li, g):
+            """d(embedding row) = sum of the layer's pre-activation gradient over each receiver's points."""
+            if (net_key, li) in bias_layers:
+                extra_grads[("bias", net_key, li)] = ops.rows_reduce(geom, g, 0, g.cols, True)
+
         enc_net, dec_net, sig_net = plan["enc"], plan["dec"], plan["sig"]
         feat_dim = plan["feat_dim"]
         dev = d_out.device
@@ -157,17 +193,19 @@ class FusedRenderTC(torch.autograd.Function):
         ws_bytes = max(ops.umma_tn_workspace_bytes(o, i, n_rows) for n in (enc_net, dec_net, sig_net) for (o, i) in n.shapes)
         ws = torch.empty(max(4, ws_bytes // 4), device=dev)
 
-        def hidden_backward(net, g, acts, bits, first_input, g_flat):
+        def hidden_backward(net, net_key, g, acts, bits, first_input, g_flat):
             """Back-propagate through layers len(acts)..1 of ``net`` given g = d(pre-activation of the last
             hidden layer); fills the weight gradients of layers >= 1 and of layer 0; returns g at layer 0."""
             wt = _weight_planes(net, pmap[id(net)], True, BWD_PLANES)
             d_mats = net.matrices(g_flat)
+            bias_grad(net_key, len(acts) - 1, g)
             for li in range(len(acts) - 1, 0, -1):
                 x = acts[li - 1]
                 ops.umma_tn(g, x, d_mats[li], ws)
                 gx = PlanePair.empty(n_rows, x.cols, dev)
                 ops.umma_nt(g, wt[li], ops.UMMA_MASK, gx, mask=bits[li - 1])
                 g = gx
+                bias_grad(net_key, li - 1, g)
             ops.umma_tn(g, first_input, d_mats[0], ws)
             return g, wt, d_mats
 
@@ -183,7 +221,7 @@ class FusedRenderTC(torch.autograd.Function):
 
         # ---- signal network hidden layers ----------------------------------------------------------------
         sig_in, dec_in = B["sig_in"], B["dec_in"]
-        g, wt_sig, _ = hidden_backward(sig_net, g, B["acts_sig"], B["bits_sig"], sig_in, g_sig)
+        g, wt_sig, _ = hidden_backward(sig_net, "sig", g, B["acts_sig"], B["bits_sig"], sig_in, g_sig)
         grads[id(sig_net)] = g_sig
         d_feat = PlanePair.empty(n_rows, feat_dim, dev)
         wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
@@ -213,8 +251,13 @@ class FusedRenderTC(torch.autograd.Function):
             gx = PlanePair.empty(n_rows, x.cols, dev)
             ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=B["bits_dec"][li - 1])
             g = gx
+            bias_grad("dec", li - 1, g)
         ops.umma_tn(g, dec_in, d_dec_mats[0], ws)
-        ops.umma_nt(g, wt_dec[0], ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=B["bits_feat"])   # d_feat += relu'(feat) * ...
+        ops.umma_nt(g, wt_dec[0].row_window(0, feat_dim), ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=B["bits_feat"])   # d_feat += relu'(feat) * ...
+        d_dec_tail = None
+        if dec_net.in_pad > feat_dim and plan.get("dec_tail"):
+            d_dec_tail = PlanePair.empty(n_rows, dec_net.in_pad - feat_dim, dev)
+            ops.umma_nt(g, wt_dec[0].row_window(feat_dim, dec_net.in_pad - feat_dim), 0, d_dec_tail)
         grads[id(dec_net)] = g_dec
 
         # ---- sigma encoder -----------------------------------------------------------------------------------
@@ -229,6 +272,7 @@ class FusedRenderTC(torch.autograd.Function):
             gx = PlanePair.empty(n_rows, x.cols, dev)
             ops.umma_nt(g, wt_enc[li], ops.UMMA_MASK, gx, mask=B["bits_enc"][li - 1])
             g = gx
+            bias_grad("enc", li - 1, g)
         x0 = B["x0"]
         ops.umma_tn(g, x0, d_enc_mats[0], ws)
         d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
@@ -236,12 +280,16 @@ class FusedRenderTC(torch.autograd.Function):
         grads[id(enc_net)] = g_enc
 
         # ---- hash tables (scatter; mode per Encoding.grid_grad) ---------------------------------------------------
-        grids = [m for (m, _) in plan["x0"] + plan["tail"] if m.grid_grad == "deterministic"]
+        grids = [m for (m, kind) in plan["x0"] + plan["tail"] if kind != "receiver_rows" and m.grid_grad == "deterministic"]
         scratch = torch.empty(max(int(m.meta.total) * 2 for m in grids), dtype=torch.int64, device=dev) if grids else None
-        for segments, d_buf in ((plan["x0"], d_x0), (plan["tail"], d_tail)):
+        for segments, d_buf in ((plan["x0"], d_x0), (plan["tail"], d_tail), (plan.get("dec_tail", []), d_dec_tail)):
             col = 0
             for mod, kind in segments:
                 wdt = mod.n_output_dims
+                if kind == "receiver_rows":
+                    extra_grads[("rows", mod.key)] = ops.rows_reduce(geom, d_buf, col, wdt, True)
+                    col += wdt
+                    continue
                 if kind == "point":
                     acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch, mod.grid_grad)
                     acc.observe(d_buf, col, wdt)
@@ -254,4 +302,4 @@ class FusedRenderTC(torch.autograd.Function):
                 grads[id(mod)] = acc.finalize()
                 col += wdt
         ctx.bufs = None
-        return (None,) * 8 + tuple(grads[id(m)] for m in mods)
+        return (None,) * 8 + tuple(grads[id(m)] for m in mods) + tuple(extra_grads[tuple(r)] for r in ctx.roles)

@@ -91,8 +91,8 @@ class Network(nn.Module):
         align = 16 if network_config.get("otype", "FullyFusedMLP") == "FullyFusedMLP" else 8
         self.width = int(network_config["n_neurons"])
         self.n_hidden = int(network_config["n_hidden_layers"])
-        if self.n_hidden < 1:
-            raise NotImplementedError("n_hidden_layers must be >= 1")
+        if self.n_hidden < 0:
+            raise ValueError("n_hidden_layers must be >= 0")
         if self.width % 4:
             raise NotImplementedError("n_neurons must be a multiple of 4")
         self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
@@ -114,47 +114,172 @@ class Network(nn.Module):
         return Fn.MLPFunction.apply(x.contiguous().float(), self.params, self)
 
 
-def _reject_channel_embedding(cfg: dict) -> None:
+class InjectionNetwork(nn.Module):
+    """``LayeredTCNNWithInjection`` (``/root/reference/model.py:11-61``): every hidden layer is its own single-matrix
+    network (``n_hidden_layers: 0``, linear) followed by ``h + layer_embeddings[l][ch_id]`` and ReLU; a linear
+    output layer.  Sub-module / parameter names follow the reference (``hidden_layers.{l}.params``,
+    ``layer_embeddings.{l}``, ``output_layer.params``).
+
+    For the fused render step the layers present themselves as one ``Network``-shaped stack (``shapes``,
+    ``matrices``, a concatenated ``params``); the embedding rows enter the tensor-core GEMM epilogue as a
+    per-receiver bias (``AVR_UMMA_BIAS``).
+    """
+
+    def __init__(self, n_input_dims: int, n_neurons: int, n_hidden_layers: int, n_output_dims: int, ch_num: int,
+                 activation: str = "ReLU", otype: str = "FullyFusedMLP", seed: int = 1337):
+        super().__init__()
+        if activation != "ReLU":
+            raise NotImplementedError("only ReLU")
+        if n_hidden_layers < 1:
+            raise ValueError("n_hidden_layers must be >= 1")
+        one = {"otype": otype, "activation": "ReLU", "output_activation": "None", "n_neurons": n_neurons,
+               "n_hidden_layers": 0}
+        align = 16 if otype == "FullyFusedMLP" else 8
+        if n_neurons % align:
+            raise NotImplementedError("n_neurons must be a multiple of the tcnn padding (16 / 8)")
+        self.hidden_layers = nn.ModuleList()
+        self.layer_embeddings = nn.ParameterList()
+        g = torch.Generator().manual_seed(seed + 100)
+        in_dim = n_input_dims
+        for i in range(n_hidden_layers):
+            self.hidden_layers.append(Network(in_dim, n_neurons, one, seed + 10 * (i + 1)))
+            self.layer_embeddings.append(nn.Parameter(torch.randn(ch_num, n_neurons, generator=g) / math.sqrt(n_neurons)))
+            in_dim = n_neurons
+        self.output_layer = Network(in_dim, n_output_dims, one, seed + 10 * (n_hidden_layers + 1))
+        self.width, self.n_hidden = int(n_neurons), int(n_hidden_layers)
+        self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
+        self.in_pad, self.out_pad = self.hidden_layers[0].in_pad, self.output_layer.out_pad
+        self.shapes = [layer.shapes[0] for layer in self._layers()]
+
+    def _layers(self):
+        return list(self.hidden_layers) + [self.output_layer]
+
+    @property
+    def params(self) -> torch.Tensor:
+        """All matrices as one flat tensor (autograd splits the gradient back to the per-layer parameters)."""
+        return torch.cat([layer.params for layer in self._layers()])
+
+    matrices = Network.matrices
+
+    def bias_rows(self, ch_idx: torch.Tensor):
+        """Per-receiver pre-activation bias of every hidden layer: ``[bs, n_neurons]`` each."""
+        return [emb[ch_idx] for emb in self.layer_embeddings]
+
+    def forward(self, x: torch.Tensor, ch_id=None) -> torch.Tensor:
+        for idx, layer in enumerate(self.hidden_layers):
+            h = layer(x)
+            if ch_id is not None:
+                h = h + self.layer_embeddings[idx][ch_id]
+            x = torch.relu(h)
+        return self.output_layer(x)
+
+
+class RowsInput:
+    """A per-receiver ``[bs, width]`` block of a network input (a channel-embedding row, 'concat' mode)."""
+
+    def __init__(self, key: str, width: int):
+        self.key, self.n_output_dims = key, int(width)
+
+
+def channel_embed_modes(cfg: dict):
+    """``model.py:71-90`` -> ({enc,dec,sig: 'injection'|'concat'|'none'}, embedding widths, ch_num)."""
     ch = cfg.get("channel_embed") or {}
-    if ch.get("is_embed", False) and ch.get("connection_type", None) in ("add", "concat"):
-        raise NotImplementedError(
-            "channel_embed.connection_type add/concat (model.py:11-61,108-113) is not built yet; the five "
-            "BASELINE configs do not set it (SURVEY 8a row a4'')")
+    is_embed, conn = ch.get("is_embed", False), ch.get("connection_type", None)
+    mode = {}
+    for k, name in (("enc", "sigma_encoder"), ("dec", "sigma_decoder"), ("sig", "signal_network")):
+        on = is_embed and bool(ch.get("is_" + name, False))
+        mode[k] = "injection" if on and conn == "add" else "concat" if on and conn == "concat" else "none"
+    dims = {"enc": int(ch.get("emb_dim_sigma_encoder", 0)), "dec": int(ch.get("emb_dim_sigma_decoder", 0)),
+            "sig": int(ch.get("emb_dim_signal_network", 0))}
+    return mode, dims, int(ch.get("ch_num", 0))
 
 
 class AVRModel(nn.Module):
-    """``/root/reference/model.py:63-235`` (MeshRIR / Simu / Real_env)."""
+    """``/root/reference/model.py:63-235`` (MeshRIR / Simu / Real_env), channel-embedding variants included
+    (``channel_embed.connection_type: add | concat``, ``model.py:71-181,193-228``)."""
+
+    _NETS = {"enc": ("_model_encoder_sigma", "encoder_channel_embedding", "sigma_encoder_network", "FullyFusedMLP"),
+             "dec": ("_model_decoder_sigma", "decoder_channel_embedding", "sigma_decoder_network", "FullyFusedMLP"),
+             "sig": ("_model_signal", "signal_channel_embedding", "signal_network", "CutlassMLP")}
 
     def __init__(self, cfg: dict, seed: int = 1337):
         super().__init__()
-        _reject_channel_embedding(cfg)
         self._pos_encoding = Encoding(3, cfg["pos_encoding_sigma"], seed=seed)
         self._dir_encoding = Encoding(3, cfg["dir_encoding_sig"], seed=seed + 1)
         self._tx_encoding = Encoding(3, cfg["tx_encoding_sig"], seed=seed + 2)
         self.signal_output_dim = int(cfg["signal_output_dim"])
-        self._model_encoder_sigma = Network(self._pos_encoding.n_output_dims, 128, cfg["sigma_encoder_network"], seed + 3)
-        self._model_decoder_sigma = Network(128, 1, cfg["sigma_decoder_network"], seed + 4)
-        sig_in = 128 + self._dir_encoding.n_output_dims + self._tx_encoding.n_output_dims
-        self._model_signal = Network(sig_in, self.signal_output_dim, cfg["signal_network"], seed + 5)
+        self.embed_mode, emb_dims, self.ch_num = channel_embed_modes(cfg)
+        self.encoder_mode, self.decoder_mode, self.signal_mode = (self.embed_mode[k] for k in ("enc", "dec", "sig"))
+        base_in = {"enc": self._pos_encoding.n_output_dims, "dec": 128,
+                   "sig": 128 + self._dir_encoding.n_output_dims + self._tx_encoding.n_output_dims}
+        n_out = {"enc": 128, "dec": 1, "sig": self.signal_output_dim}
+        g = torch.Generator().manual_seed(seed + 50)
+        for k, off in (("enc", 3), ("dec", 4), ("sig", 5)):
+            attr, emb_attr, cfg_key, default_otype = self._NETS[k]
+            ncfg = cfg[cfg_key]
+            if self.embed_mode[k] == "injection":
+                net = InjectionNetwork(base_in[k], int(ncfg["n_neurons"]), int(ncfg["n_hidden_layers"]), n_out[k],
+                                       self.ch_num, ncfg.get("activation", "ReLU"), ncfg.get("otype", default_otype),
+                                       seed + off)
+            else:
+                n_in = base_in[k]
+                if self.embed_mode[k] == "concat":
+                    if emb_dims[k] < 1 or self.ch_num < 1:
+                        raise ValueError("channel_embed concat needs ch_num and a positive emb_dim_* for the network")
+                    setattr(self, emb_attr, nn.Parameter(torch.randn(self.ch_num, emb_dims[k], generator=g) /
+                                                         math.sqrt(emb_dims[k])))
+                    n_in += emb_dims[k]
+                net = Network(n_in, n_out[k], ncfg, seed + off)
+            setattr(self, attr, net)
         self.leaky_slope = 0.01      # model.py:233 -- F.leaky_relu default, cfg["leaky_relu"] is ignored
+
+    def _run(self, k, x, ch):
+        attr, emb_attr = self._NETS[k][:2]
+        net = getattr(self, attr)
+        if self.embed_mode[k] == "injection":
+            return net(x, ch)
+        if self.embed_mode[k] == "concat":
+            if ch is None:
+                raise ValueError("this field concatenates a channel embedding: ch_idx is required")
+            x = torch.cat([x, getattr(self, emb_attr)[ch]], -1)
+        return net(x)
 
     def forward(self, pts, view, tx, ch_idx=None):
         bs, n_pts = pts.size(0), pts.size(1)
+        ch = ch_idx.unsqueeze(1).expand(-1, n_pts).reshape(-1) if ch_idx is not None else None
         u_pts = Fn.unit_cube(pts)
-        sigma_feat = self._model_encoder_sigma(self._pos_encoding(u_pts))
-        attn = self._model_decoder_sigma(torch.relu(sigma_feat))
+        sigma_feat = self._run("enc", self._pos_encoding(u_pts), ch)
+        attn = self._run("dec", torch.relu(sigma_feat), ch)
         sig_in = torch.cat([sigma_feat, self._dir_encoding(Fn.unit_cube(view)), self._tx_encoding(Fn.unit_cube(tx))], -1)
-        signal = self._model_signal(sig_in)
+        signal = self._run("sig", sig_in, ch)
         attn = torch.abs(torch.nn.functional.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)
         return attn, signal.view(bs, n_pts, self.signal_output_dim)
 
-    def fused_plan(self) -> dict:
-        return {
-            "x0": [(self._pos_encoding, "point")],
+    def fused_plan(self, ch_idx=None) -> dict:
+        """What the fused render step needs.  With a channel embedding the per-receiver rows (gathered here, under
+        autograd) ride along as ``extra_tensors``: ``('bias', net, layer)`` rows are added to a hidden layer's
+        pre-activation in the GEMM epilogue, ``('rows', key)`` blocks are broadcast into a network input."""
+        plan = {
+            "x0": [(self._pos_encoding, "point")], "dec_tail": [],
             "tail": [(self._dir_encoding, "ray"), (self._tx_encoding, "receiver_tx")],
             "enc": self._model_encoder_sigma, "dec": self._model_decoder_sigma, "sig": self._model_signal,
             "feat_dim": 128, "sig_relu_feat": False, "slope": self.leaky_slope, "needs_dir_tx": False,
+            "extras": [], "extra_tensors": [],
         }
+        for k, seg in (("enc", "x0"), ("dec", "dec_tail"), ("sig", "tail")):
+            attr, emb_attr = self._NETS[k][:2]
+            if self.embed_mode[k] == "injection" and ch_idx is not None:
+                for li, rows in enumerate(getattr(self, attr).bias_rows(ch_idx)):
+                    plan["extras"].append(("bias", k, li))
+                    plan["extra_tensors"].append(rows)
+            elif self.embed_mode[k] == "concat":
+                if ch_idx is None:
+                    raise ValueError("this field concatenates a channel embedding: ch_idx is required")
+                emb = getattr(self, emb_attr)
+                plan[seg].append((RowsInput(emb_attr, emb.shape[1]), "receiver_rows"))
+                plan["extras"].append(("rows", emb_attr))
+                plan["extra_tensors"].append(emb[ch_idx])
+        return plan
 
 
 class AVRModel_complex(nn.Module):

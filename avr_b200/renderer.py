@@ -106,14 +106,16 @@ class AVRRender(nn.Module):
         net = self.network_fn
         bs = rays_o.size(0)
         if hasattr(net, "fused_plan"):
-            plan = net.fused_plan()
+            plan = net.fused_plan(ch_idx) if "ch_idx" in inspect.signature(net.fused_plan).parameters else net.fused_plan()
             if plan["needs_dir_tx"] and direction_tx is None:
                 raise ValueError("this field needs direction_tx (AVRModel_complex, model.py:291)")
             T = int(net.signal_output_dim)
             tab = self.tables_for(T, rays_o.device)
             geom = ops.make_geom(self.render_cfg(), bs, T)
-            params = [m.params for m in plan_modules(plan)]
+            params = [m.params for m in plan_modules(plan)] + list(plan.get("extra_tensors", []))
             dtx = direction_tx if plan["needs_dir_tx"] else None
+            if plan.get("extras") and self.dense != "tc":
+                raise NotImplementedError("channel embeddings are built on the tensor-core path only (dense='tc')")
             if self.dense == "tc":
                 return FusedRenderTC.apply(plan, geom, tab.dev, ops.collapse_tspan(self.render_cfg()), rays_o,
                                            position_tx, dtx, dirs, *params)

@@ -302,7 +302,16 @@ def run_native(args, cfg):
                 sys.stderr.write(f"DETAIL {name:22s} {t:8.3f} ms  work {work:.3e} {unit}  {rate:8.1f} {'TFLOP/s' if unit == 'flop' else 'GB/s'}\n")
         dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
         roof = dict(kernels[dominant]) if dominant else {}
-        roof.update({"kernel": dominant, "traffic": None, "peak_source": pk["src"],
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "umma_traffic.json")
+        if dominant == "umma_gemm" and args.config == "simu" and args.bs == 4 and os.path.exists(tpath):
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture of this very
+            # command (profilers are never run inside a timed bench); null for any other workload
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        roof.update({"kernel": dominant, "traffic": traffic, "traffic_unit": "DRAM bytes per launch", "traffic_source": traffic_src,
+                     "peak_source": pk["src"],
                      "note": "achieved = algorithmic flops (2MNK of the fp32-grade product) or bytes (SURVEY 8d) of the timed "
                              "launches / their CUDA-event time inside the timed region; each algorithmic product costs 3 "
                              "(backward) or 6 (forward) bf16 tcgen05 products, see tensor_pipe_*"})

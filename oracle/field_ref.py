@@ -5,7 +5,8 @@ boundary: tcnn is not vendored/pinned/installed (``/root/reference/requirements.
 what follows is the published HashGrid / bias-free-MLP algorithm as recorded in
 SURVEY.md Appendix B, driven exactly the way ``/root/reference/model.py`` drives tcnn:
 
-* ``AVRModelRef``         <- ``model.py:63-235``  (``AVRModel``; MeshRIR / Simu / Real_env)
+* ``AVRModelRef``         <- ``model.py:63-235``  (``AVRModel``; MeshRIR / Simu / Real_env), with the
+  channel-embedding variants ``LayeredInjectionRef`` <- ``model.py:11-61`` ('add') and the 'concat' inputs
 * ``AVRModelComplexRef``  <- ``model.py:238-331`` (``AVRModel_complex``; RAF)
 
 Parameters live in one flat fp32 ``params`` tensor per encoding / network, named like the
@@ -158,37 +159,103 @@ class MLPRef(nn.Module):
         return x[:, : self.n_out]
 
 
-def _channel_embed_mode(cfg: dict):
+class LayeredInjectionRef(nn.Module):
+    """``/root/reference/model.py:11-61`` (``LayeredTCNNWithInjection``): one single-matrix tcnn network per
+    hidden layer (``n_hidden_layers: 0``, no activation), a ``[ch_num, n_neurons]`` embedding per hidden layer
+    added to the pre-activation when ``ch_id`` is given, the configured activation, then a linear output layer."""
+
+    def __init__(self, n_in: int, n_neurons: int, n_hidden_layers: int, n_out: int, ch_num: int,
+                 activation: str = "ReLU", otype: str = "FullyFusedMLP", seed: int = 1337):
+        super().__init__()
+        if activation != "ReLU":
+            raise NotImplementedError("only ReLU")
+        one = {"otype": otype, "activation": "None", "output_activation": "None", "n_neurons": n_neurons,
+               "n_hidden_layers": 0}                                                  # model.py:24-30
+        self.hidden_layers = nn.ModuleList()
+        self.layer_embeddings = nn.ParameterList()
+        g = torch.Generator().manual_seed(seed + 100)
+        in_dim = n_in
+        for i in range(n_hidden_layers):
+            self.hidden_layers.append(MLPRef(in_dim, n_neurons, one, seed + 10 * (i + 1)))
+            self.layer_embeddings.append(nn.Parameter(torch.randn(ch_num, n_neurons, generator=g) / math.sqrt(n_neurons)))  # :34-37
+            in_dim = n_neurons
+        self.output_layer = MLPRef(in_dim, n_out, one, seed + 10 * (n_hidden_layers + 1))              # :43-53
+
+    def forward(self, x, ch_id=None):
+        for idx, layer in enumerate(self.hidden_layers):                          # :55-61
+            h = layer(x)
+            if ch_id is not None:
+                h = h + self.layer_embeddings[idx][ch_id]
+            x = F.relu(h)
+        return self.output_layer(x)
+
+
+def _channel_embed_flags(cfg: dict):
+    """``model.py:71-90``: which of the three networks inject ('add') or concatenate ('concat') an embedding."""
     ch = cfg.get("channel_embed") or {}
-    if ch.get("is_embed", False) and ch.get("connection_type", None) in ("add", "concat"):
-        raise NotImplementedError("channel_embed add/concat is outside the five BASELINE configs")
+    is_embed = ch.get("is_embed", False)
+    conn = ch.get("connection_type", None)
+    flags = {k: bool(ch.get(f"is_{n}", False)) for k, n in
+             (("enc", "sigma_encoder"), ("dec", "sigma_decoder"), ("sig", "signal_network"))}
+    mode = {k: ("injection" if is_embed and conn == "add" and f else "concat" if is_embed and conn == "concat" and f else "none")
+            for k, f in flags.items()}
+    dims = {"enc": ch.get("emb_dim_sigma_encoder", 0), "dec": ch.get("emb_dim_sigma_decoder", 0),
+            "sig": ch.get("emb_dim_signal_network", 0)}
+    return mode, dims, int(ch.get("ch_num", 0))
 
 
 class AVRModelRef(nn.Module):
-    """``/root/reference/model.py:63-235``."""
+    """``/root/reference/model.py:63-235``, including the channel-embedding variants (:71-181, :193-228)."""
 
     def __init__(self, cfg: dict, seed: int = 1337):
         super().__init__()
-        _channel_embed_mode(cfg)
         self._pos_encoding = HashGridRef(cfg["pos_encoding_sigma"], seed)
         self._dir_encoding = HashGridRef(cfg["dir_encoding_sig"], seed + 1)
         self._tx_encoding = HashGridRef(cfg["tx_encoding_sig"], seed + 2)
         self.signal_output_dim = int(cfg["signal_output_dim"])
-        self._model_encoder_sigma = MLPRef(self._pos_encoding.n_output_dims, 128, cfg["sigma_encoder_network"], seed + 3)
-        self._model_decoder_sigma = MLPRef(128, 1, cfg["sigma_decoder_network"], seed + 4)
-        sig_in = 128 + self._dir_encoding.n_output_dims + self._tx_encoding.n_output_dims
-        self._model_signal = MLPRef(sig_in, self.signal_output_dim, cfg["signal_network"], seed + 5)
+        self.mode, dims, self.ch_num = _channel_embed_flags(cfg)
+        g = torch.Generator().manual_seed(seed + 50)
+        base_in = {"enc": self._pos_encoding.n_output_dims, "dec": 128,
+                   "sig": 128 + self._dir_encoding.n_output_dims + self._tx_encoding.n_output_dims}
+        n_out = {"enc": 128, "dec": 1, "sig": self.signal_output_dim}
+        names = {"enc": ("_model_encoder_sigma", "encoder_channel_embedding", "sigma_encoder_network", "FullyFusedMLP"),
+                 "dec": ("_model_decoder_sigma", "decoder_channel_embedding", "sigma_decoder_network", "FullyFusedMLP"),
+                 "sig": ("_model_signal", "signal_channel_embedding", "signal_network", "CutlassMLP")}
+        for k, s in (("enc", 3), ("dec", 4), ("sig", 5)):
+            attr, emb_attr, cfg_key, default_otype = names[k]
+            ncfg = cfg[cfg_key]
+            if self.mode[k] == "injection":                                          # :93-104,124-135,156-167
+                net = LayeredInjectionRef(base_in[k], ncfg["n_neurons"], ncfg["n_hidden_layers"], n_out[k], self.ch_num,
+                                          ncfg.get("activation", "ReLU"), ncfg.get("otype", default_otype), seed + s)
+            else:
+                n_in = base_in[k]
+                if self.mode[k] == "concat":                                         # :106-113,137-142,169-174
+                    setattr(self, emb_attr, nn.Parameter(torch.randn(self.ch_num, dims[k], generator=g) / math.sqrt(dims[k])))
+                    n_in += dims[k]
+                net = MLPRef(n_in, n_out[k], ncfg, seed + s)
+            setattr(self, attr, net)
         self.leaky_slope = 0.01          # model.py:233 uses F.leaky_relu's default, not cfg.leaky_relu
+
+    def _run(self, k, attr, emb_attr, x, ch):
+        net = getattr(self, attr)
+        if self.mode[k] == "injection":
+            return net(x, ch)
+        if self.mode[k] == "concat" and ch is not None:
+            x = torch.cat([x, getattr(self, emb_attr)[ch]], dim=-1)
+        return net(x)
 
     def forward(self, pts, view, tx, ch_idx=None):
         bs, n_pts = pts.size(0), pts.size(1)
         pts = (pts.reshape(-1, 3) + 1) / 2               # model.py:187-189
         view = (view.reshape(-1, 3) + 1) / 2
         tx = (tx.reshape(-1, 3) + 1) / 2
-        sigma_feat = self._model_encoder_sigma(self._pos_encoding(pts))            # :191,206
-        attn = self._model_decoder_sigma(F.relu(sigma_feat))                        # :209-216
+        ch = None
+        if ch_idx is not None:
+            ch = ch_idx.unsqueeze(1).expand(-1, n_pts).reshape(-1)                  # :193-195
+        sigma_feat = self._run("enc", "_model_encoder_sigma", "encoder_channel_embedding", self._pos_encoding(pts), ch)   # :191-206
+        attn = self._run("dec", "_model_decoder_sigma", "decoder_channel_embedding", F.relu(sigma_feat), ch)              # :209-216
         sig_in = torch.cat([sigma_feat, self._dir_encoding(view), self._tx_encoding(tx)], dim=-1)   # :219-221
-        signal = self._model_signal(sig_in)                                         # :231
+        signal = self._run("sig", "_model_signal", "signal_channel_embedding", sig_in, ch)          # :223-231
         attn = torch.abs(F.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)   # :233
         return attn, signal.view(bs, n_pts, self.signal_output_dim)
 

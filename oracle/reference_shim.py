@@ -26,3 +26,43 @@ def load_reference_renderer():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_model():
+    """-> the reference ``model`` module (``AVRModel``, ``AVRModel_complex``, ``LayeredTCNNWithInjection``) executed
+    from where it lies, with a stand-in ``tinycudann`` whose ``Encoding`` / ``Network`` are the oracle's
+    ``HashGridRef`` / ``MLPRef`` (tiny-cuda-nn itself is absent: ``requirements.txt:11``).  What this pins
+    is how ``model.py`` DRIVES tcnn -- concatenation order, which activations, the channel-embedding variants --
+    not tcnn's arithmetic."""
+    import sys
+    import types
+
+    from . import field_ref
+
+    if not os.path.isfile(os.path.join(REFERENCE_ROOT, "model.py")):
+        raise FileNotFoundError(f"no reference tree at {REFERENCE_ROOT}")
+    counter = [0]
+
+    def encoding(n_input_dims, encoding_config, dtype=None, seed=None):
+        assert n_input_dims == 3
+        counter[0] += 1
+        return field_ref.HashGridRef(encoding_config, seed=1000 + counter[0])
+
+    def network(n_input_dims, n_output_dims, network_config, seed=None):
+        counter[0] += 1
+        return field_ref.MLPRef(n_input_dims, n_output_dims, network_config, seed=1000 + counter[0])
+
+    fake = types.ModuleType("tinycudann")
+    fake.Encoding, fake.Network = encoding, network
+    saved = sys.modules.get("tinycudann")
+    sys.modules["tinycudann"] = fake
+    try:
+        spec = importlib.util.spec_from_file_location("avr_reference_model", os.path.join(REFERENCE_ROOT, "model.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            del sys.modules["tinycudann"]
+        else:
+            sys.modules["tinycudann"] = saved
+    return mod

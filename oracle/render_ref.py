@@ -163,10 +163,11 @@ class RenderRef(nn.Module):
             n_pts = dirs.size(0) * d.numel()
             dir_tx = direction_tx[:, None, :].expand(bs, n_pts, 3)
         pts_n, view, tx_n, _ = sample_geometry(rays_o, position_tx, dirs, d, cfg)
+        kw = {"ch_idx": ch_idx} if ch_idx is not None else {}           # renderer.py:68-73 (the GPU twin passes it on)
         if direction_tx is not None:
-            attn, signal = self.network_fn(pts_n, view, tx_n, dir_tx)
+            attn, signal = self.network_fn(pts_n, view, tx_n, dir_tx, **kw)
         else:
-            attn, signal = self.network_fn(pts_n, view, tx_n)
+            attn, signal = self.network_fn(pts_n, view, tx_n, **kw)
         S = cfg["n_samples"]
         attn = attn.view(bs, -1, S)
         signal = signal.view(bs, -1, S, signal.size(-1))

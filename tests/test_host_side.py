@@ -116,6 +116,35 @@ def test_state_dict_interchange_with_oracle():
             assert ka == kb and torch.equal(va, vb)
 
 
+@pytest.mark.parametrize("conn", ["add", "concat"])
+def test_channel_embedding_parameters_and_plan(conn):
+    """model.py:71-181: parameter names/shapes of the 'add' / 'concat' variants, and what the fused step is handed."""
+    from avr_b200.configs import tiny_config
+    cfg = tiny_config("AVRModel")
+    cfg["model"]["channel_embed"] = {"is_embed": True, "ch_num": 8, "connection_type": conn, "is_sigma_encoder": True,
+                                     "is_sigma_decoder": False, "is_signal_network": True, "emb_dim_sigma_encoder": 8,
+                                     "emb_dim_signal_network": 24}
+    a, b = avr_b200.AVRModel(cfg["model"]), field_ref.AVRModelRef(cfg["model"])
+    assert [(k, tuple(v.shape)) for k, v in a.state_dict().items()] == [(k, tuple(v.shape)) for k, v in b.state_dict().items()]
+    a.load_state_dict(b.state_dict())
+    assert (a.encoder_mode, a.decoder_mode, a.signal_mode) == (("injection", "none", "injection") if conn == "add"
+                                                              else ("concat", "none", "concat"))
+    ch = torch.tensor([3, 3, 0])
+    plan = a.fused_plan(ch)
+    if conn == "add":
+        n_enc, n_sig = cfg["model"]["sigma_encoder_network"]["n_hidden_layers"], cfg["model"]["signal_network"]["n_hidden_layers"]
+        assert plan["extras"] == [("bias", "enc", i) for i in range(n_enc)] + [("bias", "sig", i) for i in range(n_sig)]
+        assert torch.equal(plan["extra_tensors"][0], a._model_encoder_sigma.layer_embeddings[0][ch])
+        assert a._model_encoder_sigma.params.numel() == sum(o * i for o, i in a._model_encoder_sigma.shapes)
+        assert a.fused_plan(None)["extras"] == []                        # no ch_idx: nothing is injected (model.py:58)
+    else:
+        assert plan["extras"] == [("rows", "encoder_channel_embedding"), ("rows", "signal_channel_embedding")]
+        assert [k for _, k in plan["x0"]] == ["point", "receiver_rows"] and plan["tail"][-1][1] == "receiver_rows"
+        assert a._model_encoder_sigma.n_input_dims == a._pos_encoding.n_output_dims + 8
+        with pytest.raises(ValueError):
+            a.fused_plan(None)
+
+
 def test_grad_arena_views_and_rebind():
     p1, p2 = torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(3, 3))
     arena = avr_b200.GradArena([p1, p2])

@@ -46,3 +46,54 @@ def test_direction_table_bit_exact():
         torch.manual_seed(n_azi)
         render_ref.direction_table(n_azi, n_ele)
         assert torch.equal(a, torch.rand(1))
+
+
+def _embed(conn, enc, dec, sig):
+    return {"is_embed": True, "ch_num": 8, "connection_type": conn, "is_sigma_encoder": enc, "is_sigma_decoder": dec,
+            "is_signal_network": sig, "emb_dim_sigma_encoder": 8, "emb_dim_sigma_decoder": 16, "emb_dim_signal_network": 24}
+
+
+@pytest.mark.parametrize("embed", [None, _embed("add", True, False, True), _embed("add", True, True, True),
+                                   _embed("concat", True, True, True), _embed("concat", False, True, False),
+                                   {"is_embed": True, "ch_num": 8}])          # avr_real_exp_ch_emb_1.yml: no connection_type
+def test_field_restatement_matches_reference_model_py(embed):
+    """``oracle/field_ref.py`` composes the tcnn pieces exactly like the reference's own ``model.py`` does (executed
+    unmodified, with the oracle's HashGridRef / MLPRef standing in for the absent tiny-cuda-nn): same parameter names
+    and shapes, bit-identical outputs and gradients -- channel-embedding variants (model.py:11-61,71-228) included."""
+    from oracle.reference_shim import load_reference_model
+    ref_model = load_reference_model()
+    cfg = tiny_config("AVRModel")
+    if embed is not None:
+        cfg["model"]["channel_embed"] = embed
+    theirs = ref_model.AVRModel(cfg["model"])
+    ours = field_ref.AVRModelRef(cfg["model"], seed=5)
+    assert {k: tuple(v.shape) for k, v in theirs.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    field_ref.trained_like_(ours, seed=6)
+    theirs.load_state_dict(ours.state_dict())
+    g = torch.Generator().manual_seed(1)
+    pts, view, tx = (torch.rand(3, 30, 3, generator=g) * 2 - 1 for _ in range(3))
+    ch = torch.tensor([2, 7, 2])
+    a0, s0 = theirs(pts, view, tx, ch_idx=ch)
+    a1, s1 = ours(pts, view, tx, ch_idx=ch)
+    assert a0.shape == (3, 30, 1) and torch.equal(a0, a1) and torch.equal(s0, s1) and float(s0.abs().max()) > 0
+    G = torch.randn(s0.shape, generator=g)
+    (a0.sum() + (s0 * G).sum()).backward()
+    (a1.sum() + (s1 * G).sum()).backward()
+    mine = dict(ours.named_parameters())
+    for name, p in theirs.named_parameters():
+        assert torch.equal(p.grad, mine[name].grad), name
+
+
+def test_complex_field_restatement_matches_reference_model_py():
+    from oracle.reference_shim import load_reference_model
+    ref_model = load_reference_model()
+    cfg = tiny_config("AVRModel_complex")
+    theirs = ref_model.AVRModel_complex(cfg["model"])
+    ours = field_ref.trained_like_(field_ref.AVRModelComplexRef(cfg["model"], seed=5), seed=6)
+    assert {k: tuple(v.shape) for k, v in theirs.state_dict().items()} == {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    theirs.load_state_dict(ours.state_dict())
+    g = torch.Generator().manual_seed(2)
+    pts, view, tx, tv = (torch.rand(2, 25, 3, generator=g) * 2 - 1 for _ in range(4))
+    a0, s0 = theirs(pts, view, tx, tv)
+    a1, s1 = ours(pts, view, tx, tv)
+    assert torch.equal(a0, a1) and torch.equal(s0, s1) and float(s0.abs().max()) > 0
