@@ -78,6 +78,14 @@ SIGNATURES = {
     "avr_composite_bwd": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_spectrum_fwd": (C.c_int, [_G, _P, _P, _P, _P, _I64, _P, _P, _P, C.c_int, _P]),
     "avr_spectrum_bwd": (C.c_int, [_G, _P, _P, _P, _P, _I64, _P, _P, C.c_int, _P]),
+    "avr_crit_irfft": (C.c_int, [_P, _I32, _I32, _P, _I64, _P, C.c_int, _P]),
+    "avr_crit_irfft_adjoint": (C.c_int, [_P, _I32, _I32, _P, _I64, _P, C.c_int, _P]),
+    "avr_crit_freq_terms": (C.c_int, [_P, _P, _I32, _I32, _F, _F, _F, _P, _P, C.c_int, _P]),
+    "avr_crit_time_l1": (C.c_int, [_P, _P, _I32, _I32, _F, _P, _P, C.c_int, _P]),
+    "avr_crit_energy_workspace_bytes": (_I64, [_I32, _I32, _I32]),
+    "avr_crit_energy": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _I64, C.c_int, _P]),
+    "avr_crit_stft_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P, C.c_int, _P]),
+    "avr_crit_stft_bwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _F, _F, _F, _P, _P, C.c_int, _P]),
     "avr_adam_workspace_bytes": (_I64, []),
     "avr_fused_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _I64, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "avr_spectrum_gain": (C.c_int, [_G, _P, _P, _P, _I64, _I64, _I32, C.c_int, _P]),

@@ -269,6 +269,40 @@ AVR_API int avr_spectrum_phase_sum(const avr_render_geom* geom, const float* x, 
 AVR_API int avr_spectrum_phase_bwd(const avr_render_geom* geom, const float* d_out, const float* phase, void* dx, int64_t ldx,
                                    int64_t dx_plane, int32_t dx_nplanes, int device, void* stream);
 
+/* ---- training loss on rendered spectra (utils/criterion.py:69-100) ---------------------------
+ * Spectra are interleaved (re, im) fp32 rows of F = T/2+1 bins; time signals are fp32 rows of T samples.  Every term
+ * writes fixed-order partial sums (the caller adds them and applies weight / count) and, when the gradient pointer is
+ * non-NULL, d(scale * sum)/d(pred) in the same pass.  `dft` is the [T, ldd] (cos, -sin) table of avr_spectrum_*. */
+/* x[r,:] = irfft(spec[r,:])  (criterion.py:71-72) and its adjoint out[r,f] = d<x, d_x>/d spec[r,f] */
+AVR_API int avr_crit_irfft(const float* spec, int32_t n_rows, int32_t T, const float* dft, int64_t ldd, float* x, int device,
+                   void* stream);
+AVR_API int avr_crit_irfft_adjoint(const float* d_x, int32_t n_rows, int32_t T, const float* dft, int64_t ldd, float* out,
+                           int device, void* stream);
+/* criterion.py:86-93: partial[bs,3] = (sum |d re| + |d im|, sum ||X|-|Y||, sum |d cos| + |d sin| of the angles);
+ * grad[3,bs,F,2] (may be NULL) = scale_k * d(sum_k)/d pred */
+AVR_API int avr_crit_freq_terms(const float* pred, const float* ori, int32_t bs, int32_t F, float scale_spec, float scale_amp,
+                        float scale_angle, float* partial, float* grad, int device, void* stream);
+/* criterion.py:95: partial[bs] = sum_t |ori - pred|; d_x[bs,T] (may be NULL) = scale * d(sum)/d x_pred */
+AVR_API int avr_crit_time_l1(const float* x_pred, const float* x_ori, int32_t bs, int32_t T, float scale, float* partial,
+                     float* d_x, int device, void* stream);
+/* criterion.py:74-84,97: energy-decay curves of the rectangular-window STFT (n_fft, hop; center, reflect padding);
+ * partial[bs] = sum_m |E_ori - E_pred|; d_x[bs,T] (may be NULL) = scale * d(sum)/d x_pred */
+AVR_API int64_t avr_crit_energy_workspace_bytes(int32_t bs, int32_t T, int32_t hop);
+AVR_API int avr_crit_energy(const float* x_pred, const float* x_ori, int32_t bs, int32_t T, int32_t n_fft, int32_t hop,
+                    float scale, float* partial, float* d_x, float* workspace, int64_t workspace_bytes, int device,
+                    void* stream);
+/* One resolution of the multi-resolution STFT term (criterion.py:33,99; auraloss STFTLoss): window[win] centred in
+ * n_fft (a power of two), M = 1 + T/hop frames, K = n_fft/2+1 bins, magnitudes sqrt(max(re^2+im^2, eps)).
+ * fwd: S_pred[bs,M,K,2], mag_ori[bs,M,K], partial[bs*M,4] = sums of (P-O)^2, P^2, |log O - log P|, |O - P|.
+ * bwd: with sums[4] (device) = the column sums of `partial`, adds to d_x[bs,T] the gradient of
+ *      scale * (sqrt(A)/sqrt(B) + C/n + w_lin * D/n), n = bs*M*K; frames[bs,M,win] is scratch. */
+AVR_API int avr_crit_stft_fwd(const float* x_pred, const float* x_ori, int32_t bs, int32_t T, int32_t n_fft, int32_t hop,
+                      int32_t win, const float* window, float eps, float* S_pred, float* mag_ori, float* partial,
+                      int device, void* stream);
+AVR_API int avr_crit_stft_bwd(const float* S_pred, const float* mag_ori, const float* sums, int32_t bs, int32_t T, int32_t n_fft,
+                      int32_t hop, int32_t win, const float* window, float eps, float scale, float w_lin, float* frames,
+                      float* d_x, int device, void* stream);
+
 /* ---- fused optimiser step over flat fp32 arenas (avr_runner.py:192-200: clip_grad_norm_ -> NaN/Inf scrub -> Adam) ----
  * norm_out[0] = total gradient L2 norm (before clipping), norm_out[1] = clip coefficient.  max_norm <= 0: no
  * clipping.  step is the 1-based Adam step.  write_back_grad != 0 stores the clipped / scrubbed gradient. */

@@ -18,8 +18,12 @@ field_ref.py      fp32 torch restatement of the tiny-cuda-nn pieces the referenc
                   (``/root/reference/requirements.txt:11``) that is neither installed nor
                   installable here, and the reference holds no tests or golden vectors for
                   it; the restatement follows the published algorithm.
-reference_shim.py imports ``/root/reference/renderer_cpu.py`` unmodified (this container
-                  only; the GPU box has no ``/root/reference``).
+criterion_ref.py  fp32 torch restatement of the training loss (``utils/criterion.py:7-126``) and of
+                  the ``auraloss`` multi-resolution STFT loss it calls (absent, unpinned: that term is
+                  PARITY UNPINNED; everything else is PINNED against the unmodified reference module).
+reference_shim.py imports ``/root/reference/renderer_cpu.py``, ``model.py`` (with the oracle's HashGrid /
+                  MLP standing in for ``tinycudann``) and ``utils/criterion.py`` (stand-in ``auraloss``)
+                  unmodified (this container only; the GPU box has no ``/root/reference``).
 make_golden.py    regenerates ``tests/golden/*.npz`` from the unmodified reference renderer
                   driven by ``field_ref`` networks.
 """

@@ -127,8 +127,48 @@ def run_reference(name):
     return {k: v.numpy() for k, v in blob.items()}
 
 
+CRITERION_CASES = {
+    # name: (bs, T, train config).  Weights: avr_meshrir.yml:35-40 / avr_pra_1.yml:36-41; DAS terms: 8 microphones.
+    "criterion_meshrir_w": (4, 1600, {"spec_loss_weight": 1, "amplitude_loss_weight": 0.5, "angle_loss_weight": 0.5,
+                                      "time_loss_weight": 100, "energy_loss_weight": 5, "multistft_loss_weight": 1}),
+    "criterion_small": (3, 400, {"spec_loss_weight": 2, "amplitude_loss_weight": 4, "angle_loss_weight": 1,
+                                 "time_loss_weight": 50, "energy_loss_weight": 1, "multistft_loss_weight": 1}),
+    "criterion_das": (8, 1600, {"spec_loss_weight": 1, "amplitude_loss_weight": 0.5, "angle_loss_weight": 0.5,
+                                "time_loss_weight": 100, "energy_loss_weight": 5, "multistft_loss_weight": 1,
+                                "das_reg_loss_weight": 0.3, "das_ce_loss_weight": 0.2, "beta": 100.0}),
+}
+CRITERION_RENDER = {"fs": 16000, "speed": 343.8}
+
+
+def run_reference_criterion(name):
+    """The unmodified ``utils/criterion.py`` (stand-in auraloss = oracle restatement, see reference_shim) on seeded
+    spectra shaped like rendered IRs: a decaying random time signal -> rfft."""
+    from oracle.reference_shim import load_reference_criterion
+    bs, T, cfg = CRITERION_CASES[name]
+    crit = load_reference_criterion().Criterion(cfg, CRITERION_RENDER)
+    g = torch.Generator().manual_seed(len(name) + bs)
+    env = torch.exp(-torch.arange(T) / (0.15 * T))
+    ori = torch.fft.rfft(torch.randn(bs, T, generator=g) * env)
+    pred = torch.fft.rfft((torch.randn(bs, T, generator=g) * 0.7 + 0.3 * torch.fft.irfft(ori)) * env)
+    pred = pred.to(torch.complex64).requires_grad_()
+    ori = ori.to(torch.complex64)
+    outs = crit(pred, ori)
+    coef = torch.tensor([1.0, 0.9, 1.1, 0.8, 1.2, 0.7, 1.3, 0.6])              # distinct cotangents per loss term
+    (torch.stack([o.float() for o in outs[:8]]) * coef).sum().backward()
+    blob = {"pred": torch.view_as_real(pred.detach()), "ori": torch.view_as_real(ori), "coef": coef,
+            "losses": torch.stack([o.detach().float() for o in outs[:8]]),
+            "ori_time": outs[8].detach(), "pred_time": outs[9].detach(),
+            "grad_pred": torch.view_as_real(pred.grad)}
+    return {k: v.numpy() for k, v in blob.items()}
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name in CRITERION_CASES:
+        blob = run_reference_criterion(name)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, losses={np.round(blob['losses'], 4)}")
     for name in CASES:
         blob = run_reference(name)
         path = os.path.join(GOLDEN_DIR, name + ".npz")

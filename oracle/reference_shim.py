@@ -66,3 +66,33 @@ def load_reference_model():
         else:
             sys.modules["tinycudann"] = saved
     return mod
+
+
+def load_reference_criterion():
+    """-> the reference ``utils/criterion.py`` module executed from where it lies, with a stand-in ``auraloss`` whose
+    ``freq.MultiResolutionSTFTLoss`` is the oracle's restatement (auraloss is absent and unpinned).  Pins everything
+    ``Criterion.forward`` does itself; the multi-resolution STFT term stays parity-unpinned."""
+    import sys
+    import types
+
+    from . import criterion_ref
+
+    path = os.path.join(REFERENCE_ROOT, "utils", "criterion.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"no reference tree at {REFERENCE_ROOT}")
+    fake = types.ModuleType("auraloss")
+    fake.freq = types.ModuleType("auraloss.freq")
+    fake.freq.MultiResolutionSTFTLoss = criterion_ref.MultiResolutionSTFTLossRef
+    saved = {k: sys.modules.get(k) for k in ("auraloss", "auraloss.freq")}
+    sys.modules["auraloss"], sys.modules["auraloss.freq"] = fake, fake.freq
+    try:
+        spec = importlib.util.spec_from_file_location("avr_reference_criterion", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod

@@ -97,3 +97,32 @@ def test_complex_field_restatement_matches_reference_model_py():
     a0, s0 = theirs(pts, view, tx, tv)
     a1, s1 = ours(pts, view, tx, tv)
     assert torch.equal(a0, a1) and torch.equal(s0, s1) and float(s0.abs().max()) > 0
+
+
+TRAIN_CFG = {"spec_loss_weight": 1, "amplitude_loss_weight": 0.5, "angle_loss_weight": 0.5, "time_loss_weight": 100,
+             "energy_loss_weight": 5, "multistft_loss_weight": 1}                    # avr_meshrir.yml:35-40
+
+
+@pytest.mark.parametrize("bs,T,das", [(4, 1600, False), (3, 400, False), (8, 1600, True)])
+def test_criterion_restatement_matches_reference(bs, T, das):
+    """oracle/criterion_ref.py vs the unmodified utils/criterion.py (stand-in auraloss): every output, and d/d pred."""
+    from oracle import criterion_ref
+    from oracle.reference_shim import load_reference_criterion
+    cfg = dict(TRAIN_CFG)
+    if das:
+        cfg.update(das_reg_loss_weight=0.3, das_ce_loss_weight=0.2, beta=100.0)
+    render = {"fs": 16000, "speed": 343.8}
+    theirs = load_reference_criterion().Criterion(cfg, render)
+    ours = criterion_ref.CriterionRef(cfg, render)
+    g = torch.Generator().manual_seed(bs)
+    F_ = T // 2 + 1
+    pred = torch.complex(torch.randn(bs, F_, generator=g), torch.randn(bs, F_, generator=g)).requires_grad_()
+    pred2 = pred.detach().clone().requires_grad_()
+    ori = torch.complex(torch.randn(bs, F_, generator=g), torch.randn(bs, F_, generator=g))
+    a, b = theirs(pred, ori), ours(pred2, ori)
+    assert len(a) == len(b) == 10
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+    sum(a[:8]).backward()
+    sum(b[:8]).backward()
+    assert torch.allclose(pred.grad, pred2.grad, rtol=1e-5, atol=1e-8)
