@@ -8,6 +8,7 @@ Public surface (mirrors the reference's ``renderer.py`` / ``model.py``):
 * ``GradArena``                                   <- the DDP gradient all-reduce of avr_runner_ddp.py:98,257
 * ``FusedAdam``                                   <- clip / NaN scrub / Adam of avr_runner.py:192-200
 * ``Criterion(cfg_train, cfg_render)``            <- utils/criterion.py:7 (the training loss on rendered spectra)
+* ``save_checkpoint`` / ``load_checkpoint``       <- avr_runner.py:104-154 (same file format, both directions)
 
 The compute path is hand-written CUDA behind the C-ABI of ``include/avr_b200.h``
 (``avr_b200/libavr_b200.so``); there is no CPU or PyTorch fallback.
@@ -19,3 +20,4 @@ from .renderer import AVRRender                                       # noqa: E4
 from .ddp import GradArena                                            # noqa: E402,F401
 from .optim import FusedAdam                                          # noqa: E402,F401
 from .criterion import Criterion                                      # noqa: E402,F401
+from .checkpoint import load_checkpoint, save_checkpoint, latest_checkpoint   # noqa: E402,F401

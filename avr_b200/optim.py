@@ -15,16 +15,23 @@ from . import _lib
 from .ddp import GradArena
 
 
-class FusedAdam:
-    """``torch.optim.Adam`` semantics (lr, betas, eps, weight_decay as L2) + the reference's clipping and scrubbing."""
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` semantics (lr, betas, eps, weight_decay as L2) + the reference's clipping and scrubbing.
+
+    A ``torch.optim.Optimizer``: ``param_groups[0]["lr"]`` is what ``step`` uses, so ``CosineAnnealingLR``
+    (avr_runner.py:71,200) drives it unchanged, and ``state_dict`` / ``load_state_dict`` speak ``torch.optim.Adam``'s
+    format, so the ``optimizer_state_dict`` of a reference checkpoint (avr_runner.py:122,150) loads and saves.
+    """
 
     def __init__(self, parameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0,
                  arena: GradArena | None = None):
         params = [p for p in parameters if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False,
+                                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None))
         self.arena = arena if arena is not None else GradArena(params)
         if [id(p) for p in self.arena.params] != [id(p) for p in params]:
             raise ValueError("arena and optimiser must cover the same parameters in the same order")
-        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.max_norm = max_norm
         self.step_count = 0
         flat = self.arena.flat
         if not flat.is_cuda:
@@ -39,13 +46,58 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros_like(flat)
         self.norm = torch.zeros(2, device=flat.device)
         self._ws = torch.empty(int(_lib.load().avr_adam_workspace_bytes()) // 4 + 4, device=flat.device)
+        self._bind_state()
 
-    def zero_grad(self):
+    # hyper-parameters live in the (single) param group, like torch.optim.Adam
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    betas = property(lambda self: self.param_groups[0]["betas"])
+    eps = property(lambda self: self.param_groups[0]["eps"])
+    weight_decay = property(lambda self: self.param_groups[0]["weight_decay"])
+
+    def _bind_state(self):
+        """Per-parameter ``state`` entries are views of the flat moment buffers (torch.optim.Adam's keys)."""
+        for p, off in zip(self.arena.params, self.arena.offsets):
+            n = p.numel()
+            self.state[p] = {"step": torch.tensor(float(self.step_count)),
+                             "exp_avg": self.exp_avg[off:off + n].view_as(p),
+                             "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p)}
+
+    def state_dict(self):
+        for p in self.arena.params:
+            self.state[p]["step"] = torch.tensor(float(self.step_count))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Accepts a ``torch.optim.Adam`` state dict over the same parameters (e.g. from a reference checkpoint)."""
+        if len(state_dict["param_groups"]) != 1:
+            raise ValueError("FusedAdam keeps one parameter group")
+        super().load_state_dict(state_dict)
+        steps = set()
+        with torch.no_grad():
+            for p, off in zip(self.arena.params, self.arena.offsets):
+                st = self.state.get(p, {})
+                n = p.numel()
+                if "exp_avg" in st:
+                    self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(st["step"]))
+                else:                                                     # Adam creates state lazily: never stepped
+                    self.exp_avg[off:off + n].zero_()
+                    self.exp_avg_sq[off:off + n].zero_()
+                    steps.add(0)
+        if len(steps) > 1:
+            raise ValueError("parameters with different step counts cannot share the fused update")
+        self.step_count = steps.pop() if steps else 0
+        self._bind_state()
+
+    def zero_grad(self, set_to_none: bool = False):
         self.arena.zero_()
 
     @torch.no_grad()
-    def step(self, lr=None, write_back_grad=False):
-        """Apply one update; ``lr`` overrides the stored rate (cosine schedule is host-side, avr_runner.py:71,200)."""
+    def step(self, closure=None, lr=None, write_back_grad=False):
+        """Apply one update; ``lr`` overrides ``param_groups[0]["lr"]`` for this step."""
+        if closure is not None:
+            raise NotImplementedError("closures are not supported")
         self.step_count += 1
         flat = self.arena.flat
         dev = flat.device.index if flat.device.index is not None else torch.cuda.current_device()

@@ -73,3 +73,66 @@ def test_fused_adam_trains_the_renderer(built_library):
         losses.append(float(loss))
     assert losses[-1] < 0.9 * losses[0]
     assert set(ren.state_dict()) == {"network_fn." + k for k in net.state_dict()}
+
+
+def test_reference_format_checkpoint_round_trip(built_library, tmp_path):
+    """avr_runner.py:104-154: a checkpoint written the reference's way (stock ``torch.optim.Adam`` + cosine schedule over
+    the oracle field, reference key names) resumes under ``AVRRender`` + ``FusedAdam`` and follows the same trajectory;
+    the file written back loads into stock ``torch.optim.Adam`` again."""
+    from avr_b200.configs import tiny_config
+    from oracle import field_ref, render_ref
+    cfg = tiny_config("AVRModel")
+    gen = torch.Generator().manual_seed(4)
+    rx, tx = torch.randn(2, 3, generator=gen), torch.randn(2, 3, generator=gen)
+    azi = torch.rand(cfg["render"]["n_azi"], generator=gen)
+    target = torch.randn(2, 101, 2, generator=gen) * 1e-3
+
+    def make_opt(params):
+        opt = torch.optim.Adam(params, lr=2e-3, weight_decay=1e-4, betas=(0.9, 0.999))
+        return opt, torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=20.0, eta_min=1e-5)
+
+    # the "reference" run on the CPU: oracle field inside the oracle renderer, stock optimiser, 3 steps, save
+    ref_ren = render_ref.RenderRef(field_ref.trained_like_(field_ref.AVRModelRef(cfg["model"], seed=2), seed=3), **cfg["render"])
+    ref_opt, ref_sched = make_opt(ref_ren.parameters())
+
+    def ref_step():
+        ref_opt.zero_grad()
+        (ref_ren(rx, tx, None, azi_rand=azi) - target).square().sum().backward()
+        torch.nn.utils.clip_grad_norm_(ref_ren.parameters(), max_norm=1)
+        ref_opt.step()
+        ref_sched.step()
+
+    for _ in range(3):
+        ref_step()
+    (tmp_path / "ckpts").mkdir()
+    path = str(tmp_path / "ckpts" / "000003.tar")
+    torch.save({"current_iteration": 3, "audionerf_network_state_dict": ref_ren.state_dict(),
+                "optimizer_state_dict": ref_opt.state_dict(), "scheduler_state_dict": ref_sched.state_dict()}, path)
+    assert avr_b200.latest_checkpoint(str(tmp_path / "ckpts")) == path
+
+    # resume natively
+    net = avr_b200.AVRModel(cfg["model"]).to(DEV)
+    ren = avr_b200.AVRRender(net, **cfg["render"])
+    opt = avr_b200.FusedAdam(ren.parameters(), lr=2e-3, weight_decay=1e-4, max_norm=1.0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=20.0, eta_min=1e-5)
+    assert avr_b200.load_checkpoint(path, ren, opt, sched, map_location=DEV) == 3
+    assert opt.step_count == 3 and abs(opt.lr - ref_opt.param_groups[0]["lr"]) < 1e-12
+    for _ in range(2):
+        ref_step()
+        opt.zero_grad()
+        (ren(rx.to(DEV), tx.to(DEV), azi_rand=azi) - target.to(DEV)).square().sum().backward()
+        opt.step()
+        sched.step()
+    ref_params = dict(ref_ren.named_parameters())
+    for name, p in ren.named_parameters():
+        assert rel_l2(p, ref_params[name]) < 2e-5, name
+    # and back: the file we write is a stock-Adam checkpoint again
+    out = avr_b200.save_checkpoint(str(tmp_path / "ckpts" / "000005.tar"), ren, opt, sched, current_iteration=5)
+    ref_ren2 = render_ref.RenderRef(field_ref.AVRModelRef(cfg["model"], seed=9), **cfg["render"])
+    opt2, sched2 = make_opt(ref_ren2.parameters())
+    ck = torch.load(out, map_location="cpu", weights_only=False)
+    ref_ren2.load_state_dict(ck["audionerf_network_state_dict"])
+    opt2.load_state_dict(ck["optimizer_state_dict"])
+    sched2.load_state_dict(ck["scheduler_state_dict"])
+    assert ck["current_iteration"] == 5 and int(opt2.state[next(iter(ref_ren2.parameters()))]["step"]) == 5
+    assert abs(opt2.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-12
