@@ -44,11 +44,13 @@ struct UmmaParams {
     long long ld_bias_ray, ld_bias_rcv;
     int geo_R, geo_S;                                  // row = (b*R + r)*S + s
     float* c32; long long ldc32;                       // fp32 output / split-K partials
+    int epi_split;                                     // 1: warps 2..5 drain every chunk; 2: warps 6..9 take the odd chunks
+    uint32_t epi_warp_bytes;                           // staging bytes per epilogue warp (nc planes x 2 KB)
 };
 
 constexpr int UM = 128;            // UMMA_M
 constexpr int UBK = 64;            // k-block: 64 bf16 = one 128-byte swizzle row
-constexpr int UTHREADS = 192;
+constexpr int UTHREADS = 320;       // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane group)
 constexpr uint32_t A_PLANE_BYTES = UM * 128;          // 16 KB
 constexpr uint32_t A_TILE_BYTES = 2 * A_PLANE_BYTES;  // hi + lo
 
@@ -202,12 +204,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
     const uint32_t bres_base = smem_u32(smem);
     const uint32_t smem_base = bres_base + bres_bytes;
-    // epilogue staging: 4 warps x 3 planes x 2 KB, 1024-byte aligned, after the barrier block
+    // epilogue staging: (4 or 8) warps x nc planes x 2 KB, 1024-byte aligned, after the barrier block
     const uint32_t epi_base = (smem_base + (uint32_t)p.stages * stage_bytes + 256u + 1023u) & ~1023u;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128 * p.epi_split); }
         mbar_init(bar_bres, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -312,9 +314,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(bar_tfull + 8 * acc);                                // accumulator complete
             }
         }
-    } else {
-        // ===================================== epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+    } else if (((warp - 2) >> 2) < p.epi_split) {
+        // ===================================== epilogue: warps 2..5 (and 6..9) -> TMEM lane groups 2,3,0,1.
+        // One chunk of a tile is a latency chain (tcgen05.ld -> convert -> st.shared -> proxy fence -> bulk store ->
+        // wait for the store to have read the staging tile); with epi_split = 2 the two warps of a lane group drain
+        // alternate chunks through their own staging tiles, so two such chains are in flight per lane group.
         const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2;
         int iter = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
             const int split = tile % p.k_splits;
@@ -329,7 +335,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             //   bt*[j]  value of column 32j + lane of the warp's shared bias row           (UF_BIAS, uniform case)
             uint32_t mw[8];
             int ray_row = 0, rcv_row = 0, ray_uniform = 0, rcv_uniform = 0;
-            const uint32_t bias_s = epi_base + 4u * 3u * EPI_PLANE_BYTES + (uint32_t)lane_grp * 1024u;   // 256 floats: ray + receiver rows summed
+            const uint32_t bias_s = epi_base + 4u * (uint32_t)p.epi_split * p.epi_warp_bytes + (uint32_t)lane_grp * 1024u;   // 256 floats (UF_BIAS implies epi_split = 1)
             if (!MN_MAJOR && !(p.flags & UF_OUT_F32)) {
                 if (p.flags & UF_BIAS) {
                     const long long rrow = row_ok ? row : (long long)p.M - 1;
@@ -360,7 +366,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
             if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
                 // fp32 outputs (split-K partials, the 16-wide density head): direct stores
-                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                for (int c0 = 16 * half; c0 < p.BN; c0 += 16 * p.epi_split) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);                                   // warp-collective: outside the row guard
                     if (!row_ok) continue;
@@ -385,8 +391,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
                 // plane outputs: registers -> swizzled smem staging -> TMA bulk tensor store (full lines, rows and
                 // columns outside the output window are clipped by the tensor map)
-                const uint32_t stage = epi_base + (uint32_t)lane_grp * (3u * EPI_PLANE_BYTES);
-                for (int c0 = 0; c0 < p.BN && n0 + c0 < p.N; c0 += EPI_COLS) {
+                const uint32_t stage = epi_base + (uint32_t)(4 * half + lane_grp) * p.epi_warp_bytes;
+                for (int c0 = EPI_COLS * half; c0 < p.BN && n0 + c0 < p.N; c0 += EPI_COLS * p.epi_split) {
                     float v[32];
                     {
                         float t0[16], t1[16];
@@ -680,16 +686,28 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     if (const char* dbg = getenv("AVR_UMMA_DEBUG")) p.flags |= (atoi(dbg) & (UF_DEBUG_NOWAIT | UF_DEBUG_NOSTORE | UF_DEBUG_NOSTAGE | UF_DEBUG_NOFENCE));
     p.c32 = c_f32; p.ldc32 = ldc32;
     const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
-    const uint32_t epi_bytes = 4u * 3u * EPI_PLANE_BYTES + 4u * 1024u + 1024u;    // staging tiles + per-warp bias rows
-    const uint32_t budget = 226 * 1024 - 1024 - 256 - epi_bytes;
     p.nkb = (int)ceil_div(K, UBK);
-    p.b_resident = (p.tiles_n == 1 && p.tiles_m > 1 && (uint64_t)p.nkb * b_tile + 2ull * a_tile <= budget) ? 1 : 0;
-    const uint32_t bres_total = p.b_resident ? (uint32_t)p.nkb * b_tile : 0u;
-    const uint32_t stage_bytes = p.b_resident ? a_tile : a_tile + b_tile;
-    p.stages = (int)((budget - bres_total) / stage_bytes);
-    if (p.stages > 6) p.stages = 6;
-    if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
-    const size_t smem = (size_t)bres_total + (size_t)p.stages * stage_bytes + 1024 + 256 + epi_bytes;
+    p.epi_warp_bytes = (flags & UF_OUT_F32) ? 0u : (uint32_t)p.nc * EPI_PLANE_BYTES;
+    const uint32_t bias_bytes = (flags & UF_BIAS) ? 4u * 1024u : 0u;
+    uint32_t epi_bytes = 0, bres_total = 0, stage_bytes = 0;
+    // two epilogue warps per lane group when their staging tiles fit next to a two-stage pipeline (two-plane outputs,
+    // fp32 outputs); the per-receiver bias rows are staged per lane group, so that mode keeps one warp per group
+    for (p.epi_split = (flags & UF_BIAS) ? 1 : 2; p.epi_split >= 1; --p.epi_split) {
+        // 227 KB per CTA = alignment slack (1 KB) + operands + barrier block padded to 1 KB + staging (+ bias rows)
+        epi_bytes = 4u * (uint32_t)p.epi_split * p.epi_warp_bytes + bias_bytes;
+        const uint32_t budget = 232448u - 2048u - epi_bytes;
+        p.b_resident = (p.tiles_n == 1 && p.tiles_m > 1 && (uint64_t)p.nkb * b_tile + 2ull * a_tile <= budget) ? 1 : 0;
+        bres_total = p.b_resident ? (uint32_t)p.nkb * b_tile : 0u;
+        stage_bytes = p.b_resident ? a_tile : a_tile + b_tile;
+        p.stages = (int)((budget - bres_total) / stage_bytes);
+        if (p.stages > 6) p.stages = 6;
+        if (p.stages >= 2) break;
+    }
+    if (p.epi_split < 1 || p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
+    if (const char* e = getenv("AVR_UMMA_EPI_SPLIT")) {                   // A/B experiments: force one warp per lane group
+        if (atoi(e) == 1 && p.epi_split == 2) p.epi_split = 1;
+    }
+    const size_t smem = (size_t)bres_total + (size_t)p.stages * stage_bytes + 2048 + epi_bytes;
     CUtensorMap ta, tb, tc, tc2;
     if (int rc = make_map(&ta, a_planes, M, K, lda, a_plane, UM, p.na)) return rc;
     if (int rc = make_map(&tb, b_planes, N, K, ldb, b_plane, p.BN, p.nb)) return rc;
@@ -744,6 +762,8 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.k_splits = (int)(K > 0 ? ceil_div(K, p.k_per_split) : 1);
     p.tmem_cols = tmem_cols_for(p.BN);
     p.c32 = (float*)workspace; p.ldc32 = ldp;
+    p.epi_split = 2; p.epi_warp_bytes = 0;
+    if (const char* e = getenv("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
     const int bn_rows = (p.BN + 63) / 64 * 64;
     const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)bn_rows * 256u;
     p.stages = (int)((220 * 1024) / stage_bytes);
