@@ -57,9 +57,10 @@ SIGNATURES = {
     "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.c_int, _P, _I64,
                                    _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _I64,
-                                   C.c_int, _P]),
+                                   _P, _I64, _P, C.c_float, _P, _I64, C.c_int, _P]),
+    "avr_umma_gemm_nt_splitk_slices": (_I64, [_I64]),
     "avr_umma_gemm_tn_workspace_bytes": (_I64, [_I64, _I64, _I64]),
-    "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, C.c_int, _P, _I64,
+    "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P, _I64,
                                    C.c_int, _P]),
     "avr_delay_sort": (C.c_int, [_G, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_collapse_prefix_bytes": (_I64, [_G, _I32, _I32]),

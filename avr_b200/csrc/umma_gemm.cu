@@ -33,6 +33,7 @@ struct UmmaParams {
     int BN;                 // tile columns (multiple of 16, <= 256)
     int tiles_m, tiles_n, k_splits, k_per_split;
     int stages, tmem_cols;
+    int dual_acc;           // six-product mode: the five small products go to a second TMEM accumulator (see the MMA issuer)
     int na, nb, nc;         // planes used of A / B (2: hi,mid  3: hi,mid,lo) and written to C
     int b_resident, nkb;    // K-major, single column tile, short K: the whole B operand stays in shared memory
     int flags;
@@ -46,6 +47,12 @@ struct UmmaParams {
     float* c32; long long ldc32;                       // fp32 output / split-K partials
     int epi_split;                                     // 1: warps 2..5 drain every chunk; 2: warps 6..9 take the odd chunks
     uint32_t epi_warp_bytes;                           // staging bytes per epilogue warp (nc planes x 2 KB)
+    // near-zero guard (forward layers): elements with |out| < near_tau * (mean |out| of their row chunk) are listed
+    // and re-evaluated by umma_fixup_kernel with fp32 FMAs, so that sign decisions (ReLU, |leaky_relu|) taken on the
+    // output are as good as an fp32 GEMM's.  The tensor core truncates once per MMA: ~6e-9*K of the row scale.
+    uint2* near_list; uint32_t near_cap; uint32_t* near_count; float near_tau;
+    const __nv_bfloat16* a_raw; long long lda, a_plane;
+    const __nv_bfloat16* b_raw; long long ldb, b_plane;
 };
 
 constexpr int UM = 128;            // UMMA_M
@@ -183,6 +190,30 @@ __device__ __forceinline__ void stage_planes32(uint32_t stage, int lane, const f
     }
 }
 
+// near-zero guard of one row chunk held in registers: v[0..NV) are columns col0.. of `row`.  Cheap common path: one
+// FMNMX per element for the minimum magnitude plus a strided sample of the magnitudes for the scale.
+template <int NV>
+__device__ __forceinline__ void near_zero_guard(const UmmaParams& p, const float* v, long long row, bool row_ok, long long col0) {
+    float m = fabsf(v[0]), s = 0.f;
+#pragma unroll
+    for (int i = 1; i < NV; ++i) m = fminf(m, fabsf(v[i]));
+#pragma unroll
+    for (int i = 0; i < NV; i += NV / 8) s += fabsf(v[i]);                  // eight samples of the row chunk
+    const float thr = p.near_tau * s * 0.125f;
+    if (m < thr && row_ok) {                                                  // rare
+        uint32_t near = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) near |= (fabsf(v[i]) < thr ? 1u : 0u) << i;
+        while (near) {
+            const int i = __ffs(near) - 1;
+            near &= near - 1;
+            if (col0 + i >= p.N) break;
+            const uint32_t slot = atomicAdd(p.near_count, 1u);
+            if (slot < p.near_cap) p.near_list[slot] = make_uint2((uint32_t)row, (uint32_t)(col0 + i));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- kernel
 template <bool MN_MAJOR>
 __global__ void __launch_bounds__(UTHREADS, 1)
@@ -193,8 +224,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bn_rows = MN_MAJOR ? ((p.BN + 63) / 64) * 64 : p.BN;     // B rows (K-major) / MN extent (MN-major) in smem
     const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
-    const uint32_t a_tile_bytes = MN_MAJOR ? A_TILE_BYTES : (uint32_t)p.na * A_PLANE_BYTES;
-    const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)bn_rows * 256u : (uint32_t)p.nb * b_plane_bytes;
+    const uint32_t a_tile_bytes = (uint32_t)p.na * A_PLANE_BYTES;
+    const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)p.nb * (uint32_t)bn_rows * 128u : (uint32_t)p.nb * b_plane_bytes;
+    const uint32_t mn_blk = (uint32_t)p.na * 8192u;       // MN-major: one TMA box = 64 (mn) x 64 (k) x planes (na == nb)
     const bool bres = !MN_MAJOR && p.b_resident;
     const uint32_t bres_bytes = bres ? (uint32_t)p.nkb * b_tile_bytes : 0u;    // resident B: [k-block][plane][rows][128 B]
     const uint32_t stage_bytes = bres ? a_tile_bytes : a_tile_bytes + b_tile_bytes;
@@ -250,8 +282,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (!bres) tma_load_3d(sb, &tmB, full, k0, n0, 0);
                     } else {
                         tma_load_3d(sa, &tmA, full, m0, k0, 0);
-                        tma_load_3d(sa + 16384, &tmA, full, m0 + 64, k0, 0);
-                        for (int i = 0; i < bn_rows / 64; ++i) tma_load_3d(sb + 16384 * i, &tmB, full, n0 + 64 * i, k0, 0);
+                        tma_load_3d(sa + mn_blk, &tmA, full, m0 + 64, k0, 0);
+                        for (int i = 0; i < bn_rows / 64; ++i) tma_load_3d(sb + mn_blk * i, &tmB, full, n0 + 64 * i, k0, 0);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -270,8 +302,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int acc = iter & 1;
                 mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                uint32_t accumulate = 0;
+                // Each tcgen05.mma truncates the fp32 accumulator once (measured: ~1.5e-8 of its magnitude per MMA, toward
+                // zero).  With one accumulator all 6*K/16 MMAs of the six-product mode truncate at full magnitude; with
+                // dual_acc only the K/16 hi*hi MMAs do -- the other five products (<= 2^-8 of it) collect in a second
+                // accumulator whose truncations are 2^-8 smaller, and the epilogue adds the two in fp32.
+                const uint32_t d_main = tmem_base + (uint32_t)(acc * p.BN * (p.dual_acc ? 2 : 1));
+                const uint32_t d_small = p.dual_acc ? d_main + (uint32_t)p.BN : d_main;
+                uint32_t acc_small = 0, acc_main = 0;
                 for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -281,32 +318,40 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < UBK / 16; ++j) {
                         if (j >= k_steps) break;
-                        uint64_t a_hi, a_lo, b_hi, b_lo;
+                        uint64_t a_hi, a_lo, b_hi, b_lo, a_l3 = 0, b_l3 = 0;
+                        const bool six = p.na == 3 && p.nb == 3;
                         if (!MN_MAJOR) {
                             a_hi = smem_desc(sa + 32 * j, 16, 1024);
                             a_lo = smem_desc(sa + A_PLANE_BYTES + 32 * j, 16, 1024);
                             b_hi = smem_desc(sb + 32 * j, 16, 1024);
                             b_lo = smem_desc(sb + b_plane_bytes + 32 * j, 16, 1024);
-                            if (p.na == 3 && p.nb == 3) {
-                                // 24-bit operands: six products, smallest first (fp32-grade pre-activations, so that
-                                // ReLU decisions agree with an fp32 evaluation)
-                                const uint64_t a_l3 = smem_desc(sa + 2 * A_PLANE_BYTES + 32 * j, 16, 1024);
-                                const uint64_t b_l3 = smem_desc(sb + 2 * b_plane_bytes + 32 * j, 16, 1024);
-                                umma_bf16(d_tmem, a_l3, b_hi, idesc, accumulate);
-                                umma_bf16(d_tmem, a_hi, b_l3, idesc, 1u);
-                                umma_bf16(d_tmem, a_lo, b_lo, idesc, 1u);
-                                accumulate = 1u;
+                            if (six) {
+                                a_l3 = smem_desc(sa + 2 * A_PLANE_BYTES + 32 * j, 16, 1024);
+                                b_l3 = smem_desc(sb + 2 * b_plane_bytes + 32 * j, 16, 1024);
                             }
                         } else {
-                            a_hi = smem_desc(sa + 2048 * j, 16384, 1024);
-                            a_lo = smem_desc(sa + 8192 + 2048 * j, 16384, 1024);
-                            b_hi = smem_desc(sb + 2048 * j, 16384, 1024);
-                            b_lo = smem_desc(sb + 8192 + 2048 * j, 16384, 1024);
+                            a_hi = smem_desc(sa + 2048 * j, mn_blk, 1024);
+                            a_lo = smem_desc(sa + 8192 + 2048 * j, mn_blk, 1024);
+                            b_hi = smem_desc(sb + 2048 * j, mn_blk, 1024);
+                            b_lo = smem_desc(sb + 8192 + 2048 * j, mn_blk, 1024);
+                            if (six) {
+                                a_l3 = smem_desc(sa + 16384 + 2048 * j, mn_blk, 1024);
+                                b_l3 = smem_desc(sb + 16384 + 2048 * j, mn_blk, 1024);
+                            }
                         }
-                        umma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate);      // small terms first
-                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
-                        accumulate = 1u;
+                        if (six) {
+                            // 24-bit operands: six products, smallest first (fp32-grade pre-activations, so that ReLU
+                            // decisions agree with an fp32 evaluation; the ill-conditioned sums of the density path)
+                            umma_bf16(d_small, a_l3, b_hi, idesc, acc_small);
+                            umma_bf16(d_small, a_hi, b_l3, idesc, 1u);
+                            umma_bf16(d_small, a_lo, b_lo, idesc, 1u);
+                            acc_small = 1u;
+                        }
+                        umma_bf16(d_small, a_lo, b_hi, idesc, acc_small);      // small terms first
+                        umma_bf16(d_small, a_hi, b_lo, idesc, 1u);
+                        acc_small = 1u;
+                        umma_bf16(d_main, a_hi, b_hi, idesc, p.dual_acc ? acc_main : 1u);
+                        acc_main = 1u;
                     }
                     umma_commit(bar_empty + 8 * stage);                          // frees the stage when the MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -363,19 +408,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN * (p.dual_acc ? 2 : 1));
             if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
                 // fp32 outputs (split-K partials, the 16-wide density head): direct stores
                 for (int c0 = 16 * half; c0 < p.BN; c0 += 16 * p.epi_split) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);                                   // warp-collective: outside the row guard
+                    if (p.dual_acc) {
+                        float u[16];
+                        tmem_ld16(taddr + p.BN + c0, u);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += u[i];
+                    }
                     if (!row_ok) continue;
+                    if (!MN_MAJOR && p.near_list) near_zero_guard<16>(p, v, row, row_ok, n0 + c0);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const long long col = n0 + c0 + 8 * h;
                         if (col >= p.N) continue;
                         float* x = v + 8 * h;
-                        float* dst = MN_MAJOR ? p.c32 + ((long long)split * p.M + row) * p.ldc32 + col : p.c32 + row * p.ldc32 + col;
+                        float* dst = (MN_MAJOR || p.k_splits > 1) ? p.c32 + ((long long)split * p.M + row) * p.ldc32 + col
+                                                                  : p.c32 + row * p.ldc32 + col;
                         if (!MN_MAJOR && (p.flags & UF_ACCUM)) {
                             const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
                             x[0] += o0.x; x[1] += o0.y; x[2] += o0.z; x[3] += o0.w; x[4] += o1.x; x[5] += o1.y; x[6] += o1.z; x[7] += o1.w;
@@ -405,6 +458,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
+                        if (p.dual_acc) {                                       // + the small-products accumulator
+                            tmem_ld16(taddr + p.BN + c0, t0);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += t0[i];
+                            if (c0 + 16 < p.BN) {
+                                tmem_ld16(taddr + p.BN + c0 + 16, t1);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[16 + i] += t1[i];
+                            }
+                        }
                     }
                     if (p.flags & UF_BIAS) {
                         // per-ray / per-receiver additive terms of the first signal layer (the broadcast inputs of
@@ -429,6 +492,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 if (n0 + c0 + i < p.N) v[i] += __ldg(tab + (long long)my * ldt + n0 + c0 + i);
                         }
                     }
+                    if (p.near_list) near_zero_guard<32>(p, v, row, row_ok, n0 + c0);
                     if (p.flags & UF_MASK) {
                         uint32_t word = 0;
 #pragma unroll
@@ -489,6 +553,62 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// Second pass of the near-zero guard: one warp per listed element re-evaluates the dot product with fp32 FMAs on the
+// exact fp32 values of the operands (hi + mid + lo), applies the layer's epilogue and patches every output of the
+// element (planes, second planes, fp32, ReLU bit).  A few thousand elements per layer at most.
+__device__ __forceinline__ float planes_value(const __nv_bfloat16* q, long long plane, int n) {
+    float tail = __bfloat162float(q[plane]);
+    if (n == 3) tail += __bfloat162float(q[2 * plane]);
+    return __bfloat162float(q[0]) + tail;
+}
+__device__ __forceinline__ void planes_patch(__nv_bfloat16* q, long long plane, int n, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r);
+    q[0] = h;
+    q[plane] = m;
+    if (n == 3) q[2 * plane] = __float2bfloat16_rn(r - __bfloat162float(m));
+}
+__global__ void __launch_bounds__(256) umma_fixup_kernel(const UmmaParams p) {
+    const uint32_t total = *p.near_count;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (total > p.near_cap && warp == 0 && lane == 0) {                       // list overflow: poison, never hide
+        const float nan = __int_as_float(0x7fc00000);
+        if (p.flags & UF_OUT_F32) p.c32[0] = nan; else planes_patch(p.c, p.c_plane, p.nc, nan);
+    }
+    const uint32_t n = total < p.near_cap ? total : p.near_cap;
+    for (uint32_t e = warp; e < n; e += n_warps) {
+        const uint2 rc = p.near_list[e];
+        const long long row = rc.x, col = rc.y;
+        const __nv_bfloat16* a = p.a_raw + row * p.lda;
+        const __nv_bfloat16* b = p.b_raw + col * p.ldb;
+        float acc = 0.f;
+        for (int k = lane; k < p.K; k += 32) acc = fmaf(planes_value(a + k, p.a_plane, p.na), planes_value(b + k, p.b_plane, p.nb), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane != 0) continue;
+        if (p.flags & UF_BIAS) {
+            float tr = 0.f, tb = 0.f;
+            if (p.bias_ray) tr = p.bias_ray[((row / p.geo_S) % p.geo_R) * p.ld_bias_ray + col];
+            if (p.bias_rcv) tb = p.bias_rcv[(row / ((long long)p.geo_R * p.geo_S)) * p.ld_bias_rcv + col];
+            acc += tr + tb;
+        }
+        const float pos = fmaxf(acc, 0.f);
+        if (p.flags & UF_OUT_F32) {
+            p.c32[row * p.ldc32 + col] = (p.flags & UF_RELU) ? pos : acc;
+            continue;
+        }
+        planes_patch(p.c + row * p.ldc + col, p.c_plane, p.nc, (p.flags & UF_RELU) ? pos : acc);
+        if (p.flags & UF_DUAL_RELU) planes_patch(p.c2 + row * p.ldc2 + col, p.c2_plane, p.nc, pos);
+        if (p.flags & UF_BITS) {
+            uint32_t* w = p.bits + row * p.ldbits + (col >> 5);
+            const uint32_t bit = 1u << (col & 31);
+            if (acc > 0.f) atomicOr(w, bit); else atomicAnd(w, ~bit);
+        }
     }
 }
 
@@ -598,8 +718,8 @@ static int pick_bn(long long N, int max_bn = 256) {
     return best;
 }
 
-static int tmem_cols_for(int bn) {
-    int need = 2 * bn, c = 32;
+static int tmem_cols_for(int bn, int dual = 0) {
+    int need = (dual ? 4 : 2) * bn, c = 32;
     while (c < need) c <<= 1;
     return c;
 }
@@ -641,15 +761,24 @@ AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int
     return AVR_OK;
 }
 
+// number of interleaved K slices of the split-K mode of avr_umma_gemm_nt: 256-deep slices (1 when K <= 512)
+AVR_API int64_t avr_umma_gemm_nt_splitk_slices(int64_t K) { return K <= 512 ? 1 : ceil_div(K, 256); }
+
 // C[M,N] = A[M,K] . B[N,K]^T on plane pairs (both K-major).  Output: plane pair (default) or fp32 (UF_OUT_F32).
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
                              int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
                              int64_t ldbits, const float* bias_ray, int64_t ld_bias_ray, const float* bias_rcv,
-                             int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32, int device,
-                             void* stream) {
+                             int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32,
+                             uint32_t* near_list, int64_t near_cap, uint32_t* near_count, float near_tau,
+                             void* splitk_workspace, int64_t splitk_workspace_bytes, int device, void* stream) {
     AVR_REQUIRE(a_planes && b_planes, "null operand");
+    if (near_list) {
+        AVR_REQUIRE(near_count && near_cap > 0 && near_cap < (1ll << 31) && near_tau >= 0.f && aligned16(near_list),
+                    "near-zero guard needs a list, its capacity and a zeroed counter");
+        AVR_REQUIRE(!(flags & (UF_MASK | UF_ACCUM)), "the near-zero guard applies to forward layers (no MASK / ACCUM)");
+    }
     AVR_REQUIRE((a_nplanes == 2 || a_nplanes == 3) && (b_nplanes == 2 || b_nplanes == 3) && (c_nplanes == 2 || c_nplanes == 3),
                 "plane counts must be 2 or 3");
     if (!(a_nplanes == 3 && b_nplanes == 3)) a_nplanes = b_nplanes = 2;     // six products need 24 bits on both sides
@@ -669,7 +798,19 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.BN = pick_bn(N, a_nplanes == 3 ? 128 : 256);
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
-    p.tmem_cols = tmem_cols_for(p.BN);
+    // long reductions into an fp32 output (the DFT and its adjoint, K = T or 2F): the accumulator is truncated once per
+    // MMA, a bias that grows with the chain length.  Short interleaved K slices into separate accumulators, summed in
+    // fp32 by the deterministic reduce below, cut it by ~(number of slices)^1.5.
+    const int64_t splitk_ld = ceil_div(N, 8) * 8;
+    if (splitk_workspace) {
+        AVR_REQUIRE((flags & UF_OUT_F32) && !(flags & (UF_RELU | UF_ACCUM)) && !near_list && aligned16(splitk_workspace),
+                    "split-K applies to plain fp32 outputs");
+        const int64_t splits = avr_umma_gemm_nt_splitk_slices(K);
+        AVR_REQUIRE(splitk_workspace_bytes >= splits * M * splitk_ld * (int64_t)sizeof(float), "split-K workspace too small");
+        p.k_splits = (int)splits;
+    }
+    p.dual_acc = (p.na == 3 && p.nb == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC")) ? 1 : 0;
+    p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
     p.flags = flags;
     p.c = (__nv_bfloat16*)c_planes; p.ldc = ldc; p.c_plane = c_plane;
     p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
@@ -685,6 +826,10 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     if (getenv("AVR_UMMA_NOWAIT")) p.flags |= UF_DEBUG_NOWAIT;       // timing experiments only: results are garbage
     if (const char* dbg = getenv("AVR_UMMA_DEBUG")) p.flags |= (atoi(dbg) & (UF_DEBUG_NOWAIT | UF_DEBUG_NOSTORE | UF_DEBUG_NOSTAGE | UF_DEBUG_NOFENCE));
     p.c32 = c_f32; p.ldc32 = ldc32;
+    if (p.k_splits > 1) { p.c32 = (float*)splitk_workspace; p.ldc32 = splitk_ld; }
+    p.near_list = (uint2*)near_list; p.near_cap = (uint32_t)near_cap; p.near_count = near_count; p.near_tau = near_tau;
+    p.a_raw = (const __nv_bfloat16*)a_planes; p.lda = lda; p.a_plane = a_plane;
+    p.b_raw = (const __nv_bfloat16*)b_planes; p.ldb = ldb; p.b_plane = b_plane;
     const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
     p.nkb = (int)ceil_div(K, UBK);
     p.epi_warp_bytes = (flags & UF_OUT_F32) ? 0u : (uint32_t)p.nc * EPI_PLANE_BYTES;
@@ -719,53 +864,67 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
             if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, p.nc, true)) return rc;
     }
     AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = p.tiles_m * p.tiles_n;
+    const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
     const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
     umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, tc, tc2, p);
     AVR_LAUNCH_CHECK();
+    if (p.k_splits > 1) {
+        umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * (N / 4) * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const float*)splitk_workspace, splitk_ld, p.k_splits, M, N, c_f32, ldc32, 0);
+        AVR_LAUNCH_CHECK();
+    }
+    if (near_list) {
+        umma_fixup_kernel<<<num_sms(device), 256, 0, (cudaStream_t)stream>>>(p);
+        AVR_LAUNCH_CHECK();
+    }
     return AVR_OK;
 }
 
-AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-    if (M <= 0 || N <= 0 || K <= 0) return 0;
-    const int bn = pick_bn(N);
+// split-K slices of the weight-gradient GEMM for a given tile width
+static int64_t tn_splits(int64_t M, int64_t N, int64_t K, int bn) {
     const int64_t tiles = ceil_div(M, UM) * ceil_div(N, bn);
     int64_t splits = 148 / tiles;                  // one wave: tiles * splits <= number of SMs
     const int64_t max_by_k = ceil_div(K, 1024);
     if (splits > max_by_k) splits = max_by_k;
-    if (splits < 1) splits = 1;
-    return splits * M * (ceil_div(N, 8) * 8) * (int64_t)sizeof(float);
+    return splits < 1 ? 1 : splits;
+}
+
+AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const int64_t s2 = tn_splits(M, N, K, pick_bn(N)), s3 = tn_splits(M, N, K, pick_bn(N, 128));   // either plane count
+    return (s2 > s3 ? s2 : s3) * M * (ceil_div(N, 8) * 8) * (int64_t)sizeof(float);
 }
 
 // C[M,N] (+)= sum_k A[k,M] * B[k,N] on plane pairs stored [K, M] and [K, N] (both MN-major); fp32 output,
 // deterministic split-K over k (the sample points).
 AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
-                             const void* b_planes, int64_t ldb, int64_t b_plane, float* c, int64_t ldc, int accumulate,
-                             void* workspace, int64_t workspace_bytes, int device, void* stream) {
+                             const void* b_planes, int64_t ldb, int64_t b_plane, int nplanes, float* c, int64_t ldc,
+                             int accumulate, void* workspace, int64_t workspace_bytes, int device, void* stream) {
     AVR_REQUIRE(a_planes && b_planes && c && workspace, "null pointer");
+    AVR_REQUIRE(nplanes == 2 || nplanes == 3, "nplanes must be 2 (three products) or 3 (six products)");
     AVR_REQUIRE(M > 0 && N > 0 && K >= 0, "bad dimensions");
     AVR_REQUIRE(M % 4 == 0 && N % 4 == 0, "M and N must be multiples of 4");
     AVR_REQUIRE(K < (1ll << 31), "dimension overflow");
     AVR_ENTER(device);
     UmmaParams p = {};
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.BN = pick_bn(N);
-    p.na = p.nb = p.nc = 2;
+    p.BN = pick_bn(N, nplanes == 3 ? 128 : 256);                // three planes: two stages and two accumulators must fit
+    p.na = p.nb = nplanes; p.nc = 2;
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
-    const int64_t need = avr_umma_gemm_tn_workspace_bytes(M, N, K);
-    AVR_REQUIRE(workspace_bytes >= need && aligned16(workspace), "workspace too small or misaligned");
     const int64_t ldp = ceil_div(N, 8) * 8;                    // partial rows padded to whole 8-column store groups
-    int64_t splits = need / (M * ldp * (int64_t)sizeof(float));
-    if (splits < 1) splits = 1;
+    const int64_t splits = K > 0 ? tn_splits(M, N, K, p.BN) : 1;
+    AVR_REQUIRE(workspace_bytes >= splits * M * ldp * (int64_t)sizeof(float) && aligned16(workspace),
+                "workspace too small or misaligned");
     p.k_per_split = (int)(ceil_div(ceil_div(K, splits), UBK) * UBK);
     if (p.k_per_split < UBK) p.k_per_split = UBK;
     p.k_splits = (int)(K > 0 ? ceil_div(K, p.k_per_split) : 1);
-    p.tmem_cols = tmem_cols_for(p.BN);
+    p.dual_acc = (nplanes == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC")) ? 1 : 0;
+    p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
     p.c32 = (float*)workspace; p.ldc32 = ldp;
     p.epi_split = 2; p.epi_warp_bytes = 0;
     if (const char* e = getenv("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
     const int bn_rows = (p.BN + 63) / 64 * 64;
-    const uint32_t stage_bytes = A_TILE_BYTES + (uint32_t)bn_rows * 256u;
+    const uint32_t stage_bytes = (uint32_t)nplanes * (A_PLANE_BYTES + (uint32_t)bn_rows * 128u);
     p.stages = (int)((220 * 1024) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
@@ -773,8 +932,8 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     cudaStream_t st = (cudaStream_t)stream;
     if (K > 0) {
         CUtensorMap ta, tb;
-        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, 2)) return rc;
-        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, 2)) return rc;
+        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, nplanes)) return rc;
+        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nplanes)) return rc;
         AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);

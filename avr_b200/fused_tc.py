@@ -19,7 +19,16 @@ from .ops import PlanePair
 
 
 FWD_PLANES = 3      # forward operands carry 24 mantissa bits (six products): ReLU decisions must match fp32
-BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough
+BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough ...
+DENSITY_BWD_PLANES = 3   # ... except along the sigma decoder: the density gradient of a ray sums to ~0 over its samples
+                         # (sum_s w_s = 1), so the decoder's weight-gradient sums cancel to ~1/50 of their terms
+                         # (measured, profiles/diag_tn.py) and 16-bit operands leave ~1e-3 there
+NEAR_ZERO_GUARD = False  # forward layers: re-evaluate pre-activations too close to zero for the tensor core's
+                         # accumulation error with fp32 FMAs (ops.NearZeroGuard).  Needed with ONE accumulator per tile
+                         # (error ~6e-9*K, 3-5 flipped ReLU decisions per 1e7 vs 0-1 for fp32); with the main/small
+                         # accumulator pair the forward is fp32-grade (2.1e-7 at K = 512, cuBLAS fp32: 2.4e-7) and the
+                         # guard changes nothing measurable (profiles/r1/parity_real_networks.md), so it is off
+LAST_GUARD_COUNTS = None  # diagnostics: per-layer number of re-evaluated elements of the latest forward (device tensor)
 
 
 def _weight_planes(net, params, transpose, n):
@@ -94,6 +103,9 @@ class FusedRenderTC(torch.autograd.Function):
         small_in = {"ray": u_view, "receiver_tx": u_tx, "receiver_dir_tx": u_dtx}
         delay = torch.empty(geom.bs, geom.R, geom.S, dtype=torch.int32, device=dev)
         delay_slot = [delay]
+        guard = ops.NearZeroGuard(dev) if NEAR_ZERO_GUARD else None
+        global LAST_GUARD_COUNTS
+        LAST_GUARD_COUNTS = guard.counters if guard is not None else None
 
         # ---- sigma encoder ------------------------------------------------------------------------
         x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
@@ -107,7 +119,7 @@ class FusedRenderTC(torch.autograd.Function):
             y = PlanePair.empty(n_rows, w_enc[li].rows, dev, n=FWD_PLANES)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev)
             fl, kw = layer_flags("enc", li)
-            ops.umma_nt(h, w_enc[li], fl, y, bits_out=bits, **kw)
+            ops.umma_nt(h, w_enc[li], fl, y, bits_out=bits, guard=guard, **kw)
             acts_enc.append(y)
             bits_enc.append(bits)
             h = y
@@ -116,11 +128,11 @@ class FusedRenderTC(torch.autograd.Function):
         feat_win = sig_in.window(0, feat_dim)
         bits_feat = ops.relu_bits_empty(n_rows, feat_dim, dev)               # (sigma_feat > 0)
         if plan["sig_relu_feat"]:
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat)        # both consumers read relu(feat)
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat, guard=guard)        # both consumers read relu(feat)
             dec_in = feat_win
         else:
             dec_buf = PlanePair.empty(n_rows, dec_net.in_pad, dev, n=FWD_PLANES)
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_buf.window(0, feat_dim), bits_out=bits_feat)   # raw feat + relu(feat)
+            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_buf.window(0, feat_dim), bits_out=bits_feat, guard=guard)   # raw feat + relu(feat)
             if dec_net.in_pad > feat_dim:                                    # decoder input = [relu(feat), embedding row]
                 _assemble(plan.get("dec_tail", []), dec_buf, feat_dim, dec_net.in_pad, geom, small_in, rays_o, pos_tx, dirs,
                           d_vals, params_of, [], rows_of)
@@ -135,12 +147,12 @@ class FusedRenderTC(torch.autograd.Function):
             y = PlanePair.empty(n_rows, w_dec[li].rows, dev, n=FWD_PLANES)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev)
             fl, kw = layer_flags("dec", li)
-            ops.umma_nt(h, w_dec[li], fl, y, bits_out=bits, **kw)
+            ops.umma_nt(h, w_dec[li], fl, y, bits_out=bits, guard=guard, **kw)
             acts_dec.append(y)
             bits_dec.append(bits)
             h = y
         dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
-        ops.umma_nt(h, w_dec[-1], ops.UMMA_OUT_F32, c_f32=dec_out)
+        ops.umma_nt(h, w_dec[-1], ops.UMMA_OUT_F32, c_f32=dec_out, guard=guard)   # the |leaky_relu| kink
         w, _ = ops.ray_weights_fwd(geom, dec_out, dec_out.stride(0), tables["delta"], plan["slope"])
 
         # ---- signal network hidden layers + collapsed output layer ---------------------------------
@@ -153,7 +165,7 @@ class FusedRenderTC(torch.autograd.Function):
             y = PlanePair.empty(n_rows, w_sig[li].rows, dev, n=FWD_PLANES)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev) if li < len(w_sig) - 1 else None   # last one is read by collapse
             fl, kw = layer_flags("sig", li)
-            ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, **kw)
+            ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, guard=guard, **kw)
             acts_sig.append(y)
             bits_sig.append(bits)
             h = y
@@ -238,17 +250,17 @@ class FusedRenderTC(torch.autograd.Function):
         d_dec_out = torch.zeros_like(B["dec_out"])
         ops.ray_weights_bwd(geom, B["dec_out"], B["dec_out"].stride(0), tables["delta"], plan["slope"], d_w, d_dec_out,
                             d_dec_out.stride(0))
-        wt_dec = _weight_planes(dec_net, pmap[id(dec_net)], True, BWD_PLANES)
+        wt_dec = _weight_planes(dec_net, pmap[id(dec_net)], True, DENSITY_BWD_PLANES)
         g_dec = torch.empty_like(pmap[id(dec_net)])
         d_dec_mats = dec_net.matrices(g_dec)
-        g = PlanePair.empty(n_rows, dec_net.out_pad, dev)
+        g = PlanePair.empty(n_rows, dec_net.out_pad, dev, n=DENSITY_BWD_PLANES)
         ops.planes_split(d_dec_out, g)
         acts_dec = B["acts_dec"]
         n_dec = len(d_dec_mats)
         for li in range(n_dec - 1, 0, -1):
             x = acts_dec[li - 1]
             ops.umma_tn(g, x, d_dec_mats[li], ws)
-            gx = PlanePair.empty(n_rows, x.cols, dev)
+            gx = PlanePair.empty(n_rows, x.cols, dev, n=DENSITY_BWD_PLANES)
             ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=B["bits_dec"][li - 1])
             g = gx
             bias_grad("dec", li - 1, g)

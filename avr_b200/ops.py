@@ -331,13 +331,39 @@ def relu_bits_empty(rows, cols, device):
     return torch.empty(rows, words, dtype=torch.int32, device=device)
 
 
+class NearZeroGuard:
+    """Storage of the near-zero guard of the forward layers (``include/avr_b200.h``, ``avr_umma_gemm_nt``): one list
+    shared by the layers of a pass (each layer's fix-up kernel has consumed it before the next GEMM starts on the
+    stream) and one zeroed counter per layer, kept for inspection (``counts()``)."""
+
+    TAU_PER_K = 1e-7        # threshold relative to the row-chunk scale: TAU_PER_K * K (tensor-core error ~6e-9 * K), at least
+    TAU_MIN = 4e-6
+
+    def __init__(self, device, layers=32, capacity=1 << 20):
+        self.list = torch.empty(capacity, 2, dtype=torch.int32, device=device)
+        self.counters = torch.zeros(layers, dtype=torch.int32, device=device)
+        self.used = 0
+
+    def next_slot(self):
+        if self.used >= self.counters.numel():
+            raise RuntimeError("NearZeroGuard: out of counters")
+        self.used += 1
+        return self.counters[self.used - 1:]
+
+    def counts(self):
+        return self.counters[:self.used].tolist()
+
+
 def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlanePair = None, mask=None, c_f32=None,
-            bits_out=None, bias_ray=None, bias_rcv=None, geom=None):
+            bits_out=None, bias_ray=None, bias_rcv=None, geom=None, guard: NearZeroGuard = None, split_k=False):
     """C[M,N] = A[M,K] B[N,K]^T on the tensor cores; C is a plane set or (UMMA_OUT_F32) an fp32 tensor.
 
     ``mask`` (with UMMA_MASK): int32 bitmask ``[M, words]`` gating the product (ReLU backward);
     ``bits_out``: if given, the bitmask ``(C > 0)`` is written (forward ReLU layers).
     ``bias_ray[R,N]`` / ``bias_rcv[bs,N]`` (fp32, with ``geom``): rows added to every sample point of a ray / receiver.
+    ``guard``: near-zero guard storage; elements too close to zero for the tensor core's accumulation error are
+    re-evaluated in fp32 by a second kernel of the same call (forward layers).
+    ``split_k`` (plain fp32 outputs): short interleaved K slices into separate accumulators, summed in fp32 (long reductions).
     """
     dev, st = _ctx(a)
     M, K, N = a.rows, a.cols, b.rows
@@ -348,6 +374,10 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
     if bias_ray is not None or bias_rcv is not None:
         flags |= UMMA_BIAS
     products = 6 if (a.n == 3 and b.n == 3) else 3
+    ws = None
+    if split_k:
+        slices = int(_lib.load().avr_umma_gemm_nt_splitk_slices(K))
+        ws = torch.empty(slices * M * ((N + 7) // 8 * 8), device=a.device)
     with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * products):
         _lib.check(_lib.load().avr_umma_gemm_nt(
             M, N, K, a.ptr, a.ld, a.plane, a.n, b.ptr, b.ld, b.plane, b.n, flags,
@@ -359,7 +389,11 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
             _p(bias_ray), bias_ray.stride(0) if bias_ray is not None else 0,
             _p(bias_rcv), bias_rcv.stride(0) if bias_rcv is not None else 0,
             geom.R if geom is not None else 0, geom.S if geom is not None else 0,
-            _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0, dev, st), "avr_umma_gemm_nt")
+            _p(c_f32), c_f32.stride(0) if c_f32 is not None else 0,
+            _p(guard.list, torch.int32) if guard is not None else none, guard.list.shape[0] if guard is not None else 0,
+            _p(guard.next_slot(), torch.int32) if guard is not None else none,
+            max(NearZeroGuard.TAU_MIN, NearZeroGuard.TAU_PER_K * K) if guard is not None else 0.0,
+            _p(ws), ws.numel() * 4 if ws is not None else 0, dev, st), "avr_umma_gemm_nt")
 
 
 def umma_tn_workspace_bytes(M, N, K) -> int:
@@ -371,8 +405,9 @@ def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
     dev, st = _ctx(a)
     K, M, N = a.rows, a.cols, b.cols
     assert b.rows == K
-    with _timed("umma_gemm", 2.0 * M * N * K, "flop", 6.0 * M * N * K):
-        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, _p(c_f32),
+    nplanes = 3 if (a.n == 3 and b.n == 3) else 2          # six products only when both operands carry 24 bits
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * (6 if nplanes == 3 else 3)):
+        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, nplanes, _p(c_f32),
                                                 c_f32.stride(0), 1 if accumulate else 0,
                                                 C.c_void_p(workspace.data_ptr()),
                                                 workspace.numel() * workspace.element_size(), dev, st), "avr_umma_gemm_tn")
@@ -525,6 +560,8 @@ def collapse_bwd(g, act: PlanePair, sort, w_out, d_y, tspan, prefix, d_act: Plan
 
 
 # ---- spectrum stage with the DFT on the tensor cores ---------------------------------------------------------
+SPECTRUM_SPLIT_K = True     # False only for A/B measurements of the accumulator-truncation bias
+
 def dft_planes(tables):
     """Plane sets of the DFT matrix, built once per table set: dft^T [ldd, T] and dft [T, ldd], 3 planes each.
 
@@ -547,7 +584,7 @@ def spectrum_fwd_tc(g, y, tables):
     _lib.check(_lib.load().avr_spectrum_gain(C.byref(g), _p(_dense(y)), _p(tables["gain"]), z.ptr, z.ld, z.plane, z.n, dev, st),
                "avr_spectrum_gain")
     xbuf = torch.empty(rows, ldd, device=y.device)
-    umma_nt(z, dft_t, UMMA_OUT_F32, c_f32=xbuf)
+    umma_nt(z, dft_t, UMMA_OUT_F32, c_f32=xbuf, split_k=SPECTRUM_SPLIT_K)
     out = torch.empty(g.bs, g.T // 2 + 1, 2, device=y.device)
     _lib.check(_lib.load().avr_spectrum_phase_sum(C.byref(g), _p(xbuf), ldd, _p(tables["phase"]), _p(out), dev, st),
                "avr_spectrum_phase_sum")
@@ -562,7 +599,7 @@ def spectrum_bwd_tc(g, d_out, tables):
     _lib.check(_lib.load().avr_spectrum_phase_bwd(C.byref(g), _p(_dense(d_out)), _p(tables["phase"]), q.ptr, q.ld, q.plane,
                                                   q.n, dev, st), "avr_spectrum_phase_bwd")
     d_y = torch.empty(g.bs, g.S, g.T, device=d_out.device)
-    umma_nt(q, dft, UMMA_OUT_F32, c_f32=d_y.view(rows, g.T))
+    umma_nt(q, dft, UMMA_OUT_F32, c_f32=d_y.view(rows, g.T), split_k=SPECTRUM_SPLIT_K)
     _lib.check(_lib.load().avr_spectrum_gain(C.byref(g), _p(d_y), _p(tables["gain"]), C.c_void_p(d_y.data_ptr()), g.T, 0, 0,
                                              dev, st), "avr_spectrum_gain")
     return d_y

@@ -171,20 +171,36 @@ AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t
 AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride,
                              int nplanes, float* out, int64_t ld, int device, void* stream);
 /* C[M,N] = A[M,K] . B[N,K]^T   (A, B plane pairs with the reduction index contiguous; N % 8 == 0).
- * Forward layers (B = W[out,in]) and backward-data (B = transposed weight planes W^T[in,out]). */
+ * Forward layers (B = W[out,in]) and backward-data (B = transposed weight planes W^T[in,out]).
+ * Near-zero guard (forward layers; near_list != NULL): the tensor core truncates its accumulator once per MMA
+ * (~6e-9*K of the row scale, biased), enough to flip the sign of pre-activations that an fp32 evaluation puts within
+ * that distance of zero -- and a flipped ReLU / |leaky_relu| decision changes that unit's gradient by 100 %.  Elements
+ * with |out| < near_tau * (mean |out| of their 32-column row chunk) are appended to near_list (near_cap entries of
+ * {row, col}; *near_count must be 0 on entry and holds the number listed afterwards) and a second kernel of the same
+ * call re-evaluates them with fp32 FMAs over the exact operand values and patches c / c2 / c_f32 / bits_out.  The
+ * listed set depends only on the values, so results stay bit-identical run to run; a list overflow poisons the
+ * output with NaN. */
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
                              int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
                              int64_t ldbits, const float* bias_ray, int64_t ld_bias_ray, const float* bias_rcv,
-                             int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32, int device,
-                             void* stream);
-/* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane pairs; weight gradients).
- * fp32 output; deterministic split-K over the points through `workspace`. */
+                             int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32,
+                             uint32_t* near_list, int64_t near_cap, uint32_t* near_count, float near_tau,
+                             void* splitk_workspace, int64_t splitk_workspace_bytes, int device, void* stream);
+/* Split-K mode (plain AVR_UMMA_OUT_F32 outputs, splitk_workspace != NULL): the reduction runs as
+ * avr_umma_gemm_nt_splitk_slices(K) interleaved 256-deep slices into separate accumulators, summed in fp32 in a fixed
+ * order -- for the long reductions of the DFT and its adjoint (K = T, 2F), where the per-MMA truncation of one long
+ * accumulator chain is a visible bias (~6e-9*K).  Workspace: slices * M * roundup(N, 8) * 4 bytes. */
+AVR_API int64_t avr_umma_gemm_nt_splitk_slices(int64_t K);
+/* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane sets; weight gradients).
+ * fp32 output; deterministic split-K over the points through `workspace`.  nplanes = 2: three products on the
+ * (hi, mid) planes; 3: six products on 24-bit operands (both sets must then hold three planes) -- for the
+ * ill-conditioned sums of the density path, whose terms cancel to ~1/50 of their magnitude. */
 AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
 AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
-                             const void* b_planes, int64_t ldb, int64_t b_plane, float* c, int64_t ldc, int accumulate,
-                             void* workspace, int64_t workspace_bytes, int device, void* stream);
+                             const void* b_planes, int64_t ldb, int64_t b_plane, int nplanes, float* c, int64_t ldc,
+                             int accumulate, void* workspace, int64_t workspace_bytes, int device, void* stream);
 
 /* ---- output layer fused with the ray reduction ("collapse"; model.py:231 + renderer.py:86-90,115-118) -----
  * y[b,s,t] = sum_r w[b,r,s] [t >= delay[b,r,s]] (H[b,r,s,:] . W_out[t,:]) evaluated as a prefix sum over the

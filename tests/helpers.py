@@ -42,31 +42,22 @@ def rel_l2(a, b):
     return render_ref.rel_l2(torch.as_tensor(a).cpu(), torch.as_tensor(b).cpu())
 
 
-def oracle_fp32_noise(ref_net, render_kwargs, rx, tx, G, **fwd_kwargs):
-    """How far the fp32 oracle is from itself with the FIELD evaluated in float64 (same fp32 geometry / renderer):
-    ``(rel_l2 of the IR, {param name: rel_l2 of its gradient})``.  On the tiny test configs this rounding noise of
-    the checker can reach the 1e-4 parity bar, so tests may widen their tolerance to a small multiple of it."""
+def oracle_fp32_noise(ref_net, render_kwargs, rx, tx, G, dtx=None, **fwd_kwargs):
+    """How far the fp32 oracle is from itself with the dense layers evaluated in float64: ``(rel_l2 of the IR,
+    {param name: rel_l2 of its gradient})``.  Geometry, renderer and the hash-grid cell positions stay fp32 (the
+    network inputs are NOT widened: at the fine levels of the real grids, resolution ~2^21, a float64 position lands
+    elsewhere in the cell and would measure a different function, not rounding noise).  A single ReLU /
+    |leaky_relu| decision that differs between the two evaluations moves a gradient by ~1e-4, so on some weight
+    draws this noise of the checker reaches the 1e-4 parity bar; tests take the first seed where it does not."""
     import copy
 
-    from oracle import render_ref
     net64 = copy.deepcopy(ref_net).double()
-    for p in net64.parameters():
-        p.grad = None
-
-    class _Wrap(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.net = net64
-
-        def forward(self, *a, **kw):
-            return self.net(*[x.double() for x in a], **kw)
-
     net32 = copy.deepcopy(ref_net)
-    for p in net32.parameters():
+    for p in list(net64.parameters()) + list(net32.parameters()):
         p.grad = None
-    out32 = render_ref.RenderRef(net32, **render_kwargs)(rx, tx, None, **fwd_kwargs)
+    out32 = render_ref.RenderRef(net32, **render_kwargs)(rx, tx, dtx, **fwd_kwargs)
     (out32 * G).sum().backward()
-    out64 = render_ref.RenderRef(_Wrap(), **render_kwargs)(rx, tx, None, **fwd_kwargs)
+    out64 = render_ref.RenderRef(net64, **render_kwargs)(rx, tx, dtx, **fwd_kwargs)
     (out64 * G.double()).sum().backward()
     g32 = dict(net32.named_parameters())
     return rel_l2(out32, out64), {n: rel_l2(g32[n].grad, p.grad) for n, p in net64.named_parameters()}

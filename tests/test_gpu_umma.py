@@ -99,6 +99,91 @@ def test_umma_nt_six_products_fp32_grade(built_library, M, N, K):
     assert rel_l2(c32, ref) < bound
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 2400, 2402), (256, 1608, 1600), (100, 808, 640)])
+def test_umma_nt_split_k_long_reduction(built_library, M, N, K):
+    """The DFT / adjoint-DFT shapes: one accumulator chain of K/16*6 MMAs is truncated once per MMA (a bias of
+    ~6e-9*K); the split-K mode sums 256-deep slices in fp32 instead and must be markedly closer to float64."""
+    g = torch.Generator().manual_seed(K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    a, b = _pp(A, n=3), _pp(B, n=3)
+    ref = ops.planes_merge(a).double() @ ops.planes_merge(b).double().t()
+    c0, c1, c2 = (torch.empty(M, N, device=DEV) for _ in range(3))
+    ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c0)
+    ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c1, split_k=True)
+    ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c2, split_k=True)
+    e0, e1 = rel_l2(c0, ref), rel_l2(c1, ref)
+    assert e1 < 2.5e-6 and e1 < 0.4 * e0, (e0, e1)
+    assert torch.equal(c1, c2)
+
+
+def _unpack_bits(bits, N):
+    sh = torch.arange(32, device=bits.device, dtype=torch.int32)
+    return ((bits[:, :(N + 31) // 32].unsqueeze(-1) >> sh) & 1).reshape(bits.shape[0], -1)[:, :N].bool()
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(8192, 512, 512, "relu"), (8192, 128, 128, "dual"), (5000, 512, 208, "bias"),
+                                         (40000, 16, 128, "f32")])
+def test_umma_near_zero_guard(built_library, M, N, K, mode):
+    """Forward layers: elements too close to zero for the tensor core's accumulation error (one truncation per MMA,
+    ~6e-9*K of the row scale, biased) are listed by the epilogue and re-evaluated with fp32 FMAs, so that sign decisions
+    (ReLU masks, the |leaky_relu| kink of the density head) are fp32-grade.  The listed set is a function of the values
+    only: outputs and counts are bit-identical run to run."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g).clamp_min(0), torch.randn(N, K, generator=g) / K ** 0.5
+    a, b = _pp(A, n=3), _pp(B, n=3)
+    ref = ops.planes_merge(a).double() @ ops.planes_merge(b).double().t()
+    kw, geom = {}, None
+    if mode == "bias":
+        from avr_b200.configs import tiny_config
+        geom = ops.make_geom(tiny_config("AVRModel", n_azi=6, n_ele=4, n_samples=10)["render"], M // (26 * 10), 400)
+        M = geom.bs * geom.R * geom.S
+        a, ref = a.row_window(0, M), ref[:M]
+        t_rcv = torch.randn(geom.bs, N, generator=g).to(DEV)
+        ref = ref + t_rcv.double().repeat_interleave(geom.R * geom.S, 0)
+        kw = dict(bias_rcv=t_rcv, geom=geom)
+    scale = ref.abs().mean(1, keepdim=True)
+    tau = max(ops.NearZeroGuard.TAU_MIN, ops.NearZeroGuard.TAU_PER_K * K)
+
+    def run(guard):
+        bits = ops.relu_bits_empty(M, N, DEV).zero_()
+        c, c2 = PlanePair.zeros(M, N, DEV, n=3), PlanePair.zeros(M, N, DEV, n=3)
+        c32 = torch.zeros(M, N, device=DEV)
+        if mode == "f32":
+            ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c32, guard=guard)
+            return c32, None, None
+        if mode == "dual":
+            ops.umma_nt(a, b, ops.UMMA_DUAL_RELU, c, c2, bits_out=bits, guard=guard)
+            return ops.planes_merge(c), ops.planes_merge(c2), _unpack_bits(bits, N)
+        ops.umma_nt(a, b, ops.UMMA_RELU, c, bits_out=bits, guard=guard, **kw)
+        return None, ops.planes_merge(c), _unpack_bits(bits, N)
+
+    guard = ops.NearZeroGuard(DEV)
+    raw, pos, bits = run(guard)
+    n_listed = guard.counts()[0]
+    listed = guard.list[:n_listed].long()
+    assert 0 < n_listed < 1e-3 * M * N
+    near = torch.zeros(M, N, dtype=torch.bool, device=DEV)
+    near[listed[:, 0], listed[:, 1]] = True
+    # everything well inside the threshold is listed, nothing well outside (the scale is a 32-column estimate)
+    assert bool(near[ref.abs() < 0.3 * tau * scale].all()) and not bool(near[ref.abs() > 3 * tau * scale].any())
+    # listed elements carry fp32-FMA values: error ~1e-7 of the row scale instead of ~6e-9*K
+    for val, want in ((raw, ref), (pos, ref.clamp_min(0))):
+        if val is not None:
+            assert float(((val.double() - want).abs() / scale)[near].max()) < 6e-7
+    if bits is not None:
+        assert torch.equal(bits, pos > 0)
+        assert int((bits != (ref > 0)).sum()) <= 2                 # fp32-grade decisions (float64 disagrees ~1e-7 of the time)
+    # unguarded: same values elsewhere; guarded runs are reproducible
+    raw0, pos0, bits0 = run(None)
+    for x, x0 in ((raw, raw0), (pos, pos0)):
+        if x is not None:
+            assert torch.equal(x[~near], x0[~near])
+    guard2 = ops.NearZeroGuard(DEV)
+    raw2, pos2, bits2 = run(guard2)
+    assert guard2.counts()[0] == n_listed
+    assert all(x is None or torch.equal(x, y) for x, y in ((raw, raw2), (pos, pos2), (bits, bits2)))
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (512, 512, 20000), (16, 128, 5000), (128, 48, 3001), (512, 208, 7777),
                                    (1600, 512, 4100), (128, 80, 64)])
 def test_umma_tn_weight_grad(built_library, M, N, K):
@@ -114,6 +199,26 @@ def test_umma_tn_weight_grad(built_library, M, N, K):
     assert torch.equal(outs[0], outs[1])                     # deterministic split-K
     assert rel_l2(outs[0][:, :N], dY.double().t() @ X.double()) < TOL
     assert float(outs[0][:, N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 128, 5000), (128, 128, 20000), (128, 48, 3001), (512, 208, 2000), (128, 256, 9000)])
+def test_umma_tn_six_products_ill_conditioned(built_library, M, N, K):
+    """Weight gradients of the density path: the terms of sum_k dY[k,m] X[k,n] cancel to a few percent of their
+    magnitude, so the 16-bit (three-product) mode is ~30x too coarse there; 24-bit operands / six products are not."""
+    g = torch.Generator().manual_seed(M + N + K)
+    X = 1 + 0.5 * torch.randn(K, N, generator=g)
+    dY = torch.randn(K, M, generator=g)
+    dY -= dY.mean(0, keepdim=True)                                              # sums against X cancel ~ sqrt(K)-fold
+    a3, b3 = _pp(dY, n=3), _pp(X, n=3)
+    ref = ops.planes_merge(a3).double().t() @ ops.planes_merge(b3).double()
+    ws = torch.empty(max(4, ops.umma_tn_workspace_bytes(M, N, K) // 4), device=DEV)
+    c3, c3b, c2 = (torch.zeros(M, N, device=DEV) for _ in range(3))
+    ops.umma_tn(a3, b3, c3, ws)
+    ops.umma_tn(a3, b3, c3b, ws)
+    ops.umma_tn(_pp(dY), _pp(X), c2, ws)
+    e3, e2 = rel_l2(c3, ref), rel_l2(c2, ref)
+    assert torch.equal(c3, c3b)
+    assert e3 < 1e-5 and e3 < 0.2 * e2, (e3, e2)
 
 
 @pytest.mark.parametrize("bs,R,S,T,W", [(2, 37, 5, 200, 64), (1, 300, 7, 400, 512), (3, 66, 4, 240, 136)])
