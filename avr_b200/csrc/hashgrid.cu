@@ -20,6 +20,7 @@ struct GridDev {
     uint32_t res[AVR_MAX_LEVELS];
     uint32_t size[AVR_MAX_LEVELS];
     uint32_t offset[AVR_MAX_LEVELS];
+    uint32_t kind[AVR_MAX_LEVELS];     // 0: generic index arithmetic, 1: dense level (res^3 <= size), 2: hashed, size = 2^k
 };
 
 static GridDev make_grid(const avr_grid_meta* g) {
@@ -27,6 +28,12 @@ static GridDev make_grid(const avr_grid_meta* g) {
     d.n_levels = g->n_levels;
     for (int l = 0; l < AVR_MAX_LEVELS; ++l) {
         d.scale[l] = g->scale[l]; d.res[l] = g->res[l]; d.size[l] = g->size[l]; d.offset[l] = g->offset[l];
+        const uint64_t res = g->res[l], size = g->size[l], cube = res * res * res;
+        d.kind[l] = 0;
+        if (size > 0 && res > 0 && res < (1u << 20)) {
+            if (cube <= size) d.kind[l] = 1;
+            else if ((size & (size - 1)) == 0) d.kind[l] = 2;
+        }
     }
     return d;
 }
@@ -48,6 +55,19 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t cx, uint32_t cy, uint32_
     }
     if (size < stride) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
     return index % size;
+}
+
+// Same index, without the runtime division in the common cases (the level kind is warp-uniform): a hashed level
+// with a power-of-two table masks; a dense level's index exceeds its table only for corners outside the grid.
+template <int KIND>
+__device__ __forceinline__ uint32_t grid_index_k(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t res, uint32_t size) {
+    if (KIND == 2) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);
+    if (KIND == 1) {
+        uint32_t index = cx + cy * res + cz * (res * res);
+        if (index >= size) index %= size;
+        return index;
+    }
+    return grid_index(cx, cy, cz, res, size);
 }
 
 struct Cell {
@@ -77,11 +97,12 @@ __device__ __forceinline__ float2 encode_level(const GridDev& g, int l, const fl
     const uint32_t res = g.res[l], size = g.size[l];
     const float2* base = table + g.offset[l];
     float2 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t idx = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
-        v[k] = __ldg(base + idx);
-    }
+    const uint32_t kind = g.kind[l];
+#define AVR_GATHER(KIND)                                                                                              \
+    _Pragma("unroll") for (int k = 0; k < 8; ++k)                                                                      \
+        v[k] = __ldg(base + grid_index_k<KIND>(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size));
+    if (kind == 2) { AVR_GATHER(2) } else if (kind == 1) { AVR_GATHER(1) } else { AVR_GATHER(0) }
+#undef AVR_GATHER
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -112,9 +133,12 @@ __device__ __forceinline__ void scatter_level(const GridDev& g, int l, float ux,
     // source registers until the LSU has taken them, so interleaving address math with REDs serialises on that
     uint32_t idx[8];
     long long q0[8], q1[8];
+    const uint32_t kind = g.kind[l];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        idx[k] = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
+        const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
+        idx[k] = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
+                                                                                 : grid_index(cx, cy, cz, res, size);
         const float w = corner_weight(c, k);
         q0[k] = __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc));
         q1[k] = __float2ll_rn(__fmul_rn(__fmul_rn(w, g1), sc));
@@ -135,9 +159,12 @@ __device__ __forceinline__ void scatter_level_f32(const GridDev& g, int l, float
     const Cell c = locate(g.scale[l], ux, uy, uz);
     const uint32_t res = g.res[l], size = g.size[l];
     float* base = grad + 2ull * g.offset[l];
+    const uint32_t kind = g.kind[l];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const uint32_t idx = grid_index(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size);
+        const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
+        const uint32_t idx = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
+                                                                                           : grid_index(cx, cy, cz, res, size);
         const float w = corner_weight(c, k);
         asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(base + 2ull * idx), "f"(__fmul_rn(w, g0)), "f"(__fmul_rn(w, g1))
                      : "memory");

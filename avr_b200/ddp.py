@@ -4,7 +4,14 @@ Replaces the DDP reducer of ``avr_runner_ddp.py:98,257`` (25 MB buckets + a used
 all-reduce per step because of ``find_unused_parameters=True``).  Receivers are independent, every rank
 holds a full replica, and the only exchange is the mean of the parameter gradients: all
 ``.grad`` tensors are views into one contiguous buffer, so the exchange is a single NCCL all-reduce
-(NVLS in-switch reduction on NVSwitch) issued on the compute stream right after the backward kernels.
+(NVLS in-switch reduction on NVSwitch) issued on the compute stream right after the backward kernels
+(``all_reduce_mean``) -- or, with ``attach(renderer)``, one all-reduce per parameter tensor issued from INSIDE the
+backward pass the moment that tensor's gradient is final: the signal network and the per-ray / per-receiver hash
+tables (2/3 of the bytes) are reduced while the density path and the sigma encoder are still back-propagating,
+and only the last table's exchange (38 of 120 MB at simu) is exposed.  Measured on 8 x B200 (``profiles/ddp_overlap_check.py``,
+``profiles/r1/ddp_overlap.md``): bit-identical gradients at 2 ranks, but NOT faster -- 15.17 -> 15.10 ms at 2 GPUs,
+15.44 -> 15.63 ms at 8: the persistent GEMM CTAs own every SM, so NCCL's kernels only make progress between them
+and nine small all-reduces cost more latency than one large one.  ``attach`` therefore stays opt-in.
 
 The reference's stock wrapper also works on ``avr_b200.AVRRender`` (it is an ordinary ``nn.Module``);
 this arena is the B200-first path used by ``bench.py``.
@@ -54,6 +61,38 @@ class GradArena:
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=False)
         self.flat.div_(world)
         return work
+
+
+    # -- exchange overlapped with the backward pass -------------------------------------------------------------
+    def attach(self, renderer, group=None):
+        """Reduce every gradient inside ``renderer``'s backward pass (tensor-core path) instead of after it.
+
+        The renderer announces ``(parameter, gradient)`` as soon as the producing kernels are enqueued; the all-reduce
+        (mean) of that tensor starts on NCCL's stream behind them and runs next to the remaining backward kernels.
+        ``done`` makes the compute stream wait for all of them before autograd accumulates the (already averaged)
+        gradients into ``.grad``.  Do not call ``all_reduce_mean`` as well."""
+        self._works = []
+
+        def ready(param, grad):
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+                return
+            if grad.is_cuda and dist.get_backend(group) == "nccl":
+                self._works.append(dist.all_reduce(grad, op=dist.ReduceOp.AVG, group=group, async_op=True))
+            else:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+                grad.div_(dist.get_world_size(group))
+
+        def done():
+            for w in self._works:
+                w.wait()                                         # stream-level wait, the host does not block
+            self._works.clear()
+
+        renderer.grad_ready_hook, renderer.grad_done_hook = ready, done
+        return self
+
+    @staticmethod
+    def detach(renderer):
+        renderer.grad_ready_hook = renderer.grad_done_hook = None
 
 
 def shard_receivers(n_receivers: int, rank: int, world: int):

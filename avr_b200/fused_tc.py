@@ -202,6 +202,41 @@ class FusedRenderTC(torch.autograd.Function):
         n_rows = geom.bs * geom.R * geom.S
         d_vals = tables["d"]
         grads = {}
+        # A gradient is announced as soon as the kernels that produce it are enqueued, so that a data-parallel caller can
+        # start its all-reduce while the rest of the backward pass runs (ddp.GradArena.attach): the signal network and
+        # the per-ray / per-receiver hash tables (2/3 of all gradient bytes) are final before the density path starts.
+        ready = plan.get("grad_ready")
+        index_of = {id(m): i for i, m in enumerate(mods)}
+
+        def announce(mod):
+            if ready is not None:
+                ready(index_of[id(mod)], grads[id(mod)])
+
+        grids = [m for (m, kind) in plan["x0"] + plan["tail"] if kind != "receiver_rows" and m.grid_grad == "deterministic"]
+        scratch = torch.empty(max(int(m.meta.total) * 2 for m in grids), dtype=torch.int64, device=dev) if grids else None
+
+        def scatter_segments(segments, d_buf):
+            """Hash-table gradients (scatter; mode per Encoding.grid_grad) and embedding-row gradients of one input block."""
+            col = 0
+            for mod, kind in segments:
+                wdt = mod.n_output_dims
+                if kind == "receiver_rows":
+                    extra_grads[("rows", mod.key)] = ops.rows_reduce(geom, d_buf, col, wdt, True)
+                    col += wdt
+                    continue
+                if kind == "point":
+                    acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch, mod.grid_grad)
+                    acc.observe(d_buf, col, wdt)
+                    acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col)
+                else:
+                    small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
+                    acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch, mod.grid_grad)
+                    acc.observe(small, 0, wdt)
+                    acc.add_points(ctx.small_in[kind], small)
+                grads[id(mod)] = acc.finalize()
+                announce(mod)
+                col += wdt
+
         ws_bytes = max(ops.umma_tn_workspace_bytes(o, i, n_rows) for n in (enc_net, dec_net, sig_net) for (o, i) in n.shapes)
         ws = torch.empty(max(4, ws_bytes // 4), device=dev)
 
@@ -235,6 +270,7 @@ class FusedRenderTC(torch.autograd.Function):
         sig_in, dec_in = B["sig_in"], B["dec_in"]
         g, wt_sig, _ = hidden_backward(sig_net, "sig", g, B["acts_sig"], B["bits_sig"], sig_in, g_sig)
         grads[id(sig_net)] = g_sig
+        announce(sig_net)
         d_feat = PlanePair.empty(n_rows, feat_dim, dev)
         wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
         if plan["sig_relu_feat"]:
@@ -245,6 +281,8 @@ class FusedRenderTC(torch.autograd.Function):
         d_tail = PlanePair.empty(n_rows, tail_w, dev)
         ops.umma_nt(g, wt0.row_window(feat_dim, tail_w), 0, d_tail)
         B["acts_sig"] = None
+        scatter_segments(plan["tail"], d_tail)
+        d_tail = None
 
         # ---- density path: ray weights -> sigma decoder ---------------------------------------------------
         d_dec_out = torch.zeros_like(B["dec_out"])
@@ -271,6 +309,8 @@ class FusedRenderTC(torch.autograd.Function):
             d_dec_tail = PlanePair.empty(n_rows, dec_net.in_pad - feat_dim, dev)
             ops.umma_nt(g, wt_dec[0].row_window(feat_dim, dec_net.in_pad - feat_dim), 0, d_dec_tail)
         grads[id(dec_net)] = g_dec
+        announce(dec_net)
+        scatter_segments(plan.get("dec_tail", []), d_dec_tail)
 
         # ---- sigma encoder -----------------------------------------------------------------------------------
         wt_enc = _weight_planes(enc_net, pmap[id(enc_net)], True, BWD_PLANES)
@@ -290,28 +330,11 @@ class FusedRenderTC(torch.autograd.Function):
         d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
         ops.umma_nt(g, wt_enc[0], 0, d_x0)
         grads[id(enc_net)] = g_enc
-
-        # ---- hash tables (scatter; mode per Encoding.grid_grad) ---------------------------------------------------
-        grids = [m for (m, kind) in plan["x0"] + plan["tail"] if kind != "receiver_rows" and m.grid_grad == "deterministic"]
-        scratch = torch.empty(max(int(m.meta.total) * 2 for m in grids), dtype=torch.int64, device=dev) if grids else None
-        for segments, d_buf in ((plan["x0"], d_x0), (plan["tail"], d_tail), (plan.get("dec_tail", []), d_dec_tail)):
-            col = 0
-            for mod, kind in segments:
-                wdt = mod.n_output_dims
-                if kind == "receiver_rows":
-                    extra_grads[("rows", mod.key)] = ops.rows_reduce(geom, d_buf, col, wdt, True)
-                    col += wdt
-                    continue
-                if kind == "point":
-                    acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch, mod.grid_grad)
-                    acc.observe(d_buf, col, wdt)
-                    acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col)
-                else:
-                    small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
-                    acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch, mod.grid_grad)
-                    acc.observe(small, 0, wdt)
-                    acc.add_points(ctx.small_in[kind], small)
-                grads[id(mod)] = acc.finalize()
-                col += wdt
+        announce(enc_net)
+        scatter_segments(plan["x0"], d_x0)
+        if ready is not None:
+            for k, r in enumerate(ctx.roles):
+                ready(len(mods) + k, extra_grads[tuple(r)])
+            plan["grad_done"]()
         ctx.bufs = None
         return (None,) * 8 + tuple(grads[id(m)] for m in mods) + tuple(extra_grads[tuple(r)] for r in ctx.roles)

@@ -62,6 +62,11 @@ class AVRRender(nn.Module):
                 if isinstance(m, Encoding):
                     m.grid_grad = grid_grad
         self._tables = {}
+        #: ``hook(parameter, gradient)`` called INSIDE the backward pass as soon as a parameter's gradient is final
+        #: (tensor-core path), and ``done()`` at its end -- installed by ``ddp.GradArena.attach`` to overlap the
+        #: gradient all-reduce with the rest of the backward kernels
+        self.grad_ready_hook = None
+        self.grad_done_hook = None
 
     # -- configuration -----------------------------------------------------------------------------
     def render_cfg(self) -> dict:
@@ -117,6 +122,10 @@ class AVRRender(nn.Module):
             if plan.get("extras") and self.dense != "tc":
                 raise NotImplementedError("channel embeddings are built on the tensor-core path only (dense='tc')")
             if self.dense == "tc":
+                if self.grad_ready_hook is not None:                           # ddp.GradArena.attach: overlapped all-reduce
+                    plan = dict(plan)
+                    plan["grad_ready"] = lambda i, g, _p=params: self.grad_ready_hook(_p[i], g)
+                    plan["grad_done"] = self.grad_done_hook or (lambda: None)
                 return FusedRenderTC.apply(plan, geom, tab.dev, ops.collapse_tspan(self.render_cfg()), rays_o,
                                            position_tx, dtx, dirs, *params)
             return FusedRenderFunction.apply(plan, geom, tab.dev, rays_o, position_tx, dtx, dirs, *params)

@@ -43,6 +43,11 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="simu")
     ap.add_argument("--bs", type=int, default=4, help="receivers per GPU per step")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: fwd+bwd (+ gradient all-reduce); infer: no_grad forward only (BASELINE configs[3])")
+    ap.add_argument("--overlap", action="store_true",
+                    help="per-tensor gradient all-reduces issued inside the backward pass (GradArena.attach) instead of "
+                         "one all-reduce of the flat arena after it; measured slower at 8 GPUs (DESIGN 7), off by default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -138,7 +143,9 @@ def run_reference(args, cfg):
 def workload_config(cfg, args, world):
     r = cfg["render"]
     R = r["n_azi"] * r["n_ele"] + 2
-    return {"workload": f"avr_{args.config}.yml render step (BASELINE configs[1]): fwd+bwd, {args.bs} receivers/GPU",
+    which = {"simu": 1, "raf_furnished": 2, "meshrir": 3, "real_exp_ch_emb_1": 4}.get(args.config, 1)
+    what = "fwd+bwd" if args.mode == "train" else "inference (no_grad forward)"
+    return {"workload": f"avr_{args.config}.yml render step (BASELINE configs[{which}]): {what}, {args.bs} receivers/GPU",
             "rays": R, "samples_per_ray": r["n_samples"], "ir_len": cfg["model"]["signal_output_dim"],
             "receivers_per_gpu": args.bs, "global_receivers": args.bs * world, "field": cfg["model_class"],
             "parallelism": f"dp{world}", "weights": "random init (hash tables N(0,0.1))",
@@ -219,6 +226,9 @@ def run_native(args, cfg):
     field = field.to(dev)
     ren = avr_b200.AVRRender(field, **cfg["render"], max_receivers_per_pass=args.bs)
     arena = avr_b200.GradArena(ren.parameters())
+    overlap = world > 1 and args.overlap
+    if overlap:
+        arena.attach(ren)
     complex_field = cfg["model_class"] != "AVRModel"
 
     rx_h, tx_h, dtx_h = synthetic_inputs(cfg["render"], args.bs, 100 + rank)
@@ -234,9 +244,14 @@ def run_native(args, cfg):
             dtx = dtx_h.to(dev, non_blocking=True) if complex_field else None
         else:
             rx, tx, dtx = rx_d, tx_d, (dtx_d if complex_field else None)
-        out = ren(rx, tx, dtx)
-        out.square().sum().backward()
-        arena.all_reduce_mean()
+        if args.mode == "infer":
+            with torch.no_grad():
+                out = ren(rx, tx, dtx)
+        else:
+            out = ren(rx, tx, dtx)
+            out.square().sum().backward()
+            if not overlap:
+                arena.all_reduce_mean()
         if host_io:
             out_h.copy_(out.detach(), non_blocking=True)
 
@@ -320,7 +335,7 @@ def run_native(args, cfg):
             v, dt, desc = time_cpu_oracle(cfg, steps=1, warmup=1, ray_div=(4, 2))
             cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC if args.mode == "train" else "rendered IRs/sec (inference)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, args, world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -328,7 +343,7 @@ def run_native(args, cfg):
                                               (cfg["render"]["n_azi"] * cfg["render"]["n_ele"] + 2) * 12),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": int(launches), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "grad_allreduce_bytes": int(arena.numel() * 4) if world > 1 else 0,
+            "grad_allreduce_bytes": int(arena.numel() * 4) if world > 1 and args.mode == "train" else 0,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -29,8 +29,20 @@ def _worker(rank, world, port, out_dir):
     mine = shard_receivers(8, rank, world)
     arena.zero_()
     lin(x[mine]).square().mean().backward()                  # per-rank mean over its local receivers
+    local = arena.flat.clone()
     arena.all_reduce_mean()
     torch.save(arena.flat.clone(), os.path.join(out_dir, f"g{rank}.pt"))
+    # the overlapped exchange (GradArena.attach): the renderer announces each gradient from inside its backward pass
+    class _Renderer:
+        grad_ready_hook = grad_done_hook = None
+    ren = _Renderer()
+    arena.attach(ren)
+    announced = local.clone()
+    ren.grad_ready_hook(lin.weight, announced)
+    ren.grad_done_hook()
+    torch.save(announced, os.path.join(out_dir, f"h{rank}.pt"))
+    avr_b200.GradArena.detach(ren)
+    assert ren.grad_ready_hook is None
     dist.destroy_process_group()
 
 
@@ -39,6 +51,7 @@ def test_two_rank_gradient_mean_equals_single_process(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     g0, g1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
     assert torch.equal(g0, g1)
+    assert torch.equal(torch.load(tmp_path / "h0.pt"), g0) and torch.equal(torch.load(tmp_path / "h1.pt"), g0)
     torch.manual_seed(0)
     lin = torch.nn.Linear(6, 4, bias=False)
     x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
