@@ -163,30 +163,35 @@ __device__ __forceinline__ void store_planes8(__nv_bfloat16* base, long long pla
 constexpr int EPI_COLS = 32;                              // columns per staged chunk (64-byte rows, SWIZZLE_64B)
 constexpr uint32_t EPI_PLANE_BYTES = 32 * EPI_COLS * 2;   // 32 rows x 64 B = 2 KB per plane per warp
 
-// Split 32 fp32 values of one row into nplanes bf16 planes and write them into the warp's staging tiles
-// ([plane][32 rows][64 B], 64-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)).
-__device__ __forceinline__ void stage_planes32(uint32_t stage, int lane, const float* v, bool relu, int nplanes) {
+// Split 32 fp32 values of one row into nplanes bf16 planes (packed pairs, registers only) ...
+__device__ __forceinline__ void pack_planes32(const float* v, bool relu, int nplanes, uint32_t (&h)[16], uint32_t (&m)[16],
+                                              uint32_t (&l)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        // packed conversions (cvt.rn.bf16x2.f32): one instruction per pair and per plane; the epilogue is bound by the
+        // issue rate of its warps, so instruction count is what matters here
+        h[i] = cvt_bf16x2(a, b);
+        const float ar = a - bf_lo(h[i]), br = b - bf_hi(h[i]);
+        m[i] = cvt_bf16x2(ar, br);
+        l[i] = nplanes == 3 ? cvt_bf16x2(ar - bf_lo(m[i]), br - bf_hi(m[i])) : 0u;
+    }
+}
+// ... and write them into the warp's staging tiles ([plane][32 rows][64 B], 64-byte swizzle: 16-byte chunk c of row r
+// lives at chunk c ^ ((r >> 1) & 3)).  Kept apart so that the conversions run BEFORE the warp waits for the previous
+// chunk's bulk store to release the staging tiles.
+__device__ __forceinline__ void stage_packed32(uint32_t stage, int lane, int nplanes, const uint32_t (&h)[16],
+                                               const uint32_t (&m)[16], const uint32_t (&l)[16]) {
     const uint32_t row_base = stage + (uint32_t)lane * 64u;
     const uint32_t sw = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint32_t h[4], m[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float a = v[8 * q + 2 * i], b = v[8 * q + 2 * i + 1];
-            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            // packed conversions (cvt.rn.bf16x2.f32): one instruction per pair and per plane; the epilogue is bound by the
-            // issue rate of its four warps, so instruction count is what matters here
-            h[i] = cvt_bf16x2(a, b);
-            const float ar = a - bf_lo(h[i]), br = b - bf_hi(h[i]);
-            m[i] = cvt_bf16x2(ar, br);
-            l[i] = nplanes == 3 ? cvt_bf16x2(ar - bf_lo(m[i]), br - bf_hi(m[i])) : 0u;
-        }
         const uint32_t off = row_base + (((uint32_t)q ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off + EPI_PLANE_BYTES), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off), "r"(h[4 * q]), "r"(h[4 * q + 1]), "r"(h[4 * q + 2]), "r"(h[4 * q + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off + EPI_PLANE_BYTES), "r"(m[4 * q]), "r"(m[4 * q + 1]), "r"(m[4 * q + 2]), "r"(m[4 * q + 3]) : "memory");
         if (nplanes == 3)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off + 2 * EPI_PLANE_BYTES), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(off + 2 * EPI_PLANE_BYTES), "r"(l[4 * q]), "r"(l[4 * q + 1]), "r"(l[4 * q + 2]), "r"(l[4 * q + 3]) : "memory");
     }
 }
 
@@ -529,9 +534,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     const int n_out = (p.flags & UF_DUAL_RELU) ? 2 : 1;
                     for (int o = 0; o < n_out; ++o) {
+                        uint32_t ph[16], pm[16], pl[16];
+                        pack_planes32(v, o == 1 || (p.flags & UF_RELU), p.nc, ph, pm, pl);
                         if (lane == 0 && !(p.flags & UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
                         __syncwarp();
-                        if (!(p.flags & UF_DEBUG_NOSTAGE)) stage_planes32(stage, lane, v, o == 1 || (p.flags & UF_RELU), p.nc);
+                        if (!(p.flags & UF_DEBUG_NOSTAGE)) stage_packed32(stage, lane, p.nc, ph, pm, pl);
                         if (!(p.flags & UF_DEBUG_NOFENCE)) fence_async_smem();
                         __syncwarp();
                         if (lane == 0 && !(p.flags & UF_DEBUG_NOSTORE)) {
