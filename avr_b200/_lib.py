@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libavr_b200
 GEMM_RELU, GEMM_ACCUM, GEMM_MASK, GEMM_RELU_A, GEMM_RELU_B = 1, 2, 4, 8, 16
 K_CONTIG, I_CONTIG = 0, 1
 UMMA_RELU, UMMA_ACCUM, UMMA_MASK, UMMA_OUT_F32, UMMA_DUAL_RELU, UMMA_BITS, UMMA_BIAS = 1, 2, 4, 8, 16, 32, 64
+UMMA_DUAL_COPY = 2048
 
 
 class AVRLibraryError(RuntimeError):
@@ -56,17 +57,17 @@ SIGNATURES = {
     "avr_planes_split": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.c_int, _P, _I64,
-                                   _I64, C.c_int, _P, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _I64,
+                                   _I64, C.c_int, _P, _I64, _I64, C.c_int, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _I64,
                                    _P, _I64, _P, C.c_float, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt_splitk_slices": (_I64, [_I64]),
     "avr_umma_gemm_tn_workspace_bytes": (_I64, [_I64, _I64, _I64]),
-    "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P, _I64,
-                                   C.c_int, _P]),
+    "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _P, _I64, C.c_int,
+                                   _P, _I64, C.c_int, _P]),
     "avr_delay_sort": (C.c_int, [_G, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_collapse_prefix_bytes": (_I64, [_G, _I32, _I32]),
     "avr_collapse_suffix_bytes": (_I64, [_G, _I32, _I32]),
-    "avr_collapse_fwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _I32, _P, _I64, _P, C.c_int, _P]),
-    "avr_collapse_bwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _I64, _P, _I64, _I64,
+    "avr_collapse_fwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _P, _I64, _P, C.c_int, _P]),
+    "avr_collapse_bwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _I64, _P, _I64, _I64,
                                    _P, _P, _I64, C.c_int, C.c_int, _P]),
     "avr_rows_broadcast": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I64, _I64, _I32, _I32, C.c_int, _P]),
     "avr_rows_block_sum": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, C.c_int, _P]),

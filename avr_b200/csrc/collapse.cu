@@ -31,15 +31,15 @@
 namespace avr {
 
 struct Planes {
-    const __nv_bfloat16* p;
+    const __nv_bfloat16* p;     // 16-bit planes: bf16 (hi, mid[, lo]) or an fp16 (hi, lo'*2^11) pair
     long long ld, plane;
+    bool f16;
 };
 
-__device__ __forceinline__ void unpack4(uint2 hi, uint2 lo, float (&x)[4]) {
-    x[0] = __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
-    x[1] = __uint_as_float(hi.x & 0xFFFF0000u) + __uint_as_float(lo.x & 0xFFFF0000u);
-    x[2] = __uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16);
-    x[3] = __uint_as_float(hi.y & 0xFFFF0000u) + __uint_as_float(lo.y & 0xFFFF0000u);
+// four values from planes 0 and 1 (the first 16 bits of a bf16 set, all 24 of an fp16 pair)
+__device__ __forceinline__ void unpack4(bool f16, uint2 hi, uint2 lo, float (&x)[4]) {
+    const float2 a = planes_unpack2(f16, hi.x, lo.x), b = planes_unpack2(f16, hi.y, lo.y);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
 }
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b, uint32_t& lo_out) {
     const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
@@ -191,7 +191,7 @@ prefix_walk_kernel(const Geom geo, const Planes act, int width, const int* __res
                 asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "r"(src));
                 asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "r"(src + 8));
                 float x[4];
-                unpack4(hi, lo, x);
+                unpack4(act.f16, hi, lo, x);
                 const float wk = l_w[k];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[i] = fmaf(wk, x[i], acc[i]);
@@ -333,7 +333,7 @@ ray_backward_kernel(const Geom geo, const Planes act, int width, const int* __re
                 const __nv_bfloat16* q = act.p + row * act.ld + c;
                 const uint2 hi = __ldg(reinterpret_cast<const uint2*>(q)), lo = __ldg(reinterpret_cast<const uint2*>(q + act.plane));
                 float x[4];
-                unpack4(hi, lo, x);
+                unpack4(act.f16, hi, lo, x);
                 dot = x[0] * g.x + x[1] * g.y + x[2] * g.z + x[3] * g.w;
                 uint32_t l0, l1;
                 const uint32_t h0 = pack_bf2(x[0] > 0.f ? wk * g.x : 0.f, x[1] > 0.f ? wk * g.y : 0.f, l0);
@@ -393,13 +393,14 @@ AVR_API int64_t avr_collapse_suffix_bytes(const avr_render_geom* geom, int32_t w
 // y[bs,S,T] and the prefix workspace (kept by the caller for the backward pass).
 // tspan: static bound on (max delay - min delay) within one (b,s); a violation poisons the results with NaN.
 AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             int32_t act_kind, int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
                              const float* w_out, int64_t ldw, int32_t tspan, void* prefix_ws, int64_t prefix_bytes, float* y,
                              int device, void* stream) {
     AVR_REQUIRE(geom && order && sdelay && sw && w_out && y && prefix_ws, "null pointer");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     if (int rc = check_collapse(geo, width, act_planes, ld_act, act_plane)) return rc;
+    AVR_REQUIRE(planes_kind_ok(act_kind), "unknown plane-set kind");
     AVR_REQUIRE(ldw % 4 == 0 && aligned16(w_out) && aligned16(prefix_ws), "W_out / workspace must be 16-byte aligned");
     AVR_REQUIRE(tspan > 0 && prefix_bytes >= avr_collapse_prefix_bytes(geom, width, tspan), "prefix workspace too small");
     const int cells = geo.bs * geo.S;
@@ -409,7 +410,7 @@ AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes
     const int threads = ((width / 4 + 31) / 32) * 32;
     const size_t smem = (((size_t)geo.R * 12 + 15) & ~(size_t)15) + (size_t)PW_GROUP * PW_NGROUPS * threads * 16;
     AVR_CUDA(cudaFuncSetAttribute(prefix_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane};
+    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane, planes_f16(act_kind)};
     prefix_walk_kernel<<<cells, threads, smem, st>>>(geo, act, width, order, sdelay, sw, ws, tspan);
     AVR_LAUNCH_CHECK();
     const int t_chunks = 8;
@@ -421,7 +422,7 @@ AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes
 
 // d_act (plane pair, gradient w.r.t. the pre-activation), d_w[bs,R,S] and d_W_out[T,width] (+)=
 AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             int32_t act_kind, int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
                              const float* w_out, int64_t ldw, const float* d_y, int32_t tspan, const void* prefix_ws,
                              void* suffix_ws, int64_t suffix_bytes, void* d_act_planes, int64_t ld_d, int64_t d_plane,
                              float* d_w, float* d_wout, int64_t ld_dw, int accumulate, int device, void* stream) {
@@ -430,6 +431,7 @@ AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     if (int rc = check_collapse(geo, width, act_planes, ld_act, act_plane)) return rc;
+    AVR_REQUIRE(planes_kind_ok(act_kind), "unknown plane-set kind");
     AVR_REQUIRE(ldw % 4 == 0 && ld_dw % 4 == 0 && aligned16(w_out) && aligned16(d_wout) && aligned16(suffix_ws), "16-byte alignment");
     AVR_REQUIRE(ld_d % 4 == 0 && d_plane % 4 == 0 && (reinterpret_cast<uintptr_t>(d_act_planes) & 7u) == 0, "d_act misaligned");
     AVR_REQUIRE(tspan > 0 && suffix_bytes >= avr_collapse_suffix_bytes(geom, width, tspan), "suffix workspace too small");
@@ -445,7 +447,7 @@ AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes
     AVR_CUDA(cudaFuncSetAttribute(suffix_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     suffix_walk_kernel<<<dim3(cells, (unsigned)ceil_div(width, 128)), 32, smem, st>>>(geo, width, ws.range, tspan, w_out, ldw, d_y, gs);
     AVR_LAUNCH_CHECK();
-    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane};
+    const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane, planes_f16(act_kind)};
     const int rays_per_block = 4 * RB_RAYS;
     ray_backward_kernel<<<dim3(cells, (unsigned)ceil_div(geo.R, rays_per_block)), 128, 0, st>>>(
         geo, act, width, order, sdelay, sw, ws.range, tspan, gs, (__nv_bfloat16*)d_act_planes, ld_d, d_plane, d_w);

@@ -329,17 +329,8 @@ __global__ void rows_broadcast_kernel(const Geom geo, const float* __restrict__ 
     const int64_t row = per_receiver ? n / ((int64_t)geo.R * geo.S) : (n / geo.S) % geo.R;
     const float v = __ldg(src + row * w + c);
     const int64_t o = n * ld_dst + col0 + c;
-    if (dst_plane == 0) {
-        reinterpret_cast<float*>(dst_v)[o] = v;
-    } else {
-        __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(dst_v);
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(hi);
-        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-        db[o] = hi;
-        db[o + dst_plane] = mid;
-        if (dst_np == 3) db[o + 2 * dst_plane] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-    }
+    if (dst_plane == 0) reinterpret_cast<float*>(dst_v)[o] = v;
+    else planes_store(dst_v, o, dst_plane, dst_np, v);
 }
 
 // plane-set destination, 8 columns (one 16-byte store per plane) per thread
@@ -358,19 +349,11 @@ __global__ void rows_broadcast_planes8_kernel(const Geom geo, const float* __res
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t h[4], m[4], l[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-        const float r0 = v[2 * k] - __low2float(hh), r1 = v[2 * k + 1] - __high2float(hh);
-        const __nv_bfloat162 mm = __floats2bfloat162_rn(r0, r1);
-        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0 - __low2float(mm), r1 - __high2float(mm));
-        h[k] = *reinterpret_cast<const uint32_t*>(&hh);
-        m[k] = *reinterpret_cast<const uint32_t*>(&mm);
-        l[k] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
+    for (int k = 0; k < 4; ++k) planes_pack2(dst_np, v[2 * k], v[2 * k + 1], h[k], m[k], l[k]);
     __nv_bfloat16* o = db + n * ld_dst + col0 + 8 * g;
     *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(o + dst_plane) = make_uint4(m[0], m[1], m[2], m[3]);
-    if (dst_np == 3) *reinterpret_cast<uint4*>(o + 2 * dst_plane) = make_uint4(l[0], l[1], l[2], l[3]);
+    if (planes_count(dst_np) == 3) *reinterpret_cast<uint4*>(o + 2 * dst_plane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // plane-set source, 8 columns (one 16-byte load per plane) per thread; same partial layout and a fixed summation order

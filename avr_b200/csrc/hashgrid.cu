@@ -228,17 +228,8 @@ encode_fwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
         if (n0 + pp >= n_pts) continue;
         const float v = tile[pp * Wp + c];
         const int64_t o = (n0 + pp) * ld_out + col0 + c;
-        if (out_plane == 0) {
-            reinterpret_cast<float*>(out_v)[o] = v;
-        } else {                                            // error-compensated bf16 plane pair (tensor-core operand)
-            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_v);
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const float r1 = v - __bfloat162float(hi);
-            const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-            ob[o] = hi;
-            ob[o + out_plane] = mid;
-            if (out_np == 3) ob[o + 2 * out_plane] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-        }
+        if (out_plane == 0) reinterpret_cast<float*>(out_v)[o] = v;
+        else planes_store(out_v, o, out_plane, out_np, v);  // tensor-core operand: plane set of kind out_np
     }
 }
 
@@ -402,7 +393,7 @@ static int encode_fwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
                              int32_t col0, int32_t n_ones, int32_t* delay, void* stream) {
     if (int rc = check_grid(grid)) return rc;
     AVR_REQUIRE(table && out, "null table/out");
-    AVR_REQUIRE(out_plane == 0 || out_np == 2 || out_np == 3, "plane count must be 2 or 3");
+    AVR_REQUIRE(out_plane == 0 || planes_kind_ok(out_np), "unknown plane-set kind");
     AVR_REQUIRE(n_ones >= 0 && col0 >= 0 && ld_out >= col0 + 2 * grid->n_levels + n_ones, "bad output window");
     AVR_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7u) == 0, "table must be 8-byte aligned");
     if (n_pts == 0) return AVR_OK;

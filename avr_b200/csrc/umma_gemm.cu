@@ -26,7 +26,7 @@
 
 namespace avr {
 
-enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32, UF_BIAS = 64, UF_DEBUG_NOWAIT = 128, UF_DEBUG_NOSTORE = 256, UF_DEBUG_NOSTAGE = 512, UF_DEBUG_NOFENCE = 1024 };
+enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32, UF_BIAS = 64, UF_DUAL_COPY = 2048, UF_DEBUG_NOWAIT = 128, UF_DEBUG_NOSTORE = 256, UF_DEBUG_NOSTAGE = 512, UF_DEBUG_NOFENCE = 1024 };
 
 struct UmmaParams {
     int M, N, K;            // K-major: rows, cols, reduction.  MN-major: A extent, B extent, reduction (points)
@@ -35,6 +35,9 @@ struct UmmaParams {
     int stages, tmem_cols;
     int dual_acc;           // six-product mode: the five small products go to a second TMEM accumulator (see the MMA issuer)
     int na, nb, nc;         // planes used of A / B (2: hi,mid  3: hi,mid,lo) and written to C
+    int fa, fb, kc, kc2;    // A / B planes are fp16 (hi, lo'*2^11) pairs; plane-set kinds of C and C2 (AVR_PLANES_*)
+    int mode;               // product schedule, see the MMA issuer
+    float small_scale;      // factor of the small-products accumulator in the epilogue (2^-11 with an fp16 operand)
     int b_resident, nkb;    // K-major, single column tile, short K: the whole B operand stays in shared memory
     int flags;
     __nv_bfloat16* c; long long ldc, c_plane;          // plane-pair output
@@ -132,12 +135,6 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-// two fp32 -> packed bf16x2 (round to nearest even); low half = first argument
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -164,19 +161,22 @@ constexpr int EPI_COLS = 32;                              // columns per staged 
 constexpr uint32_t EPI_PLANE_BYTES = 32 * EPI_COLS * 2;   // 32 rows x 64 B = 2 KB per plane per warp
 
 // Split 32 fp32 values of one row into nplanes bf16 planes (packed pairs, registers only) ...
-__device__ __forceinline__ void pack_planes32(const float* v, bool relu, int nplanes, uint32_t (&h)[16], uint32_t (&m)[16],
-                                              uint32_t (&l)[16]) {
+template <int KIND>
+__device__ __forceinline__ void pack_planes32_k(const float* v, bool relu, uint32_t (&h)[16], uint32_t (&m)[16], uint32_t (&l)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float a = v[2 * i], b = v[2 * i + 1];
         if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        // packed conversions (cvt.rn.bf16x2.f32): one instruction per pair and per plane; the epilogue is bound by the
-        // issue rate of its warps, so instruction count is what matters here
-        h[i] = cvt_bf16x2(a, b);
-        const float ar = a - bf_lo(h[i]), br = b - bf_hi(h[i]);
-        m[i] = cvt_bf16x2(ar, br);
-        l[i] = nplanes == 3 ? cvt_bf16x2(ar - bf_lo(m[i]), br - bf_hi(m[i])) : 0u;
+        // packed conversions (cvt.rn.{bf16x2,f16x2}.f32): one instruction per pair and per plane; the epilogue is bound
+        // by the issue rate of its warps, so instruction count is what matters here
+        planes_pack2(KIND, a, b, h[i], m[i], l[i]);
     }
+}
+__device__ __forceinline__ void pack_planes32(const float* v, bool relu, int kind, uint32_t (&h)[16], uint32_t (&m)[16],
+                                              uint32_t (&l)[16]) {
+    if (kind == AVR_PLANES_F16x2) pack_planes32_k<AVR_PLANES_F16x2>(v, relu, h, m, l);          // one branch per chunk,
+    else if (kind == AVR_PLANES_BF16x3) pack_planes32_k<AVR_PLANES_BF16x3>(v, relu, h, m, l);   // straight-line bodies
+    else pack_planes32_k<AVR_PLANES_BF16x2>(v, relu, h, m, l);
 }
 // ... and write them into the warp's staging tiles ([plane][32 rows][64 B], 64-byte swizzle: 16-byte chunk c of row r
 // lives at chunk c ^ ((r >> 1) & 3)).  Kept apart so that the conversions run BEFORE the warp waits for the previous
@@ -231,7 +231,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
     const uint32_t a_tile_bytes = (uint32_t)p.na * A_PLANE_BYTES;
     const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)p.nb * (uint32_t)bn_rows * 128u : (uint32_t)p.nb * b_plane_bytes;
-    const uint32_t mn_blk = (uint32_t)p.na * 8192u;       // MN-major: one TMA box = 64 (mn) x 64 (k) x planes (na == nb)
+    const uint32_t mn_blk_a = (uint32_t)p.na * 8192u;     // MN-major: one TMA box = 64 (mn) x 64 (k) x planes
+    const uint32_t mn_blk_b = (uint32_t)p.nb * 8192u;
     const bool bres = !MN_MAJOR && p.b_resident;
     const uint32_t bres_bytes = bres ? (uint32_t)p.nkb * b_tile_bytes : 0u;    // resident B: [k-block][plane][rows][128 B]
     const uint32_t stage_bytes = bres ? a_tile_bytes : a_tile_bytes + b_tile_bytes;
@@ -287,8 +288,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (!bres) tma_load_3d(sb, &tmB, full, k0, n0, 0);
                     } else {
                         tma_load_3d(sa, &tmA, full, m0, k0, 0);
-                        tma_load_3d(sa + mn_blk, &tmA, full, m0 + 64, k0, 0);
-                        for (int i = 0; i < bn_rows / 64; ++i) tma_load_3d(sb + mn_blk * i, &tmB, full, n0 + 64 * i, k0, 0);
+                        tma_load_3d(sa + mn_blk_a, &tmA, full, m0 + 64, k0, 0);
+                        for (int i = 0; i < bn_rows / 64; ++i) tma_load_3d(sb + mn_blk_b * i, &tmB, full, n0 + 64 * i, k0, 0);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -297,7 +298,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===================================== MMA issuer
         if (lane == 0) {
-            uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+            // instruction descriptor: fp32 accumulate, A / B element formats (0 = f16, 1 = bf16), N, M
+            uint32_t idesc = (1u << 4) | ((p.fa ? 0u : 1u) << 7) | ((p.fb ? 0u : 1u) << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(UM >> 4) << 24);
             if (MN_MAJOR) idesc |= (1u << 15) | (1u << 16);
             int stage = 0, iter = 0;
             uint32_t phase = 0;
@@ -313,7 +316,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // accumulator whose truncations are 2^-8 smaller, and the epilogue adds the two in fp32.
                 const uint32_t d_main = tmem_base + (uint32_t)(acc * p.BN * (p.dual_acc ? 2 : 1));
                 const uint32_t d_small = p.dual_acc ? d_main + (uint32_t)p.BN : d_main;
-                uint32_t acc_small = 0, acc_main = 0;
+                uint32_t acc_main = 0u, acc_small = 0u;                           // "accumulate" flags (one accumulator when !dual_acc)
+                const uint32_t shared_acc = p.dual_acc ? 0u : 0xffffffffu;
                 for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -323,40 +327,34 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < UBK / 16; ++j) {
                         if (j >= k_steps) break;
-                        uint64_t a_hi, a_lo, b_hi, b_lo, a_l3 = 0, b_l3 = 0;
-                        const bool six = p.na == 3 && p.nb == 3;
-                        if (!MN_MAJOR) {
-                            a_hi = smem_desc(sa + 32 * j, 16, 1024);
-                            a_lo = smem_desc(sa + A_PLANE_BYTES + 32 * j, 16, 1024);
-                            b_hi = smem_desc(sb + 32 * j, 16, 1024);
-                            b_lo = smem_desc(sb + b_plane_bytes + 32 * j, 16, 1024);
-                            if (six) {
-                                a_l3 = smem_desc(sa + 2 * A_PLANE_BYTES + 32 * j, 16, 1024);
-                                b_l3 = smem_desc(sb + 2 * b_plane_bytes + 32 * j, 16, 1024);
-                            }
-                        } else {
-                            a_hi = smem_desc(sa + 2048 * j, mn_blk, 1024);
-                            a_lo = smem_desc(sa + 8192 + 2048 * j, mn_blk, 1024);
-                            b_hi = smem_desc(sb + 2048 * j, mn_blk, 1024);
-                            b_lo = smem_desc(sb + 8192 + 2048 * j, mn_blk, 1024);
-                            if (six) {
-                                a_l3 = smem_desc(sa + 16384 + 2048 * j, mn_blk, 1024);
-                                b_l3 = smem_desc(sb + 16384 + 2048 * j, mn_blk, 1024);
+                        uint64_t da[3] = {0, 0, 0}, db[3] = {0, 0, 0};              // descriptors of planes 0 (hi), 1, 2
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            if (!MN_MAJOR) {
+                                if (q < p.na) da[q] = smem_desc(sa + q * A_PLANE_BYTES + 32 * j, 16, 1024);
+                                if (q < p.nb) db[q] = smem_desc(sb + q * b_plane_bytes + 32 * j, 16, 1024);
+                            } else {
+                                if (q < p.na) da[q] = smem_desc(sa + q * 8192 + 2048 * j, mn_blk_a, 1024);
+                                if (q < p.nb) db[q] = smem_desc(sb + q * 8192 + 2048 * j, mn_blk_b, 1024);
                             }
                         }
-                        if (six) {
-                            // 24-bit operands: six products, smallest first (fp32-grade pre-activations, so that ReLU
-                            // decisions agree with an fp32 evaluation; the ill-conditioned sums of the density path)
-                            umma_bf16(d_small, a_l3, b_hi, idesc, acc_small);
-                            umma_bf16(d_small, a_hi, b_l3, idesc, 1u);
-                            umma_bf16(d_small, a_lo, b_lo, idesc, 1u);
-                            acc_small = 1u;
+#define AVR_SMALL(I, J) { umma_bf16(d_small, da[I], db[J], idesc, acc_small | (acc_main & shared_acc)); acc_small = 1u; }
+#define AVR_MAIN(I, J) { umma_bf16(d_main, da[I], db[J], idesc, acc_main | (acc_small & shared_acc)); acc_main = 1u; }
+                        // Product schedules, smallest terms first.  With fp16 pairs the products that involve a lo' plane
+                        // carry a factor 2^11 and MUST go to the small accumulator (scaled back in the epilogue).  A and B
+                        // share one element format: tcgen05.mma raises an illegal-instruction fault on a bf16 x f16 mix.
+                        switch (p.mode) {
+                        case 1:     // bf16x3 . bf16x3: six products (fp32-grade pre-activations / ill-conditioned sums)
+                            AVR_SMALL(2, 0) AVR_SMALL(0, 2) AVR_SMALL(1, 1)
+                            // fall through
+                        case 0:     // bf16x2 . bf16x2: three products (16 bits; gradients enter linearly)
+                        case 2:     // f16x2 . f16x2: three products, 24 bits: hi*lo' + lo'*hi scaled, hi*hi
+                        default:
+                            AVR_SMALL(1, 0) AVR_SMALL(0, 1) AVR_MAIN(0, 0)
+                            break;
                         }
-                        umma_bf16(d_small, a_lo, b_hi, idesc, acc_small);      // small terms first
-                        umma_bf16(d_small, a_hi, b_lo, idesc, 1u);
-                        acc_small = 1u;
-                        umma_bf16(d_main, a_hi, b_hi, idesc, p.dual_acc ? acc_main : 1u);
-                        acc_main = 1u;
+#undef AVR_SMALL
+#undef AVR_MAIN
                     }
                     umma_commit(bar_empty + 8 * stage);                          // frees the stage when the MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -423,7 +421,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         float u[16];
                         tmem_ld16(taddr + p.BN + c0, u);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += u[i];
+                        for (int i = 0; i < 16; ++i) v[i] = fmaf(u[i], p.small_scale, v[i]);
                     }
                     if (!row_ok) continue;
                     if (!MN_MAJOR && p.near_list) near_zero_guard<16>(p, v, row, row_ok, n0 + c0);
@@ -466,11 +464,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (p.dual_acc) {                                       // + the small-products accumulator
                             tmem_ld16(taddr + p.BN + c0, t0);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] += t0[i];
+                            for (int i = 0; i < 16; ++i) v[i] = fmaf(t0[i], p.small_scale, v[i]);
                             if (c0 + 16 < p.BN) {
                                 tmem_ld16(taddr + p.BN + c0 + 16, t1);
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) v[16 + i] += t1[i];
+                                for (int i = 0; i < 16; ++i) v[16 + i] = fmaf(t1[i], p.small_scale, v[16 + i]);
                             }
                         }
                     }
@@ -532,19 +530,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                     }
-                    const int n_out = (p.flags & UF_DUAL_RELU) ? 2 : 1;
+                    // second output: max(out, 0) next to the raw values (DUAL_RELU), or the same values as a plane set of
+                    // another kind (DUAL_COPY: fp16 pair for the next forward layer + bf16 pair for the weight gradient)
+                    const int n_out = (p.flags & (UF_DUAL_RELU | UF_DUAL_COPY)) ? 2 : 1;
                     for (int o = 0; o < n_out; ++o) {
                         uint32_t ph[16], pm[16], pl[16];
-                        pack_planes32(v, o == 1 || (p.flags & UF_RELU), p.nc, ph, pm, pl);
+                        const int kind_o = o == 0 ? p.kc : p.kc2;
+                        const int n_o = planes_count(kind_o);
+                        pack_planes32(v, (o == 1 && (p.flags & UF_DUAL_RELU)) || (p.flags & UF_RELU), kind_o, ph, pm, pl);
                         if (lane == 0 && !(p.flags & UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
                         __syncwarp();
-                        if (!(p.flags & UF_DEBUG_NOSTAGE)) stage_packed32(stage, lane, p.nc, ph, pm, pl);
+                        if (!(p.flags & UF_DEBUG_NOSTAGE)) stage_packed32(stage, lane, n_o, ph, pm, pl);
                         if (!(p.flags & UF_DEBUG_NOFENCE)) fence_async_smem();
                         __syncwarp();
                         if (lane == 0 && !(p.flags & UF_DEBUG_NOSTORE)) {
                             const CUtensorMap* map = o == 0 ? &tmC : &tmC2;
-                            for (int pl = 0; pl < p.nc; ++pl)
-                                tma_store_3d(map, stage + pl * EPI_PLANE_BYTES, n0 + c0, m0 + lane_grp * 32, pl);
+                            for (int q = 0; q < n_o; ++q)
+                                tma_store_3d(map, stage + q * EPI_PLANE_BYTES, n0 + c0, m0 + lane_grp * 32, q);
                             tma_store_commit();
                         }
                     }
@@ -619,31 +621,24 @@ __global__ void __launch_bounds__(256) umma_fixup_kernel(const UmmaParams p) {
     }
 }
 
-// fp32 [rows, cols] (ld) -> bf16 plane pair [2][rows][ldp]; optionally transposed (out[c][r] = in[r][c])
+// fp32 [rows, cols] (ld) -> plane set [n][rows][ldp] of kind `kind`; optionally transposed (out[c][r] = in[r][c])
 __global__ void planes_split_kernel(const float* __restrict__ x, long long rows, long long cols, long long ld,
-                                    __nv_bfloat16* __restrict__ out, long long ldp, long long plane, int nplanes,
+                                    void* __restrict__ out, long long ldp, long long plane, int kind,
                                     int transpose, int relu) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const long long r = i / cols, c = i - r * cols;
     float v = x[r * ld + c];
     if (relu) v = fmaxf(v, 0.f);
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    const long long o = transpose ? c * ldp + r : r * ldp + c;
-    out[o] = hi;
-    out[o + plane] = lo;
-    if (nplanes == 3) out[o + 2 * plane] = __float2bfloat16_rn((v - __bfloat162float(hi)) - __bfloat162float(lo));
+    planes_store(out, transpose ? c * ldp + r : r * ldp + c, plane, kind, v);
 }
 
-__global__ void planes_merge_kernel(const __nv_bfloat16* __restrict__ in, long long rows, long long cols, long long ldp,
-                                    long long plane, int nplanes, float* __restrict__ out, long long ld) {
+__global__ void planes_merge_kernel(const void* __restrict__ in, long long rows, long long cols, long long ldp,
+                                    long long plane, int kind, float* __restrict__ out, long long ld) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const long long r = i / cols, c = i - r * cols;
-    float tail = __bfloat162float(in[r * ldp + c + plane]);
-    if (nplanes == 3) tail += __bfloat162float(in[r * ldp + c + 2 * plane]);
-    out[r * ld + c] = __bfloat162float(in[r * ldp + c]) + tail;
+    out[r * ld + c] = planes_load(in, r * ldp + c, plane, kind);
 }
 
 // dW[m, n] (+)= sum over splits of partial[split][m][n].  One warp per float4 of the output: lane l adds the
@@ -747,11 +742,11 @@ extern "C" {
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
                              int64_t plane_stride, int nplanes, int transpose, int relu, int device, void* stream) {
     AVR_REQUIRE(planes && (x || rows * cols == 0), "null pointer");
-    AVR_REQUIRE(nplanes == 2 || nplanes == 3, "nplanes must be 2 or 3");
+    AVR_REQUIRE(planes_kind_ok(nplanes), "unknown plane-set kind");
     AVR_ENTER(device);
     if (rows * cols == 0) return AVR_OK;
     planes_split_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, rows, cols, ld, (__nv_bfloat16*)planes, ldp, plane_stride, nplanes, transpose, relu);
+        x, rows, cols, ld, planes, ldp, plane_stride, nplanes, transpose, relu);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
@@ -759,11 +754,11 @@ AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t
 AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride, int nplanes,
                              float* out, int64_t ld, int device, void* stream) {
     AVR_REQUIRE(planes && out, "null pointer");
-    AVR_REQUIRE(nplanes == 2 || nplanes == 3, "nplanes must be 2 or 3");
+    AVR_REQUIRE(planes_kind_ok(nplanes), "unknown plane-set kind");
     AVR_ENTER(device);
     if (rows * cols == 0) return AVR_OK;
     planes_merge_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)planes, rows, cols, ldp, plane_stride, nplanes, out, ld);
+        planes, rows, cols, ldp, plane_stride, nplanes, out, ld);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }
@@ -775,7 +770,7 @@ AVR_API int64_t avr_umma_gemm_nt_splitk_slices(int64_t K) { return K <= 512 ? 1 
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
-                             int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
+                             int64_t c2_plane, int c2_nplanes, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
                              int64_t ldbits, const float* bias_ray, int64_t ld_bias_ray, const float* bias_rcv,
                              int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32,
                              uint32_t* near_list, int64_t near_cap, uint32_t* near_count, float near_tau,
@@ -786,8 +781,11 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
                     "near-zero guard needs a list, its capacity and a zeroed counter");
         AVR_REQUIRE(!(flags & (UF_MASK | UF_ACCUM)), "the near-zero guard applies to forward layers (no MASK / ACCUM)");
     }
-    AVR_REQUIRE((a_nplanes == 2 || a_nplanes == 3) && (b_nplanes == 2 || b_nplanes == 3) && (c_nplanes == 2 || c_nplanes == 3),
-                "plane counts must be 2 or 3");
+    AVR_REQUIRE(planes_kind_ok(a_nplanes) && planes_kind_ok(b_nplanes) && planes_kind_ok(c_nplanes), "unknown plane-set kind");
+    const int a_f16 = planes_f16(a_nplanes), b_f16 = planes_f16(b_nplanes), c_kind = c_nplanes;
+    AVR_REQUIRE(a_f16 == b_f16, "A and B must both be bf16 plane sets or both fp16 pairs");
+    AVR_REQUIRE(!near_list || (!a_f16 && !planes_f16(c_kind)), "the near-zero guard works on bf16 plane sets");
+    a_nplanes = planes_count(a_nplanes); b_nplanes = planes_count(b_nplanes); c_nplanes = planes_count(c_nplanes);
     if (!(a_nplanes == 3 && b_nplanes == 3)) a_nplanes = b_nplanes = 2;     // six products need 24 bits on both sides
     AVR_REQUIRE(M >= 0 && N > 0 && K > 0, "bad dimensions");
     AVR_REQUIRE((flags & UF_OUT_F32) ? N % 8 == 0 : N % 4 == 0, "N must be a multiple of 8 (fp32 output) / 4 (plane output)");
@@ -796,13 +794,20 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     else AVR_REQUIRE(c_planes && ldc % 8 == 0 && c_plane % 8 == 0 && aligned16(c_planes), "plane output must be 16-byte aligned");
     if (flags & UF_MASK) AVR_REQUIRE(mask_bits && ldmask * 32 >= N, "MASK needs a bitmask with >= N/32 words per row");
     if (flags & UF_BITS) AVR_REQUIRE(bits_out && ldbits * 32 >= N && !(flags & UF_OUT_F32), "BITS needs a bitmask output");
-    if (flags & UF_DUAL_RELU) AVR_REQUIRE(c2_planes && ldc2 % 8 == 0 && c2_plane % 8 == 0 && aligned16(c2_planes), "second output misaligned");
+    const bool dual = (flags & (UF_DUAL_RELU | UF_DUAL_COPY)) != 0;
+    AVR_REQUIRE((flags & (UF_DUAL_RELU | UF_DUAL_COPY)) != (UF_DUAL_RELU | UF_DUAL_COPY), "DUAL_RELU and DUAL_COPY exclude each other");
+    if (dual) AVR_REQUIRE(c2_planes && ldc2 % 8 == 0 && c2_plane % 8 == 0 && aligned16(c2_planes) && planes_kind_ok(c2_nplanes) &&
+                          !(flags & (UF_OUT_F32 | UF_ACCUM)), "second output missing / misaligned / unknown kind");
+    if (!dual) c2_nplanes = c_kind;
     AVR_ENTER(device);
     if (M == 0) return AVR_OK;
     UmmaParams p = {};
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.na = a_nplanes; p.nb = b_nplanes; p.nc = c_nplanes;
-    p.BN = pick_bn(N, a_nplanes == 3 ? 128 : 256);
+    p.fa = a_f16; p.fb = b_f16; p.kc = c_kind; p.kc2 = c2_nplanes;
+    p.mode = a_f16 ? 2 : (a_nplanes == 3 ? 1 : 0);
+    p.small_scale = a_f16 ? F16_LO_INV : 1.0f;
+    p.BN = pick_bn(N, (a_nplanes == 3 || a_f16) ? 128 : 256);                // two accumulators per tile: 4 * BN <= 512
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
     // long reductions into an fp32 output (the DFT and its adjoint, K = T or 2F): the accumulator is truncated once per
@@ -816,7 +821,7 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         AVR_REQUIRE(splitk_workspace_bytes >= splits * M * splitk_ld * (int64_t)sizeof(float), "split-K workspace too small");
         p.k_splits = (int)splits;
     }
-    p.dual_acc = (p.na == 3 && p.nb == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC")) ? 1 : 0;
+    p.dual_acc = (a_f16 || (p.na == 3 && p.nb == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
     p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
     p.flags = flags;
     p.c = (__nv_bfloat16*)c_planes; p.ldc = ldc; p.c_plane = c_plane;
@@ -839,7 +844,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.b_raw = (const __nv_bfloat16*)b_planes; p.ldb = ldb; p.b_plane = b_plane;
     const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
     p.nkb = (int)ceil_div(K, UBK);
-    p.epi_warp_bytes = (flags & UF_OUT_F32) ? 0u : (uint32_t)p.nc * EPI_PLANE_BYTES;
+    const int nc2 = planes_count(c2_nplanes);
+    p.epi_warp_bytes = (flags & UF_OUT_F32) ? 0u : (uint32_t)(p.nc > nc2 ? p.nc : nc2) * EPI_PLANE_BYTES;
     const uint32_t bias_bytes = (flags & UF_BIAS) ? 4u * 1024u : 0u;
     uint32_t epi_bytes = 0, bres_total = 0, stage_bytes = 0;
     // two epilogue warps per lane group when their staging tiles fit next to a two-stage pipeline (two-plane outputs,
@@ -867,8 +873,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     if (!(flags & UF_OUT_F32)) {
         if (int rc = make_map(&tc, c_planes, M, N, ldc, c_plane, 32, p.nc, true)) return rc;
         tc2 = tc;
-        if (flags & UF_DUAL_RELU)
-            if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, p.nc, true)) return rc;
+        if (dual)
+            if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, nc2, true)) return rc;
     }
     AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
@@ -905,18 +911,27 @@ AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K
 // C[M,N] (+)= sum_k A[k,M] * B[k,N] on plane pairs stored [K, M] and [K, N] (both MN-major); fp32 output,
 // deterministic split-K over k (the sample points).
 AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
-                             const void* b_planes, int64_t ldb, int64_t b_plane, int nplanes, float* c, int64_t ldc,
-                             int accumulate, void* workspace, int64_t workspace_bytes, int device, void* stream) {
+                             int a_kind, const void* b_planes, int64_t ldb, int64_t b_plane, int b_kind, float* c,
+                             int64_t ldc, int accumulate, void* workspace, int64_t workspace_bytes, int device,
+                             void* stream) {
     AVR_REQUIRE(a_planes && b_planes && c && workspace, "null pointer");
-    AVR_REQUIRE(nplanes == 2 || nplanes == 3, "nplanes must be 2 (three products) or 3 (six products)");
+    AVR_REQUIRE(planes_kind_ok(a_kind) && planes_kind_ok(b_kind) && !planes_f16(a_kind) && !planes_f16(b_kind),
+                "weight gradients take bf16 plane sets (one element format per MMA; gradients need bf16's range)");
+    const int b_f16 = 0;
+    int na = planes_count(a_kind), nb = planes_count(b_kind);
+    if (!b_f16 && !(na == 3 && nb == 3)) na = nb = 2;                       // bf16 . bf16: six products need 24 bits on both sides
+    const int nplanes = (na == 3 || b_f16) ? 3 : 2;                         // "wide" mode: 128-column tiles, two accumulators
     AVR_REQUIRE(M > 0 && N > 0 && K >= 0, "bad dimensions");
     AVR_REQUIRE(M % 4 == 0 && N % 4 == 0, "M and N must be multiples of 4");
     AVR_REQUIRE(K < (1ll << 31), "dimension overflow");
     AVR_ENTER(device);
     UmmaParams p = {};
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.BN = pick_bn(N, nplanes == 3 ? 128 : 256);                // three planes: two stages and two accumulators must fit
-    p.na = p.nb = nplanes; p.nc = 2;
+    p.BN = pick_bn(N, nplanes == 3 ? 128 : 256);                // two stages and two accumulators must fit
+    p.na = na; p.nb = nb; p.nc = 2;
+    p.fa = 0; p.fb = b_f16; p.kc = p.kc2 = AVR_PLANES_BF16x2;
+    p.mode = b_f16 ? (na == 3 ? 4 : 3) : (na == 3 ? 1 : 0);
+    p.small_scale = b_f16 ? F16_LO_INV : 1.0f;
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     const int64_t ldp = ceil_div(N, 8) * 8;                    // partial rows padded to whole 8-column store groups
     const int64_t splits = K > 0 ? tn_splits(M, N, K, p.BN) : 1;
@@ -925,13 +940,13 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.k_per_split = (int)(ceil_div(ceil_div(K, splits), UBK) * UBK);
     if (p.k_per_split < UBK) p.k_per_split = UBK;
     p.k_splits = (int)(K > 0 ? ceil_div(K, p.k_per_split) : 1);
-    p.dual_acc = (nplanes == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC")) ? 1 : 0;
+    p.dual_acc = (b_f16 || (nplanes == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
     p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
     p.c32 = (float*)workspace; p.ldc32 = ldp;
     p.epi_split = 2; p.epi_warp_bytes = 0;
     if (const char* e = getenv("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
     const int bn_rows = (p.BN + 63) / 64 * 64;
-    const uint32_t stage_bytes = (uint32_t)nplanes * (A_PLANE_BYTES + (uint32_t)bn_rows * 128u);
+    const uint32_t stage_bytes = (uint32_t)na * A_PLANE_BYTES + (uint32_t)nb * (uint32_t)bn_rows * 128u;
     p.stages = (int)((220 * 1024) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
     if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
@@ -939,8 +954,8 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     cudaStream_t st = (cudaStream_t)stream;
     if (K > 0) {
         CUtensorMap ta, tb;
-        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, nplanes)) return rc;
-        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nplanes)) return rc;
+        if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, na)) return rc;
+        if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nb)) return rc;
         AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);

@@ -11,6 +11,8 @@ B200-first changes:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -18,7 +20,15 @@ from .fused import plan_modules
 from .ops import PlanePair
 
 
-FWD_PLANES = 3      # forward operands carry 24 mantissa bits (six products): ReLU decisions must match fp32
+FWD_KIND = ops.PLANES_BF16x3  # forward operands carry 24 mantissa bits (six products): ReLU decisions must match fp32
+SIG_HIDDEN_F16 = os.environ.get("AVR_SIG_F16", "1") != "0"
+# The 512 x 512 hidden layers of the signal network (tensor-bound, half of the forward MMA time) take fp16
+# (hi, lo' * 2^11) pairs: 24 bits in two planes, THREE products instead of six.  The producing layer writes each hidden
+# activation twice (ops.UMMA_DUAL_COPY): as an fp16 pair for the next layer / the collapsed output layer, and as a bf16
+# (hi, mid) pair for the weight-gradient GEMM (gradients need bf16's range, and tcgen05.mma faults on a bf16 x f16 mix).
+# Measured on one box, same run: 14.6 -> 14.1 ms per step; the layers become L2-feed-bound (512 KB of operands per
+# 128 x 128 tile) instead of MMA-bound, hence not the full 2x.  Range: fp16's -- like tiny-cuda-nn's own activations --
+# inf / NaN beyond 65504 (loud), absolute error <= 1.5e-11 below 6e-5.  AVR_SIG_F16=0 keeps bf16 triples everywhere.
 BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough ...
 DENSITY_BWD_PLANES = 3   # ... except along the sigma decoder: the density gradient of a ray sums to ~0 over its samples
                          # (sum_s w_s = 1), so the decoder's weight-gradient sums cancel to ~1/50 of their terms
@@ -32,11 +42,12 @@ LAST_GUARD_COUNTS = None  # diagnostics: per-layer number of re-evaluated elemen
 
 
 def _weight_planes(net, params, transpose, n):
-    """Plane sets of every matrix of ``net`` (``W[out,in]``) or of its transpose (``W^T[in,out]``)."""
+    """Plane sets (kind ``n``: 2 / 3 bf16 planes or ops.PLANES_F16x2) of every matrix of ``net`` (``W[out,in]``) or of
+    its transpose (``W^T[in,out]``)."""
     out = []
     for w in net.matrices(params):
         o, i = w.shape
-        pp = PlanePair.empty(i, o, w.device, n=n) if transpose else PlanePair.empty(o, i, w.device, n=n)
+        pp = PlanePair.empty(i, o, w.device, kind=n) if transpose else PlanePair.empty(o, i, w.device, kind=n)
         ops.planes_split(w, pp, transpose=transpose)
         out.append(pp)
     return out
@@ -108,15 +119,15 @@ class FusedRenderTC(torch.autograd.Function):
         LAST_GUARD_COUNTS = guard.counters if guard is not None else None
 
         # ---- sigma encoder ------------------------------------------------------------------------
-        x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
+        x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, kind=FWD_KIND)
         _assemble(plan["x0"], x0, 0, enc_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals, params_of, delay_slot,
                   rows_of)
         if delay_slot:
             _, _, _, delay = ops.sample_points(geom, rays_o, pos_tx, dirs, d_vals, want_pts=False)
-        w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_PLANES)
+        w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_KIND)
         acts_enc, bits_enc, h = [], [], x0
         for li in range(len(w_enc) - 1):
-            y = PlanePair.empty(n_rows, w_enc[li].rows, dev, n=FWD_PLANES)
+            y = PlanePair.empty(n_rows, w_enc[li].rows, dev, kind=FWD_KIND)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev)
             fl, kw = layer_flags("enc", li)
             ops.umma_nt(h, w_enc[li], fl, y, bits_out=bits, guard=guard, **kw)
@@ -124,14 +135,14 @@ class FusedRenderTC(torch.autograd.Function):
             bits_enc.append(bits)
             h = y
         # sigma_feat lands directly in the signal network's input buffer (no concat)
-        sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev, n=FWD_PLANES)
+        sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev, kind=FWD_KIND)
         feat_win = sig_in.window(0, feat_dim)
         bits_feat = ops.relu_bits_empty(n_rows, feat_dim, dev)               # (sigma_feat > 0)
         if plan["sig_relu_feat"]:
             ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat, guard=guard)        # both consumers read relu(feat)
             dec_in = feat_win
         else:
-            dec_buf = PlanePair.empty(n_rows, dec_net.in_pad, dev, n=FWD_PLANES)
+            dec_buf = PlanePair.empty(n_rows, dec_net.in_pad, dev, kind=FWD_KIND)
             ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_buf.window(0, feat_dim), bits_out=bits_feat, guard=guard)   # raw feat + relu(feat)
             if dec_net.in_pad > feat_dim:                                    # decoder input = [relu(feat), embedding row]
                 _assemble(plan.get("dec_tail", []), dec_buf, feat_dim, dec_net.in_pad, geom, small_in, rays_o, pos_tx, dirs,
@@ -141,10 +152,10 @@ class FusedRenderTC(torch.autograd.Function):
             raise NotImplementedError("sigma decoder input width does not match the sigma feature width")
 
         # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
-        w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_PLANES)
+        w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND)
         acts_dec, bits_dec, h = [], [], dec_in
         for li in range(len(w_dec) - 1):
-            y = PlanePair.empty(n_rows, w_dec[li].rows, dev, n=FWD_PLANES)
+            y = PlanePair.empty(n_rows, w_dec[li].rows, dev, kind=FWD_KIND)
             bits = ops.relu_bits_empty(n_rows, y.cols, dev)
             fl, kw = layer_flags("dec", li)
             ops.umma_nt(h, w_dec[li], fl, y, bits_out=bits, guard=guard, **kw)
@@ -159,14 +170,30 @@ class FusedRenderTC(torch.autograd.Function):
         _assemble(plan["tail"], sig_in, feat_dim, sig_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals,
                   params_of, [], rows_of)
         sig_mats = sig_net.matrices(params_of(sig_net))
-        w_sig = _weight_planes(sig_net, params_of(sig_net), False, FWD_PLANES)[:-1]
-        acts_sig, bits_sig, h = [], [], sig_in
-        for li in range(len(w_sig)):
-            y = PlanePair.empty(n_rows, w_sig[li].rows, dev, n=FWD_PLANES)
-            bits = ops.relu_bits_empty(n_rows, y.cols, dev) if li < len(w_sig) - 1 else None   # last one is read by collapse
+        n_sig = len(sig_mats) - 1                                            # hidden layers (the output layer is collapsed)
+        f16 = SIG_HIDDEN_F16 and guard is None
+        w_sig = []
+        for li, wm in enumerate(sig_mats[:-1]):                              # layer li > 0 multiplies an fp16-pair activation
+            o, i = wm.shape
+            w_sig.append(ops.planes_split(wm, PlanePair.empty(o, i, dev, kind=ops.PLANES_F16x2 if (f16 and li > 0) else FWD_KIND)))
+        acts_sig, bits_sig, h = [], [], sig_in                               # acts_sig: what the weight gradients read
+        for li in range(n_sig):
+            last = li == n_sig - 1
+            bits = ops.relu_bits_empty(n_rows, w_sig[li].rows, dev) if not last else None   # the last one is read by collapse
             fl, kw = layer_flags("sig", li)
-            ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, guard=guard, **kw)
-            acts_sig.append(y)
+            if f16:
+                y = PlanePair.empty(n_rows, w_sig[li].rows, dev, kind=ops.PLANES_F16x2)
+                if last:                                                     # H: only the collapsed output layer reads it
+                    ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, **kw)
+                    acts_sig.append(y)
+                else:
+                    y_bf = PlanePair.empty(n_rows, w_sig[li].rows, dev)
+                    ops.umma_nt(h, w_sig[li], fl | ops.UMMA_DUAL_COPY, y, y_bf, bits_out=bits, **kw)
+                    acts_sig.append(y_bf)
+            else:
+                y = PlanePair.empty(n_rows, w_sig[li].rows, dev, kind=FWD_KIND)
+                ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, guard=guard, **kw)
+                acts_sig.append(y)
             bits_sig.append(bits)
             h = y
         sort = ops.delay_sort(geom, delay, w)
@@ -327,7 +354,7 @@ class FusedRenderTC(torch.autograd.Function):
             bias_grad("enc", li - 1, g)
         x0 = B["x0"]
         ops.umma_tn(g, x0, d_enc_mats[0], ws)
-        d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev, n=FWD_PLANES)
+        d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev)
         ops.umma_nt(g, wt_enc[0], 0, d_x0)
         grads[id(enc_net)] = g_enc
         announce(enc_net)

@@ -16,7 +16,8 @@ import torch
 
 from . import _lib
 from ._lib import (GEMM_ACCUM, GEMM_MASK, GEMM_RELU, GEMM_RELU_A, GEMM_RELU_B, I_CONTIG, K_CONTIG,  # noqa: F401
-                   UMMA_ACCUM, UMMA_BIAS, UMMA_BITS, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta, RenderGeom)
+                   UMMA_ACCUM, UMMA_BIAS, UMMA_BITS, UMMA_DUAL_COPY, UMMA_DUAL_RELU, UMMA_MASK, UMMA_OUT_F32, UMMA_RELU, GridMeta,
+                   RenderGeom)
 
 # ---- optional per-launch timing (bench.py): CUDA events on the launching stream ----------------------
 PROFILE = None          # set to a list to collect (name, work, unit, start_event, end_event)
@@ -43,14 +44,21 @@ class _timed:
         return False
 
 
+PLANES_BF16x2, PLANES_BF16x3, PLANES_F16x2 = 2, 3, 18       # include/avr_b200.h, plane-set kinds
+
+
 class PlanePair:
-    """x = hi + mid (+ lo) stored as a bf16 buffer ``[n, rows, ld]`` (n = 2: 16 mantissa bits, n = 3: 24);
-    optionally a row / column window of it."""
+    """A plane set: a 16-bit buffer ``[n, rows, ld]``, optionally a row / column window of it.
+
+    bf16 buffer: ``x = hi + mid (+ lo)`` (n = 2: 16 mantissa bits, n = 3: 24, fp32 range);
+    fp16 buffer (n = 2): ``x = hi + lo' * 2^-11`` with ``lo' = fp16((x - hi) * 2^11)`` -- 24 bits in two planes within
+    fp16's range, so a product needs three tensor-core MMAs where two bf16 triples need six."""
 
     __slots__ = ("buf", "ld", "row0", "rows", "col0", "cols")
 
     def __init__(self, buf, col0=0, cols=None, row0=0, rows=None):
-        assert buf.dtype == torch.bfloat16 and buf.dim() == 3 and buf.shape[0] in (2, 3) and buf.is_contiguous()
+        assert buf.dim() == 3 and buf.is_contiguous()
+        assert (buf.dtype == torch.bfloat16 and buf.shape[0] in (2, 3)) or (buf.dtype == torch.float16 and buf.shape[0] == 2)
         self.buf, self.ld = buf, buf.shape[2]
         self.row0 = row0
         self.rows = buf.shape[1] - row0 if rows is None else rows
@@ -59,20 +67,32 @@ class PlanePair:
         assert col0 % 8 == 0 and self.ld % 8 == 0, "plane windows must stay 16-byte aligned"
 
     @staticmethod
-    def empty(rows, cols, device, ld=None, n=2):
+    def empty(rows, cols, device, ld=None, n=2, kind=None):
+        """``kind`` (PLANES_*) overrides ``n``: PLANES_F16x2 allocates an fp16 pair."""
         ld = cols if ld is None else ld
         ld = (ld + 7) // 8 * 8
+        if kind == PLANES_F16x2:
+            return PlanePair(torch.empty(2, rows, ld, dtype=torch.float16, device=device), 0, cols)
+        n = n if kind is None else kind
         return PlanePair(torch.empty(n, rows, ld, dtype=torch.bfloat16, device=device), 0, cols)
 
     @staticmethod
-    def zeros(rows, cols, device, ld=None, n=2):
-        pp = PlanePair.empty(rows, cols, device, ld, n)
+    def zeros(rows, cols, device, ld=None, n=2, kind=None):
+        pp = PlanePair.empty(rows, cols, device, ld, n, kind)
         pp.buf.zero_()
         return pp
 
     @property
     def n(self):
         return self.buf.shape[0]
+
+    @property
+    def f16(self):
+        return self.buf.dtype == torch.float16
+
+    @property
+    def kind(self):
+        return PLANES_F16x2 if self.f16 else self.buf.shape[0]
 
     def window(self, col0, cols):
         return PlanePair(self.buf, self.col0 + col0, cols, self.row0, self.rows)
@@ -118,7 +138,7 @@ def _dense(t):
 
 
 def _np(x):
-    return x.n if isinstance(x, PlanePair) else 0
+    return x.kind if isinstance(x, PlanePair) else 0
 
 
 def _mat(x):
@@ -312,7 +332,7 @@ def planes_split(x, out: PlanePair, transpose=False, relu=False):
     dev, st = _ctx(x)
     rows, cols = x.shape
     assert x.stride(1) == 1
-    _lib.check(_lib.load().avr_planes_split(_p(x), rows, cols, x.stride(0), out.ptr, out.ld, out.plane, out.n,
+    _lib.check(_lib.load().avr_planes_split(_p(x), rows, cols, x.stride(0), out.ptr, out.ld, out.plane, out.kind,
                                             1 if transpose else 0, 1 if relu else 0, dev, st), "avr_planes_split")
     return out
 
@@ -320,7 +340,7 @@ def planes_split(x, out: PlanePair, transpose=False, relu=False):
 def planes_merge(pp: PlanePair):
     dev, st = _ctx(pp)
     out = torch.empty(pp.rows, pp.cols, device=pp.device)
-    _lib.check(_lib.load().avr_planes_merge(pp.ptr, pp.rows, pp.cols, pp.ld, pp.plane, pp.n, _p(out), pp.cols, dev, st),
+    _lib.check(_lib.load().avr_planes_merge(pp.ptr, pp.rows, pp.cols, pp.ld, pp.plane, pp.kind, _p(out), pp.cols, dev, st),
                "avr_planes_merge")
     return out
 
@@ -374,16 +394,18 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
     if bias_ray is not None or bias_rcv is not None:
         flags |= UMMA_BIAS
     products = 6 if (a.n == 3 and b.n == 3) else 3
+    assert a.f16 == b.f16, "A and B must both be bf16 plane sets or both fp16 pairs"
     ws = None
     if split_k:
         slices = int(_lib.load().avr_umma_gemm_nt_splitk_slices(K))
         ws = torch.empty(slices * M * ((N + 7) // 8 * 8), device=a.device)
     with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * products):
         _lib.check(_lib.load().avr_umma_gemm_nt(
-            M, N, K, a.ptr, a.ld, a.plane, a.n, b.ptr, b.ld, b.plane, b.n, flags,
+            M, N, K, a.ptr, a.ld, a.plane, a.kind, b.ptr, b.ld, b.plane, b.kind, flags,
             c.ptr if c is not None else none, c.ld if c is not None else 0, c.plane if c is not None else 0,
-            c.n if c is not None else 2,
+            c.kind if c is not None else 2,
             c2.ptr if c2 is not None else none, c2.ld if c2 is not None else 0, c2.plane if c2 is not None else 0,
+            c2.kind if c2 is not None else 2,
             _p(mask, torch.int32), mask.stride(0) if mask is not None else 0,
             _p(bits_out, torch.int32), bits_out.stride(0) if bits_out is not None else 0,
             _p(bias_ray), bias_ray.stride(0) if bias_ray is not None else 0,
@@ -405,9 +427,10 @@ def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
     dev, st = _ctx(a)
     K, M, N = a.rows, a.cols, b.cols
     assert b.rows == K
-    nplanes = 3 if (a.n == 3 and b.n == 3) else 2          # six products only when both operands carry 24 bits
-    with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * (6 if nplanes == 3 else 3)):
-        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, b.ptr, b.ld, b.plane, nplanes, _p(c_f32),
+    assert not a.f16 and not b.f16, "weight gradients take bf16 plane sets"
+    products = 6 if (a.n == 3 and b.n == 3) else 3       # six products only when both operands carry 24 bits
+    with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * products):
+        _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, a.kind, b.ptr, b.ld, b.plane, b.kind, _p(c_f32),
                                                 c_f32.stride(0), 1 if accumulate else 0,
                                                 C.c_void_p(workspace.data_ptr()),
                                                 workspace.numel() * workspace.element_size(), dev, st), "avr_umma_gemm_tn")
@@ -536,7 +559,7 @@ def collapse_fwd(g, act: PlanePair, sort, w_out, tspan):
     prefix = torch.empty((nbytes + 3) // 4, device=act.device)
     n_pts = g.bs * g.R * g.S
     with _timed("collapse_fwd", float(n_pts) * act.cols * 4 + float(g.bs * g.S) * g.T * act.cols * 4, "byte"):
-        _lib.check(_lib.load().avr_collapse_fwd(C.byref(g), act.ptr, act.ld, act.plane, act.cols, _p(order, torch.int32),
+        _lib.check(_lib.load().avr_collapse_fwd(C.byref(g), act.ptr, act.ld, act.plane, act.kind, act.cols, _p(order, torch.int32),
                                                 _p(sdelay, torch.int32), _p(sw), _p(w_out), w_out.stride(0), tspan,
                                                 _p(prefix), prefix.numel() * 4, _p(y), dev, st), "avr_collapse_fwd")
     return y, prefix
@@ -551,7 +574,7 @@ def collapse_bwd(g, act: PlanePair, sort, w_out, d_y, tspan, prefix, d_act: Plan
     suffix = torch.empty((nbytes + 3) // 4, device=act.device)
     n_pts = g.bs * g.R * g.S
     with _timed("collapse_bwd", float(n_pts) * act.cols * 8 + 2.0 * g.bs * g.S * g.T * act.cols * 4, "byte"):
-        _lib.check(_lib.load().avr_collapse_bwd(C.byref(g), act.ptr, act.ld, act.plane, act.cols, _p(order, torch.int32),
+        _lib.check(_lib.load().avr_collapse_bwd(C.byref(g), act.ptr, act.ld, act.plane, act.kind, act.cols, _p(order, torch.int32),
                                                 _p(sdelay, torch.int32), _p(sw), _p(w_out), w_out.stride(0),
                                                 _p(_dense(d_y)), tspan, _p(prefix), _p(suffix), suffix.numel() * 4,
                                                 d_act.ptr, d_act.ld, d_act.plane, _p(d_w), _p(d_wout), d_wout.stride(0),

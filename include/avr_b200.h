@@ -156,6 +156,15 @@ AVR_API int avr_gemm(int layout_a, int layout_b, int64_t M, int64_t N, int64_t K
  *   3 planes x 3 planes: + hi*lo + lo*hi + mid*mid          (~2^-24: fp32-grade pre-activations, needed in the
  *                        forward pass so that ReLU decisions agree with an fp32 evaluation -- DESIGN.md 5)
  * all accumulated in one fp32 TMEM accumulator. */
+/* Plane-set kinds (every `*_nplanes` / `*_kind` argument of this header):
+ *   AVR_PLANES_BF16x2 / AVR_PLANES_BF16x3   x = hi + mid (+ lo), bf16 planes: 16 / 24 mantissa bits, fp32 range
+ *   AVR_PLANES_F16x2                        x = hi + lo' * 2^-11 with hi = fp16(x), lo' = fp16((x - hi) * 2^11):
+ *                                           24 mantissa bits in TWO planes for |x| in fp16's normal range
+ *                                           (6.1e-5 .. 65504; absolute error <= 1.5e-11 below it, inf above --
+ *                                           the range tiny-cuda-nn's own fp16 activations live in).
+ * A product of two F16x2 operands needs three tcgen05 MMAs for fp32 grade (hi*hi into one accumulator, hi*lo' +
+ * lo'*hi into a second one that the epilogue scales by 2^-11) where two BF16x3 operands need six. */
+enum { AVR_PLANES_BF16x2 = 2, AVR_PLANES_BF16x3 = 3, AVR_PLANES_F16x2 = 18 };
 enum {
     AVR_UMMA_RELU = 1,        /* out = max(out, 0)                                                   */
     AVR_UMMA_ACCUM = 2,       /* out += previous contents of the output                              */
@@ -163,7 +172,9 @@ enum {
     AVR_UMMA_OUT_F32 = 8,     /* write fp32 c_f32 instead of a plane pair                            */
     AVR_UMMA_DUAL_RELU = 16,  /* additionally write max(out,0) as a second plane pair (c2)           */
     AVR_UMMA_BITS = 32,       /* additionally write the bitmask (out > 0) to bits_out (1 bit / element) */
-    AVR_UMMA_BIAS = 64        /* out[row,:] += bias_ray[ray(row),:] + bias_rcv[receiver(row),:], row = (b*R + r)*S + s */
+    AVR_UMMA_BIAS = 64,       /* out[row,:] += bias_ray[ray(row),:] + bias_rcv[receiver(row),:], row = (b*R + r)*S + s */
+    AVR_UMMA_DUAL_COPY = 2048 /* additionally write the same values (after RELU) as a second plane set (c2) of kind c2_nplanes:
+                                 an fp16 pair feeds the next forward layer, a bf16 pair the weight-gradient GEMM */
 };
 /* fp32 [rows, cols] (ld) <-> plane pair; transpose != 0 writes planes[c, r] = x[r, c]; relu != 0 clamps */
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
@@ -183,7 +194,7 @@ AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int
 AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_nplanes, const void* b_planes, int64_t ldb, int64_t b_plane, int b_nplanes, int flags,
                              void* c_planes, int64_t ldc, int64_t c_plane, int c_nplanes, void* c2_planes, int64_t ldc2,
-                             int64_t c2_plane, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
+                             int64_t c2_plane, int c2_nplanes, const uint32_t* mask_bits, int64_t ldmask, uint32_t* bits_out,
                              int64_t ldbits, const float* bias_ray, int64_t ld_bias_ray, const float* bias_rcv,
                              int64_t ld_bias_rcv, int32_t geo_R, int32_t geo_S, float* c_f32, int64_t ldc32,
                              uint32_t* near_list, int64_t near_cap, uint32_t* near_count, float near_tau,
@@ -194,13 +205,17 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
  * accumulator chain is a visible bias (~6e-9*K).  Workspace: slices * M * roundup(N, 8) * 4 bytes. */
 AVR_API int64_t avr_umma_gemm_nt_splitk_slices(int64_t K);
 /* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane sets; weight gradients).
- * fp32 output; deterministic split-K over the points through `workspace`.  nplanes = 2: three products on the
- * (hi, mid) planes; 3: six products on 24-bit operands (both sets must then hold three planes) -- for the
- * ill-conditioned sums of the density path, whose terms cancel to ~1/50 of their magnitude. */
+ * fp32 output; deterministic split-K over the points through `workspace`.  A (the gradient) is a bf16 plane set, B
+ * (the activation) a bf16 set or an fp16 pair:
+ *   BF16x2 . BF16x2 (or mixed counts): three products on the (hi, mid) planes
+ *   BF16x3 . BF16x3: six products on 24-bit operands -- for the ill-conditioned sums of the density path, whose
+ *                    terms cancel to ~1/50 of their magnitude
+ * fp16 pairs are not accepted: gradients need bf16's exponent range, and tcgen05.mma faults on a bf16 x f16 mix. */
 AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
 AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
-                             const void* b_planes, int64_t ldb, int64_t b_plane, int nplanes, float* c, int64_t ldc,
-                             int accumulate, void* workspace, int64_t workspace_bytes, int device, void* stream);
+                             int a_kind, const void* b_planes, int64_t ldb, int64_t b_plane, int b_kind, float* c,
+                             int64_t ldc, int accumulate, void* workspace, int64_t workspace_bytes, int device,
+                             void* stream);
 
 /* ---- output layer fused with the ray reduction ("collapse"; model.py:231 + renderer.py:86-90,115-118) -----
  * y[b,s,t] = sum_r w[b,r,s] [t >= delay[b,r,s]] (H[b,r,s,:] . W_out[t,:]) evaluated as a prefix sum over the
@@ -215,13 +230,13 @@ AVR_API int avr_delay_sort(const avr_render_geom* geom, const int32_t* delay, co
 AVR_API int64_t avr_collapse_prefix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan);
 AVR_API int64_t avr_collapse_suffix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan);
 AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             int32_t act_kind, int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
                              const float* w_out, int64_t ldw, int32_t tspan, void* prefix_ws, int64_t prefix_bytes, float* y,
                              int device, void* stream);
 /* d_act = (H > 0) * w * g[delay] as a plane pair (gradient w.r.t. the pre-activation), d_w[bs,R,S] = H . g[delay],
  * d_W_out[T, width] (+)= sum_{b,s} d_y[b,s,t] G[b,s,t,:] */
 AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes, int64_t ld_act, int64_t act_plane,
-                             int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
+                             int32_t act_kind, int32_t width, const int32_t* order, const int32_t* sdelay, const float* sw,
                              const float* w_out, int64_t ldw, const float* d_y, int32_t tspan, const void* prefix_ws,
                              void* suffix_ws, int64_t suffix_bytes, void* d_act_planes, int64_t ld_d, int64_t d_plane,
                              float* d_w, float* d_wout, int64_t ld_dw, int accumulate, int device, void* stream);

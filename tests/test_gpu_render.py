@@ -34,9 +34,13 @@ def _check_grads(native, ref_net, tol=TOL):
     return worst
 
 
-@pytest.mark.parametrize("dense", ["tc", "simt"])
+@pytest.mark.parametrize("dense", ["tc", "tc-bf16x3", "simt"])
 @pytest.mark.parametrize("name", GOLDEN_CASES[:3])
-def test_fused_render_vs_golden(built_library, name, dense):
+def test_fused_render_vs_golden(built_library, name, dense, monkeypatch):
+    if dense == "tc-bf16x3":                                   # bf16 triples in the signal network's hidden layers too
+        from avr_b200 import fused_tc
+        monkeypatch.setattr(fused_tc, "SIG_HIDDEN_F16", False)
+        dense = "tc"
     g = load_golden(name)
     model_class, cfg = case_config(name)
     ref_net = oracle_field(model_class, cfg["model"], g)

@@ -116,6 +116,63 @@ def test_umma_nt_split_k_long_reduction(built_library, M, N, K):
     assert torch.equal(c1, c2)
 
 
+def _pp16(x, ld=None):
+    out = PlanePair.empty(x.shape[0], x.shape[1], DEV, ld, kind=ops.PLANES_F16x2)
+    return ops.planes_split(x.to(DEV).contiguous(), out)
+
+
+def test_f16_pair_roundtrip(built_library):
+    """x = hi + lo' * 2^-11: 24 bits in two fp16 planes inside fp16's normal range; absolute error <= 1.5e-11 below it."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(500, 72, generator=g) * 10 ** (torch.rand(500, 72, generator=g) * 6 - 3)     # 1e-3 .. 1e3
+    pp = _pp16(x, ld=80)
+    assert pp.kind == ops.PLANES_F16x2 and pp.buf.dtype == torch.float16
+    back = ops.planes_merge(pp).cpu()
+    assert bool(((back - x).abs() <= 2 ** -22 * x.abs() + 3e-11).all())
+    tiny = torch.randn(64, 8, generator=g) * 1e-6
+    assert float((ops.planes_merge(_pp16(tiny)).cpu() - tiny).abs().max()) <= 3e-11
+    t = PlanePair.empty(72, 500, DEV, 504, kind=ops.PLANES_F16x2)
+    ops.planes_split(x.to(DEV), t, transpose=True, relu=True)
+    assert rel_l2(ops.planes_merge(t), x.clamp_min(0).t()) < 2e-7
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 128, 48), (4099, 512, 512), (300, 16, 128), (777, 208, 128), (130, 512, 208),
+                                   (2050, 1600, 512)])
+def test_umma_nt_f16_pairs_fp32_grade(built_library, M, N, K):
+    """fp16 (hi, lo') pairs: three products (hi*hi; hi*lo' + lo'*hi through the scaled second accumulator) are as
+    accurate as the six products of bf16 triples -- and as an fp32 GEMM."""
+    g = torch.Generator().manual_seed(M * N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    a, b = _pp16(A), _pp16(B)
+    ref = ops.planes_merge(a).double() @ ops.planes_merge(b).double().t()
+    assert rel_l2(ops.planes_merge(a), A) < 1e-7
+    c = PlanePair.empty(M, N, DEV, kind=ops.PLANES_F16x2)
+    bits = ops.relu_bits_empty(M, N, DEV)
+    ops.umma_nt(a, b, ops.UMMA_RELU, c, bits_out=bits)
+    got = ops.planes_merge(c)
+    bound = 2e-9 * K + 4e-7
+    assert rel_l2(got, ref.clamp_min(0)) < bound, (rel_l2(got, ref.clamp_min(0)), bound)
+    assert torch.equal(_unpack_bits(bits, N), got > 0)
+    fp32 = (A.to(DEV) @ B.to(DEV).t())
+    assert rel_l2(got, ref.clamp_min(0)) < 3 * rel_l2(fp32.clamp_min(0), (A.double() @ B.double().t()).clamp_min(0)) + 1e-7
+    c32 = torch.empty(M, N, device=DEV)
+    ops.umma_nt(a, b, ops.UMMA_OUT_F32, c_f32=c32)
+    assert rel_l2(c32, ref) < bound
+    if N % 8 == 0 and N >= 128:
+        c1, c2 = PlanePair.empty(M, N, DEV, kind=ops.PLANES_F16x2), PlanePair.empty(M, N, DEV, kind=ops.PLANES_F16x2)
+        ops.umma_nt(a, b, ops.UMMA_DUAL_RELU, c1, c2)                        # raw + ReLU outputs
+        assert rel_l2(ops.planes_merge(c1), ref) < bound and torch.equal(ops.planes_merge(c2), got)
+        # the same activation twice: fp16 pair for the next forward layer, bf16 (hi, mid) pair for the weight gradient
+        c3, c4 = PlanePair.empty(M, N, DEV, kind=ops.PLANES_F16x2), PlanePair.empty(M, N, DEV, ld=N + 8)
+        ops.umma_nt(a, b, ops.UMMA_RELU | ops.UMMA_DUAL_COPY, c3, c4, bits_out=bits)
+        assert torch.equal(ops.planes_merge(c3), got) and rel_l2(ops.planes_merge(c4), got) < 2 ** -16
+        # bf16 triples in, fp16 pair + bf16 pair out (first hidden layer of the signal network)
+        a3, b3 = _pp(A, n=3), _pp(B, n=3)
+        ops.umma_nt(a3, b3, ops.UMMA_RELU | ops.UMMA_DUAL_COPY, c3, c4)
+        ref3 = (ops.planes_merge(a3).double() @ ops.planes_merge(b3).double().t()).clamp_min(0)
+        assert rel_l2(ops.planes_merge(c3), ref3) < bound and rel_l2(ops.planes_merge(c4), ref3) < 2 ** -16
+
+
 def _unpack_bits(bits, N):
     sh = torch.arange(32, device=bits.device, dtype=torch.int32)
     return ((bits[:, :(N + 31) // 32].unsqueeze(-1) >> sh) & 1).reshape(bits.shape[0], -1)[:, :N].bool()
@@ -222,7 +279,8 @@ def test_umma_tn_six_products_ill_conditioned(built_library, M, N, K):
 
 
 @pytest.mark.parametrize("bs,R,S,T,W", [(2, 37, 5, 200, 64), (1, 300, 7, 400, 512), (3, 66, 4, 240, 136)])
-def test_collapse_matches_literal_output_layer(built_library, bs, R, S, T, W):
+@pytest.mark.parametrize("act_kind", [ops.PLANES_BF16x2, ops.PLANES_F16x2])
+def test_collapse_matches_literal_output_layer(built_library, bs, R, S, T, W, act_kind):
     """y, d_H, d_w, d_W_out of the collapsed output layer == literal GEMM + masked ray reduction (float64)."""
     g = torch.Generator().manual_seed(R + T)
     n = bs * R * S
@@ -233,7 +291,7 @@ def test_collapse_matches_literal_output_layer(built_library, bs, R, S, T, W):
     delay[0, :, 0] = 7                                                    # one (b,s) where every ray shares a delay
     dy = torch.randn(bs, S, T, generator=g)
     geom = ops.RenderGeom(bs, R, S, T, -10.0, 20.0, 16000.0, 343.8)
-    hp = PlanePair.empty(n, W, DEV)
+    hp = PlanePair.empty(n, W, DEV, kind=act_kind)
     ops.planes_split(H.to(DEV), hp)
     Hq = ops.planes_merge(hp).cpu().double()                              # the values the kernels actually see
     Hq.requires_grad_()
