@@ -34,6 +34,8 @@ struct UmmaParams {
     int tiles_m, tiles_n, k_splits, k_per_split;
     int stages, tmem_cols;
     int dual_acc;           // six-product mode: the five small products go to a second TMEM accumulator (see the MMA issuer)
+    int acc_bufs;           // tiles buffered in TMEM: 2 (the epilogue of one overlaps the MMAs of the next) or 1 (256-wide
+                            // tiles with two accumulators fill the 512 columns: less operand traffic, no overlap)
     int na, nb, nc;         // planes used of A / B (2: hi,mid  3: hi,mid,lo) and written to C
     int fa, fb, kc, kc2;    // A / B planes are fp16 (hi, lo'*2^11) pairs; plane-set kinds of C and C2 (AVR_PLANES_*)
     int mode;               // product schedule, see the MMA issuer
@@ -120,6 +122,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// two TMEM loads in flight, one wait: the load latency is paid once per pair (each tcgen05.wait::ld stalls the warp)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
+}
+
+// 32 columns of the main and of the small accumulator: two x32 loads, one wait; v = main + small * scale
+__device__ __forceinline__ void tmem_ld32_dual(uint32_t ta, uint32_t tb, float scale, float (&v)[32]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[32 + i]), scale, __uint_as_float(r[i]));
 }
 
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1)
@@ -307,8 +340,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (bres && (int)blockIdx.x < n_tiles) mbar_wait(bar_bres, 0);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
                 const int split = tile % p.k_splits;
-                const int acc = iter & 1;
-                mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
+                const int acc = p.acc_bufs == 2 ? (iter & 1) : 0;
+                const uint32_t acc_phase = (uint32_t)(p.acc_bufs == 2 ? (iter >> 1) : iter) & 1u;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
                 tc_fence_after();
                 // Each tcgen05.mma truncates the fp32 accumulator once (measured: ~1.5e-8 of its magnitude per MMA, toward
                 // zero).  With one accumulator all 6*K/16 MMAs of the six-product mode truncate at full magnitude; with
@@ -374,7 +408,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int split = tile % p.k_splits;
             const int mn = tile / p.k_splits;
             const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
-            const int acc = iter & 1;
+            const int acc = p.acc_bufs == 2 ? (iter & 1) : 0;
+            const uint32_t acc_phase = (uint32_t)(p.acc_bufs == 2 ? (iter >> 1) : iter) & 1u;
             const long long row = m0 + lane_grp * 32 + lane;
             const bool row_ok = row < p.M;
             // per-tile operands of the epilogue are fetched BEFORE waiting for the accumulator, so that their
@@ -409,7 +444,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (p.flags & UF_BIAS) __syncwarp();
             }
-            mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.BN * (p.dual_acc ? 2 : 1));
             if (MN_MAJOR || (p.flags & UF_OUT_F32)) {
@@ -452,24 +487,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float v[32];
                     {
                         float t0[16], t1[16];
-                        tmem_ld16(taddr + c0, t0);
-                        if (c0 + 16 < p.BN) {
-                            tmem_ld16(taddr + c0 + 16, t1);
-                        } else {                                                // ragged last chunk (single-tile N only):
-#pragma unroll                                                                  // the missing columns lie outside the
-                            for (int i = 0; i < 16; ++i) t1[i] = 0.f;           // output window and are clipped by TMA
-                        }
+                        const bool second = c0 + 16 < p.BN;                     // ragged last chunk (single-tile N only): the
+                        if (p.dual_acc && second) {
+                            tmem_ld32_dual(taddr + c0, taddr + p.BN + c0, p.small_scale, v);
+                        } else if (p.dual_acc) {                                // missing columns lie outside the output
+                            tmem_ld16x2(taddr + c0, taddr + p.BN + c0, t0, t1); // window and are clipped by TMA
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
-                        if (p.dual_acc) {                                       // + the small-products accumulator
-                            tmem_ld16(taddr + p.BN + c0, t0);
+                            for (int i = 0; i < 16; ++i) v[i] = fmaf(t1[i], p.small_scale, t0[i]);   // + the small-products accumulator
+                            if (second) {
+                                tmem_ld16x2(taddr + c0 + 16, taddr + p.BN + c0 + 16, t0, t1);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaf(t0[i], p.small_scale, v[i]);
-                            if (c0 + 16 < p.BN) {
-                                tmem_ld16(taddr + p.BN + c0 + 16, t1);
+                                for (int i = 0; i < 16; ++i) v[16 + i] = fmaf(t1[i], p.small_scale, t0[i]);
+                            } else {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) v[16 + i] = fmaf(t1[i], p.small_scale, v[16 + i]);
+                                for (int i = 0; i < 16; ++i) v[16 + i] = 0.f;
                             }
+                        } else {
+                            if (second) {
+                                tmem_ld16x2(taddr + c0, taddr + c0 + 16, t0, t1);
+                            } else {
+                                tmem_ld16(taddr + c0, t0);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) t1[i] = 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; }
                         }
                     }
                     if (p.flags & UF_BIAS) {
@@ -720,8 +762,8 @@ static int pick_bn(long long N, int max_bn = 256) {
     return best;
 }
 
-static int tmem_cols_for(int bn, int dual = 0) {
-    int need = (dual ? 4 : 2) * bn, c = 32;
+static int tmem_cols_for(int bn, int dual = 0, int bufs = 2) {
+    int need = (dual ? 2 : 1) * bufs * bn, c = 32;
     while (c < need) c <<= 1;
     return c;
 }
@@ -808,6 +850,11 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.mode = a_f16 ? 2 : (a_nplanes == 3 ? 1 : 0);
     p.small_scale = a_f16 ? F16_LO_INV : 1.0f;
     p.BN = pick_bn(N, (a_nplanes == 3 || a_f16) ? 128 : 256);                // two accumulators per tile: 4 * BN <= 512
+    p.acc_bufs = 2;
+    // fp16 pairs, wide layers: three products make a 128 x 128 tile L2-feed-bound (512 KB of operands per 10 k clk of
+    // MMAs); a 128 x 256 tile moves 25 % fewer bytes per flop.  Its two accumulators fill TMEM, so tiles are not
+    // double-buffered there.
+    if (a_f16 && N % 256 == 0 && K >= 256 && !(flags & UF_BIAS) && !getenv("AVR_UMMA_F16_BN128")) { p.BN = 256; p.acc_bufs = 1; }
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
     // long reductions into an fp32 output (the DFT and its adjoint, K = T or 2F): the accumulator is truncated once per
@@ -822,7 +869,7 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         p.k_splits = (int)splits;
     }
     p.dual_acc = (a_f16 || (p.na == 3 && p.nb == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
-    p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
+    p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc, p.acc_bufs);
     p.flags = flags;
     p.c = (__nv_bfloat16*)c_planes; p.ldc = ldc; p.c_plane = c_plane;
     p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
@@ -930,6 +977,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.BN = pick_bn(N, nplanes == 3 ? 128 : 256);                // two stages and two accumulators must fit
     p.na = na; p.nb = nb; p.nc = 2;
     p.fa = 0; p.fb = b_f16; p.kc = p.kc2 = AVR_PLANES_BF16x2;
+    p.acc_bufs = 2;
     p.mode = b_f16 ? (na == 3 ? 4 : 3) : (na == 3 ? 1 : 0);
     p.small_scale = b_f16 ? F16_LO_INV : 1.0f;
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
