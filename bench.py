@@ -98,7 +98,7 @@ def cpu_oracle_step_fn(cfg, bs, seed=0):
         net.zero_grad(set_to_none=True)
         out = ren(rx, tx, dtx)
         out.square().sum().backward()
-        return float(out[0, 0, 0])
+        return float(out.detach()[0, 0, 0])
     return step
 
 
@@ -213,7 +213,17 @@ def run_native(args, cfg):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)                        # NCCL prints its version banner on stdout when the communicator is
+        os.dup2(2, 1)                            # created: send it to stderr, stdout carries the one JSON line
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.load()
 
     cls = avr_b200.AVRModel if cfg["model_class"] == "AVRModel" else avr_b200.AVRModel_complex
@@ -329,7 +339,7 @@ def run_native(args, cfg):
                      "peak_source": pk["src"],
                      "note": "achieved = algorithmic flops (2MNK of the fp32-grade product) or bytes (SURVEY 8d) of the timed "
                              "launches / their CUDA-event time inside the timed region; each algorithmic product costs 3 "
-                             "(backward) or 6 (forward) bf16 tcgen05 products, see tensor_pipe_*"})
+                             "(backward bf16 pairs, forward fp16 pairs) or 6 (forward bf16 triples) tcgen05 products, see tensor_pipe_*"})
         cpu = None
         if not args.no_cpu_baseline:
             v, dt, desc = time_cpu_oracle(cfg, steps=1, warmup=1, ray_div=(4, 2))
