@@ -358,37 +358,46 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = bres ? bres_base + (uint32_t)(k0 / UBK) * b_tile_bytes : sa + a_tile_bytes;
                     const int k_steps = min(UBK / 16, (p.K - k0 + 15) / 16);    // the zero-filled tail of the last block is skipped
+                    // The single issuing thread must stay ahead of the tensor pipe (a 128 x 80 x 16 MMA retires in ~40 clk):
+                    // plane descriptors are built once per k-block, a k16 step only adds a constant to their address
+                    // field (32 B K-major, 2 KB MN-major, in 16-byte units), and each schedule is straight-line code.
+                    uint64_t a0, a1, a2 = 0, b0, b1, b2 = 0;                    // planes 0 (hi), 1, 2 of A and B
+                    if (!MN_MAJOR) {
+                        a0 = smem_desc(sa, 16, 1024); a1 = smem_desc(sa + A_PLANE_BYTES, 16, 1024);
+                        b0 = smem_desc(sb, 16, 1024); b1 = smem_desc(sb + b_plane_bytes, 16, 1024);
+                        if (p.mode == 1) { a2 = smem_desc(sa + 2 * A_PLANE_BYTES, 16, 1024); b2 = smem_desc(sb + 2 * b_plane_bytes, 16, 1024); }
+                    } else {
+                        a0 = smem_desc(sa, mn_blk_a, 1024); a1 = smem_desc(sa + 8192, mn_blk_a, 1024);
+                        b0 = smem_desc(sb, mn_blk_b, 1024); b1 = smem_desc(sb + 8192, mn_blk_b, 1024);
+                        if (p.mode == 1) { a2 = smem_desc(sa + 16384, mn_blk_a, 1024); b2 = smem_desc(sb + 16384, mn_blk_b, 1024); }
+                    }
+                    const uint64_t step = MN_MAJOR ? (2048u >> 4) : (32u >> 4);
+                    // Product schedules, smallest terms first.  With fp16 pairs the products that involve a lo' plane carry
+                    // a factor 2^11 and MUST go to the small accumulator (scaled back in the epilogue).  A and B share one
+                    // element format: tcgen05.mma raises an illegal-instruction fault on a bf16 x f16 mix.
+                    if (p.mode == 1) {          // bf16x3 . bf16x3: six products (fp32-grade pre-activations / ill-conditioned sums)
 #pragma unroll
-                    for (int j = 0; j < UBK / 16; ++j) {
-                        if (j >= k_steps) break;
-                        uint64_t da[3] = {0, 0, 0}, db[3] = {0, 0, 0};              // descriptors of planes 0 (hi), 1, 2
+                        for (int j = 0; j < UBK / 16; ++j) {
+                            if (j >= k_steps) break;
+                            const uint64_t o = step * j;
+                            umma_bf16(d_small, a2 + o, b0 + o, idesc, acc_small | (acc_main & shared_acc));
+                            umma_bf16(d_small, a0 + o, b2 + o, idesc, 1u);
+                            umma_bf16(d_small, a1 + o, b1 + o, idesc, 1u);
+                            umma_bf16(d_small, a1 + o, b0 + o, idesc, 1u);
+                            umma_bf16(d_small, a0 + o, b1 + o, idesc, 1u);
+                            umma_bf16(d_main, a0 + o, b0 + o, idesc, p.dual_acc ? acc_main : 1u);
+                            acc_small = acc_main = 1u;
+                        }
+                    } else {                    // bf16x2 . bf16x2 (16 bits; gradients) and f16x2 . f16x2 (24 bits): three products
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            if (!MN_MAJOR) {
-                                if (q < p.na) da[q] = smem_desc(sa + q * A_PLANE_BYTES + 32 * j, 16, 1024);
-                                if (q < p.nb) db[q] = smem_desc(sb + q * b_plane_bytes + 32 * j, 16, 1024);
-                            } else {
-                                if (q < p.na) da[q] = smem_desc(sa + q * 8192 + 2048 * j, mn_blk_a, 1024);
-                                if (q < p.nb) db[q] = smem_desc(sb + q * 8192 + 2048 * j, mn_blk_b, 1024);
-                            }
+                        for (int j = 0; j < UBK / 16; ++j) {
+                            if (j >= k_steps) break;
+                            const uint64_t o = step * j;
+                            umma_bf16(d_small, a1 + o, b0 + o, idesc, acc_small | (acc_main & shared_acc));
+                            umma_bf16(d_small, a0 + o, b1 + o, idesc, 1u);
+                            umma_bf16(d_main, a0 + o, b0 + o, idesc, p.dual_acc ? acc_main : 1u);
+                            acc_small = acc_main = 1u;
                         }
-#define AVR_SMALL(I, J) { umma_bf16(d_small, da[I], db[J], idesc, acc_small | (acc_main & shared_acc)); acc_small = 1u; }
-#define AVR_MAIN(I, J) { umma_bf16(d_main, da[I], db[J], idesc, acc_main | (acc_small & shared_acc)); acc_main = 1u; }
-                        // Product schedules, smallest terms first.  With fp16 pairs the products that involve a lo' plane
-                        // carry a factor 2^11 and MUST go to the small accumulator (scaled back in the epilogue).  A and B
-                        // share one element format: tcgen05.mma raises an illegal-instruction fault on a bf16 x f16 mix.
-                        switch (p.mode) {
-                        case 1:     // bf16x3 . bf16x3: six products (fp32-grade pre-activations / ill-conditioned sums)
-                            AVR_SMALL(2, 0) AVR_SMALL(0, 2) AVR_SMALL(1, 1)
-                            // fall through
-                        case 0:     // bf16x2 . bf16x2: three products (16 bits; gradients enter linearly)
-                        case 2:     // f16x2 . f16x2: three products, 24 bits: hi*lo' + lo'*hi scaled, hi*hi
-                        default:
-                            AVR_SMALL(1, 0) AVR_SMALL(0, 1) AVR_MAIN(0, 0)
-                            break;
-                        }
-#undef AVR_SMALL
-#undef AVR_MAIN
                     }
                     umma_commit(bar_empty + 8 * stage);                          // frees the stage when the MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
