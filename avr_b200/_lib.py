@@ -46,7 +46,7 @@ SIGNATURES = {
     "avr_sample_points": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_aux_inputs": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "avr_raygen_encode_fwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _I32, _P, C.c_int, _P]),
-    "avr_raygen_encode_bwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _I64, _I64, _I32, _P, _I32, _P, C.c_int, _P]),
+    "avr_raygen_encode_bwd": (C.c_int, [_G, _M, _P, _P, _P, _P, _I64, _I64, _I32, _P, _I32, _P, C.c_float, C.c_int, _P]),
     "avr_grid_encode_fwd": (C.c_int, [_M, _P, _I64, _P, _P, _I64, _I64, _I32, _I32, _I32, C.c_int, _P]),
     "avr_grid_encode_bwd": (C.c_int, [_M, _P, _I64, _P, _I64, _I64, _I32, _P, _I32, _P, C.c_int, _P]),
     "avr_absmax_bits": (C.c_int, [_P, _I64, _I64, _I64, _I32, _I32, _P, C.c_int, _P]),

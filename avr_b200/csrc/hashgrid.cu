@@ -171,6 +171,74 @@ __device__ __forceinline__ void scatter_level_f32(const GridDev& g, int l, float
     }
 }
 
+// Coarse levels: consecutive samples of a ray (= consecutive lanes) stay in one cell for several steps, so runs of
+// adjacent lanes add to the SAME table entry.  A segmented shuffle reduction sums each run and only its first lane issues
+// the RED: the LSU takes a RED one lane-packet at a time (the kernel's bound), a run of 13 lanes at level 0 costs one.
+// Every lane of the warp must call this (inactive lanes pass ok = false).
+__device__ __forceinline__ void scatter_level_f32_merged(const GridDev& g, int l, float ux, float uy, float uz, float g0,
+                                                         float g1, bool ok, float* __restrict__ grad) {
+    const Cell c = locate(g.scale[l], ux, uy, uz);
+    const uint32_t res = g.res[l], size = g.size[l];
+    float* base = grad + 2ull * g.offset[l];
+    const uint32_t kind = g.kind[l];
+    const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
+        uint32_t idx = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
+                                                                                     : grid_index(cx, cy, cz, res, size);
+        if (!ok) idx = 0xFFFFFFFFu;                                       // never equal to a valid neighbour's index
+        const float w = corner_weight(c, k);
+        float v0 = ok ? __fmul_rn(w, g0) : 0.f, v1 = ok ? __fmul_rn(w, g1) : 0.f;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
+        const bool head = lane == 0 || prev != idx;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t after = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));   // bit j: lane + 1 + j starts a new run
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float o0 = __shfl_down_sync(0xffffffffu, v0, d), o1 = __shfl_down_sync(0xffffffffu, v1, d);
+            if (lane + d < 32 && (after & ((1u << d) - 1u)) == 0u) { v0 += o0; v1 += o1; }
+        }
+        if (head && ok)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(base + 2ull * idx), "f"(v0), "f"(v1) : "memory");
+    }
+}
+
+// the same for the deterministic mode: 2^e-scaled int64 addends (integer sums are exact, so merging keeps the result
+// bit-identical to the unmerged scatter)
+__device__ __forceinline__ void scatter_level_i64_merged(const GridDev& g, int l, float ux, float uy, float uz, float g0,
+                                                         float g1, float sc, bool ok, unsigned long long* __restrict__ acc) {
+    const Cell c = locate(g.scale[l], ux, uy, uz);
+    const uint32_t res = g.res[l], size = g.size[l];
+    unsigned long long* base = acc + 2ull * g.offset[l];
+    const uint32_t kind = g.kind[l];
+    const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
+        uint32_t idx = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
+                                                                                     : grid_index(cx, cy, cz, res, size);
+        if (!ok) idx = 0xFFFFFFFFu;
+        const float w = corner_weight(c, k);
+        long long q0 = ok ? __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc)) : 0ll;
+        long long q1 = ok ? __float2ll_rn(__fmul_rn(__fmul_rn(w, g1), sc)) : 0ll;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
+        const bool head = lane == 0 || prev != idx;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t after = lane == 31 ? 0xffffffffu : (heads >> (lane + 1));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o0 = __shfl_down_sync(0xffffffffu, q0, d), o1 = __shfl_down_sync(0xffffffffu, q1, d);
+            if (lane + d < 32 && (after & ((1u << d) - 1u)) == 0u) { q0 += o0; q1 += o1; }
+        }
+        if (head && ok) {
+            unsigned long long* dst = base + 2ull * idx;
+            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(dst), "l"(q0) : "memory");
+            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(dst + 1), "l"(q1) : "memory");
+        }
+    }
+}
+
 // unit-cube position of sample n=(b,r,s); optionally its tx delay
 __device__ __forceinline__ void sample_unit(const Geom& geo, int64_t n, const float* __restrict__ rays_o,
                                             const float* __restrict__ dirs, const float* __restrict__ d_vals,
@@ -238,7 +306,8 @@ __global__ void __launch_bounds__(ENC_PTS* ENC_LG)
 encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t n_pts, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ d_vals, const float* __restrict__ u_in,
                   const void* __restrict__ d_out_v, int64_t ld_out, int64_t d_plane, int col0,
-                  const uint32_t* __restrict__ gmax_bits, int headroom, unsigned long long* __restrict__ acc) {
+                  const uint32_t* __restrict__ gmax_bits, int headroom, unsigned long long* __restrict__ acc,
+                  int merge_levels) {
     extern __shared__ float tile[];
     float sc = 1.f;
     if (!F32ACC) {
@@ -267,18 +336,27 @@ encode_bwd_kernel(const Geom geo, const __grid_constant__ GridDev grid, int64_t 
     }
     __syncthreads();
     const int64_t n = n0 + p;
-    if (n >= n_pts) return;
-    float ux, uy, uz;
-    if (RAYGEN) {
-        float nx, ny, nz;
-        int b;
-        sample_unit(geo, n, rays_o, dirs, d_vals, ux, uy, uz, nx, ny, nz, b);
-    } else {
-        ux = __ldg(u_in + 3 * n + 0); uy = __ldg(u_in + 3 * n + 1); uz = __ldg(u_in + 3 * n + 2);
+    const bool active = n < n_pts;
+    if (!active && merge_levels == 0) return;                 // the merged levels need whole warps
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (active) {
+        if (RAYGEN) {
+            float nx, ny, nz;
+            int b;
+            sample_unit(geo, n, rays_o, dirs, d_vals, ux, uy, uz, nx, ny, nz, b);
+        } else {
+            ux = __ldg(u_in + 3 * n + 0); uy = __ldg(u_in + 3 * n + 1); uz = __ldg(u_in + 3 * n + 2);
+        }
     }
     for (int l = lg; l < grid.n_levels; l += ENC_LG) {
-        const float g0 = tile[p * Wp + 2 * l], g1 = tile[p * Wp + 2 * l + 1];
-        if (g0 == 0.f && g1 == 0.f) continue;
+        const float g0 = active ? tile[p * Wp + 2 * l] : 0.f, g1 = active ? tile[p * Wp + 2 * l + 1] : 0.f;
+        const bool ok = active && !(g0 == 0.f && g1 == 0.f);
+        if (l < merge_levels) {                               // warp-uniform: l depends on threadIdx.y only
+            if (F32ACC) scatter_level_f32_merged(grid, l, ux, uy, uz, g0, g1, ok, reinterpret_cast<float*>(acc));
+            else scatter_level_i64_merged(grid, l, ux, uy, uz, g0, g1, sc, ok, acc);
+            continue;
+        }
+        if (!ok) continue;
         if (F32ACC) scatter_level_f32(grid, l, ux, uy, uz, g0, g1, reinterpret_cast<float*>(acc));
         else scatter_level(grid, l, ux, uy, uz, g0, g1, sc, acc);
     }
@@ -442,7 +520,7 @@ extern "C" int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, in
 static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* grid, int64_t n_pts, const float* rays_o,
                              const float* dirs, const float* d_vals, const float* u, const void* d_out, int64_t ld_out,
                              int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t headroom, void* acc,
-                             void* stream) {
+                             float sample_step, void* stream) {
     if (int rc = check_grid(grid)) return rc;
     const bool f32acc = headroom == AVR_GRID_GRAD_F32;
     AVR_REQUIRE(d_out && acc && (gmax_bits || f32acc), "null d_out/gmax/acc");
@@ -454,10 +532,19 @@ static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
     const size_t smem = (size_t)ENC_PTS * (W | 1) * sizeof(float);
     const dim3 block(ENC_PTS, ENC_LG);
     const unsigned blocks = (unsigned)ceil_div(n_pts, ENC_PTS);
+    // Leading levels whose cells hold >= 2 consecutive samples of a ray on average get the run-merging scatter
+    // (ray-generation mode: consecutive points are consecutive samples, `sample_step` apart in unit-cube coordinates).
+    int merge_levels = 0;
+    if (raygen && sample_step > 0.f) {
+        for (int l = 0; l < grid->n_levels && grid->scale[l] * sample_step < 0.5f; ++l) merge_levels = l + 1;
+        if (const char* e = getenv("AVR_SCATTER_MERGE_LEVELS")) merge_levels = atoi(e);      // A/B measurements
+        if (merge_levels > grid->n_levels) merge_levels = grid->n_levels;
+        if (merge_levels < 0) merge_levels = 0;
+    }
     auto launch = [&](auto kernel) -> int {
         AVR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<blocks, block, smem, (cudaStream_t)stream>>>(geo, gd, n_pts, rays_o, dirs, d_vals, u, d_out, ld_out, d_plane,
-                                                             col0, gmax_bits, headroom, (unsigned long long*)acc);
+                                                             col0, gmax_bits, headroom, (unsigned long long*)acc, merge_levels);
         return AVR_OK;
     };
     int rc;
@@ -471,12 +558,12 @@ static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
 extern "C" int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
                                      const float* dirs, const float* d_vals, const void* d_out, int64_t ld_out,
                                      int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom,
-                                     void* acc, int device, void* stream) {
+                                     void* acc, float sample_step, int device, void* stream) {
     AVR_REQUIRE(geom && rays_o && dirs && d_vals, "null input");
     AVR_ENTER(device);
     const Geom geo = make_geom(geom);
     return encode_bwd_common(true, geo, grid, (int64_t)geo.bs * geo.R * geo.S, rays_o, dirs, d_vals, nullptr, d_out,
-                             ld_out, d_plane, col0, gmax_bits, log2_headroom, acc, stream);
+                             ld_out, d_plane, col0, gmax_bits, log2_headroom, acc, sample_step, stream);
 }
 
 extern "C" int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const void* d_out,
@@ -486,7 +573,7 @@ extern "C" int avr_grid_encode_bwd(const avr_grid_meta* grid, const float* u, in
     AVR_ENTER(device);
     Geom geo = {};
     return encode_bwd_common(false, geo, grid, n_pts, nullptr, nullptr, nullptr, u, d_out, ld_out, d_plane, col0,
-                             gmax_bits, log2_headroom, acc, stream);
+                             gmax_bits, log2_headroom, acc, 0.f, stream);
 }
 
 extern "C" int avr_absmax_bits(const void* x, int64_t rows, int64_t ld, int64_t plane, int32_t col0, int32_t ncols,

@@ -139,7 +139,7 @@ class FusedRenderFunction(torch.autograd.Function):
                 if kind == "point":
                     acc = ops.GridGradAccumulator(mod.meta, dev, n_rows, scratch, mod.grid_grad)
                     acc.observe(d_buf, col, wdt)
-                    acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col)
+                    acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col, sample_step=tables.get("sample_step", 0.0))
                 else:
                     small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
                     acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch, mod.grid_grad)

@@ -258,7 +258,8 @@ class GridGradAccumulator:
         _lib.check(_lib.load().avr_absmax_bits(ptr, _rows(d_out), ld, plane, col0, ncols, _p(self.gmax, torch.int32),
                                                dev, st), "avr_absmax_bits")
 
-    def add_rays(self, g, rays_o, dirs, d_vals, d_out, col0=0):
+    def add_rays(self, g, rays_o, dirs, d_vals, d_out, col0=0, sample_step=0.0):
+        """``sample_step``: spacing of a ray's samples in unit-cube coordinates (0: unknown), see avr_raygen_encode_bwd."""
         dev, st = _ctx(d_out)
         ptr, ld, plane = _mat(d_out)
         n_pts = g.bs * g.R * g.S
@@ -267,7 +268,8 @@ class GridGradAccumulator:
             _lib.check(_lib.load().avr_raygen_encode_bwd(C.byref(g), C.byref(self.meta), _p(_dense(rays_o)),
                                                          _p(_dense(dirs)), _p(_dense(d_vals)), ptr, ld, plane, col0,
                                                          _p(self.gmax, torch.int32), self.headroom,
-                                                         C.c_void_p(self.acc.data_ptr()), dev, st), "avr_raygen_encode_bwd")
+                                                         C.c_void_p(self.acc.data_ptr()), float(sample_step), dev, st),
+                       "avr_raygen_encode_bwd")
 
     def add_points(self, u, d_out, col0=0):
         dev, st = _ctx(d_out)

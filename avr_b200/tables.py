@@ -73,10 +73,13 @@ class RenderTables:
         phase = torch.exp(-1j * 2 * np.pi / T * torch.arange(0, F).unsqueeze(0) * tau.unsqueeze(1))   # :108
         delta = torch.cat([d[1:] - d[:-1], torch.tensor([1e10])])                # :185-186
         self.T, self.F, self.S = T, F, S
+        #: spacing of a ray's samples in unit-cube coordinates (avr_raygen_encode_bwd's run-merging scatter)
+        self.sample_step = float(far - near) / max(1, S - 1) / float(cfg["xyz_max"] - cfg["xyz_min"])
         self.host = {"d": d, "tau": tau, "shift": shift, "pl": pl, "delta": delta}
         self.dev = {
             "d": d.to(device), "delta": delta.to(device),
             "gain": gain.float().contiguous().to(device),
             "phase": torch.view_as_real(phase.to(torch.complex64)).contiguous().to(device),
             "dft": dft_matrix(T).to(device),
+            "sample_step": self.sample_step,
         }

@@ -118,12 +118,16 @@ AVR_API int avr_raygen_encode_fwd(const avr_render_geom* geom, const avr_grid_me
  *     same gmax_bits); gmax_bits is a device uint32 filled by avr_absmax_bits; avr_grid_grad_finalize converts.
  *   log2_headroom == AVR_GRID_GRAD_F32  acc[total*2] is the fp32 gradient itself (zeroed, or a partial sum); one
  *     red.global.add.v2.f32 per cell corner (half the reductions of the int64 mode, summation order -- and
- *     so the last bits -- vary from run to run, as in tcnn); gmax_bits is ignored and may be NULL. */
+ *     so the last bits -- vary from run to run, as in tcnn); gmax_bits is ignored and may be NULL.
+ * sample_step (ray-generation entry): distance between consecutive samples of a ray in unit-cube
+ * coordinates, (far - near) / (S - 1) / (xyz_max - xyz_min), or 0 if unknown.  On the leading levels whose cells hold
+ * two or more consecutive samples, runs of adjacent points that add to the same entry are summed with warp shuffles
+ * and issue one reduction. */
 #define AVR_GRID_GRAD_F32 (-1)
 AVR_API int avr_raygen_encode_bwd(const avr_render_geom* geom, const avr_grid_meta* grid, const float* rays_o,
                           const float* dirs, const float* d_vals, const void* d_out, int64_t ld_out,
                           int64_t d_plane, int32_t col0, const uint32_t* gmax_bits, int32_t log2_headroom, void* acc,
-                          int device, void* stream);
+                          float sample_step, int device, void* stream);
 
 /* Encode explicit unit-cube points u[N,3] (model.py:191,219-220 on arbitrary inputs). */
 AVR_API int avr_grid_encode_fwd(const avr_grid_meta* grid, const float* u, int64_t n_pts, const float* table,

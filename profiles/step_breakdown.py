@@ -1,5 +1,5 @@
 """Per-call CUDA-event timing of one simu render step (fwd+bwd, 4 receivers) in call order: every timed op of
-avr_b200.ops with its work and rate.   python profiles/step_breakdown.py [config] [bs]"""
+avr_b200.ops with its work and rate.   python profiles/step_breakdown.py [config] [bs] [atomic|deterministic]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,7 +17,7 @@ with torch.no_grad():
         if "encoding" in n:
             p.normal_(0, 0.1)
 r = cfg["render"]
-ren = avr_b200.AVRRender(net, **r)
+ren = avr_b200.AVRRender(net, **r, grid_grad=(sys.argv[3] if len(sys.argv) > 3 else None))
 c = (r["xyz_min"] + r["xyz_max"]) / 2
 gen = torch.Generator().manual_seed(0)
 rx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 2).to(DEV); tx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 2).to(DEV)
