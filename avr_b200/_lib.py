@@ -70,6 +70,7 @@ SIGNATURES = {
     "avr_collapse_bwd": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _I64, _P, _I64, _I64,
                                    _P, _P, _I64, C.c_int, C.c_int, _P]),
     "avr_rows_broadcast": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I64, _I64, _I32, _I32, C.c_int, _P]),
+    "avr_rows_broadcast2": (C.c_int, [_G, _P, _I32, C.c_int, _P, _I32, C.c_int, _P, _I64, _I64, _I32, _I32, C.c_int, _P]),
     "avr_rows_block_sum": (C.c_int, [_G, _P, _I64, _I64, _I32, _P, C.c_int, _P]),
     "avr_rows_reduce_workspace_bytes": (_I64, [_G, _I32, C.c_int]),
     "avr_rows_reduce": (C.c_int, [_G, _P, _I64, _I64, _I32, _I32, C.c_int, _P, _P, _I64, C.c_int, _P]),

@@ -333,19 +333,24 @@ __global__ void rows_broadcast_kernel(const Geom geo, const float* __restrict__ 
     else planes_store(dst_v, o, dst_plane, dst_np, v);
 }
 
-// plane-set destination, 8 columns (one 16-byte store per plane) per thread
+// plane-set destination, 8 columns (one 16-byte store per plane) per thread.  Two adjacent blocks (src, then src2) can be
+// written by one launch: a 40-column block is 2.5 sectors per plane row, two of them side by side are whole sectors.
 __global__ void rows_broadcast_planes8_kernel(const Geom geo, const float* __restrict__ src, int w, int per_receiver,
+                                              const float* __restrict__ src2, int w2, int per_receiver2,
                                               __nv_bfloat16* __restrict__ db, int64_t ld_dst, int64_t dst_plane, int dst_np,
                                               int col0) {
-    const int groups = w >> 3;
+    const int groups = (w + w2) >> 3, g1 = w >> 3;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_pts = (int64_t)geo.bs * geo.R * geo.S;
     if (i >= n_pts * groups) return;
     const int64_t n = i / groups;
     const int g = (int)(i - n * groups);
-    const int64_t row = per_receiver ? n / ((int64_t)geo.R * geo.S) : (n / geo.S) % geo.R;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src + row * w + 8 * g));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(src + row * w + 8 * g) + 1);
+    const bool second = g >= g1;
+    const bool rcv = second ? per_receiver2 != 0 : per_receiver != 0;
+    const int64_t row = rcv ? n / ((int64_t)geo.R * geo.S) : (n / geo.S) % geo.R;
+    const float* sp = second ? src2 + row * w2 + 8 * (g - g1) : src + row * w + 8 * g;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(sp));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(sp) + 1);
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t h[4], m[4], l[4];
 #pragma unroll
@@ -610,10 +615,29 @@ extern "C" int avr_rows_broadcast(const avr_render_geom* geom, const float* src,
     if (total == 0) return AVR_OK;
     if (dst_plane != 0 && w % 8 == 0 && col0 % 8 == 0 && ld_dst % 8 == 0 && dst_plane % 8 == 0 && aligned16(dst) && aligned16(src))
         rows_broadcast_planes8_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-            geo, src, w, per_receiver, (__nv_bfloat16*)dst, ld_dst, dst_plane, dst_nplanes, col0);
+            geo, src, w, per_receiver, nullptr, 0, 0, (__nv_bfloat16*)dst, ld_dst, dst_plane, dst_nplanes, col0);
     else
         rows_broadcast_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(geo, src, w, per_receiver, dst,
                                                                                              ld_dst, dst_plane, dst_nplanes, col0);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+// two adjacent column blocks in one launch: dst[n, col0:col0+w] = src[row(n)], dst[n, col0+w:col0+w+w2] = src2[row2(n)]
+extern "C" int avr_rows_broadcast2(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,
+                                   const float* src2, int32_t w2, int per_receiver2, void* dst, int64_t ld_dst,
+                                   int64_t dst_plane, int32_t dst_nplanes, int32_t col0, int device, void* stream) {
+    AVR_REQUIRE(geom && src && src2 && dst, "null pointer");
+    AVR_REQUIRE(w > 0 && w2 > 0 && col0 >= 0 && ld_dst >= col0 + w + w2, "bad column window");
+    AVR_REQUIRE(dst_plane != 0 && w % 8 == 0 && w2 % 8 == 0 && col0 % 8 == 0 && ld_dst % 8 == 0 && dst_plane % 8 == 0 &&
+                aligned16(dst) && aligned16(src) && aligned16(src2) && planes_kind_ok(dst_nplanes),
+                "the two-block broadcast writes plane sets in 8-column groups");
+    AVR_ENTER(device);
+    const Geom geo = make_geom(geom);
+    const int64_t total = (int64_t)geo.bs * geo.R * geo.S * (w + w2);
+    if (total == 0) return AVR_OK;
+    rows_broadcast_planes8_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        geo, src, w, per_receiver, src2, w2, per_receiver2, (__nv_bfloat16*)dst, ld_dst, dst_plane, dst_nplanes, col0);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

@@ -59,27 +59,39 @@ def _assemble(segments, buf: PlanePair, col, end_col, geom, small_in, rays_o, po
     dev = rays_o.device
     if not segments and end_col > col:
         segments = [(None, "ones")]
+    pending = None                                       # (small table, per_receiver, column) of a broadcast not yet written
     for k, (mod, kind) in enumerate(segments):
         w = mod.n_output_dims if mod is not None else 0
         last = k == len(segments) - 1
         n_ones = end_col - (col + w) if last else 0
+        small = None
         if kind == "point":
             delay = delay_slot.pop() if delay_slot else None
             ops.raygen_encode_fwd(geom, mod.meta, rays_o, pos_tx, dirs, d_vals, params_of(mod), buf, col0=col,
                                   n_ones=n_ones, delay=delay)
+        elif kind == "receiver_rows":                                        # channel-embedding rows (model.py:201-203)
+            small, per_rcv = rows_of[mod.key], True
+        elif kind != "ones":
+            u = small_in[kind]
+            small = torch.empty(u.shape[0], w, device=dev)
+            ops.grid_encode_fwd(mod.meta, u, params_of(mod), small)
+            per_rcv = kind != "ray"
+        # adjacent broadcast blocks go out in pairs: one launch, whole sectors (a 40-column block alone ends mid-sector)
+        if small is not None and pending is not None and small.shape[1] % 8 == 0 and pending[0].shape[1] % 8 == 0 \
+                and pending[2] % 8 == 0:
+            ops.rows_broadcast2(geom, pending[0], pending[1], small, per_rcv, buf, pending[2])
+            pending = None
         else:
-            if kind == "receiver_rows":                                      # channel-embedding rows (model.py:201-203)
-                ops.rows_broadcast(geom, rows_of[mod.key], True, buf, col)
-            elif kind != "ones":
-                u = small_in[kind]
-                small = torch.empty(u.shape[0], w, device=dev)
-                ops.grid_encode_fwd(mod.meta, u, params_of(mod), small)
-                ops.rows_broadcast(geom, small, kind != "ray", buf, col)
-            if n_ones:                                                       # tcnn pads the network input with ones
-                c0 = buf.col0 + col + w
-                buf.buf[0, :, c0:c0 + n_ones] = 1.0
-                buf.buf[1:, :, c0:c0 + n_ones] = 0.0
+            if pending is not None:
+                ops.rows_broadcast(geom, pending[0], pending[1], buf, pending[2])
+            pending = (small, per_rcv, col) if small is not None else None
+        if kind != "point" and n_ones:                                       # tcnn pads the network input with ones
+            c0 = buf.col0 + col + w
+            buf.buf[0, :, c0:c0 + n_ones] = 1.0
+            buf.buf[1:, :, c0:c0 + n_ones] = 0.0
         col += w
+    if pending is not None:
+        ops.rows_broadcast(geom, pending[0], pending[1], buf, pending[2])
     return col
 
 

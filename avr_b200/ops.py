@@ -446,6 +446,15 @@ def rows_broadcast(g, src, per_receiver, dst, col0):
                                               ptr, ld, plane, _np(dst), col0, dev, st), "avr_rows_broadcast")
 
 
+def rows_broadcast2(g, src, per_receiver, src2, per_receiver2, dst: PlanePair, col0):
+    """Two adjacent column blocks of a plane set in one launch (whole sectors instead of two half-written ones)."""
+    dev, st = _ctx(dst)
+    ptr, ld, plane = _mat(dst)
+    _lib.check(_lib.load().avr_rows_broadcast2(C.byref(g), _p(_dense(src)), src.shape[1], 1 if per_receiver else 0,
+                                               _p(_dense(src2)), src2.shape[1], 1 if per_receiver2 else 0,
+                                               ptr, ld, plane, _np(dst), col0, dev, st), "avr_rows_broadcast2")
+
+
 def rows_block_sum(g, x):
     """-> fp32 ``[bs*R, w]``: sum over the S sample rows of every (receiver, ray) of ``x`` (fp32 2-D or PlanePair)."""
     dev, st = _ctx(x)

@@ -250,6 +250,11 @@ AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes
 AVR_API int avr_rows_broadcast(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,
                        void* dst, int64_t ld_dst, int64_t dst_plane, int32_t dst_nplanes, int32_t col0, int device,
                        void* stream);
+/* two adjacent column blocks in one launch (plane-set destinations; whole 32-byte sectors where one 40-column block
+ * alone leaves half-written ones): dst[n, col0:col0+w] = src[row(n)], dst[n, col0+w:col0+w+w2] = src2[row2(n)] */
+AVR_API int avr_rows_broadcast2(const avr_render_geom* geom, const float* src, int32_t w, int per_receiver,
+                        const float* src2, int32_t w2, int per_receiver2, void* dst, int64_t ld_dst, int64_t dst_plane,
+                        int32_t dst_nplanes, int32_t col0, int device, void* stream);
 /* transpose of the above: d_src[row, :] = sum over the points mapped to `row` (fixed order). */
 /* partial[(b*R + r), 0:w] = sum over the S sample rows of (b, r) of x (fp32, or plane set: first two planes) */
 AVR_API int avr_rows_block_sum(const avr_render_geom* geom, const void* x, int64_t ldx, int64_t x_plane, int32_t w,
