@@ -162,6 +162,18 @@ def test_raygen_encode_matches_explicit_points(built_library):
     acc = ops.GridGradAccumulator(meta, DEV, n)
     acc.observe(dbuf, 0, W)
     acc.add_rays(geom, rx.to(DEV), dirs.to(DEV), tab["d"].to(DEV), dbuf, 0)
+    plain = acc.finalize().cpu()
+    assert rel_l2(plain, enc.params.grad) < 1e-5
+    # run merging (avr_raygen_encode_bwd's sample_step): consecutive samples of a ray that add to the same coarse-level
+    # entry are summed with warp shuffles and issue one reduction.  Integer addends: bit-identical to the plain scatter.
+    step = float(r["far"] - r["near"]) / (r["n_samples"] - 1) / float(r["xyz_max"] - r["xyz_min"])
+    assert step * meta.scale[0] < 0.5                                             # at least the coarsest level merges
+    acc = ops.GridGradAccumulator(meta, DEV, n)
+    acc.observe(dbuf, 0, W)
+    acc.add_rays(geom, rx.to(DEV), dirs.to(DEV), tab["d"].to(DEV), dbuf, 0, sample_step=step)
+    assert torch.equal(acc.finalize().cpu(), plain)
+    acc = ops.GridGradAccumulator(meta, DEV, n, mode="atomic")
+    acc.add_rays(geom, rx.to(DEV), dirs.to(DEV), tab["d"].to(DEV), dbuf, 0, sample_step=step)
     assert rel_l2(acc.finalize(), enc.params.grad) < 1e-5
 
 
