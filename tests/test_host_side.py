@@ -154,3 +154,28 @@ def test_grad_arena_views_and_rebind():
     assert torch.equal(arena.flat[8:17], torch.full((9,), 3.0))
     arena.zero_()
     assert float(arena.flat.abs().sum()) == 0 and p2.grad.data_ptr() == arena.flat[8:].data_ptr()
+
+
+def test_plane_set_kinds_and_sample_step(built_library):
+    """Host-side description of the tensor-core operands (include/avr_b200.h, plane-set kinds) and of the scatter's
+    run-merging hint."""
+    from avr_b200 import ops
+    header = open(os.path.join(ROOT, "include", "avr_b200.h")).read()
+    kinds = dict(re.findall(r"(AVR_PLANES_\w+)\s*=\s*(\d+)", header))
+    assert (int(kinds["AVR_PLANES_BF16x2"]), int(kinds["AVR_PLANES_BF16x3"]), int(kinds["AVR_PLANES_F16x2"])) == \
+        (ops.PLANES_BF16x2, ops.PLANES_BF16x3, ops.PLANES_F16x2)
+    flags = dict(re.findall(r"(AVR_UMMA_\w+)\s*=\s*(\d+)", header))
+    assert int(flags["AVR_UMMA_DUAL_COPY"]) == ops.UMMA_DUAL_COPY and int(flags["AVR_UMMA_BIAS"]) == ops.UMMA_BIAS
+    a = ops.PlanePair.empty(10, 20, "cpu", n=3)
+    b = ops.PlanePair.empty(10, 20, "cpu", kind=ops.PLANES_F16x2)
+    assert (a.kind, a.n, a.f16, a.ld) == (3, 3, False, 24) and (b.kind, b.n, b.f16) == (ops.PLANES_F16x2, 2, True)
+    assert b.window(8, 8).cols == 8 and b.window(8, 8).kind == ops.PLANES_F16x2
+    with pytest.raises(AssertionError):
+        ops.PlanePair(torch.empty(3, 4, 8, dtype=torch.float16))           # fp16 sets are pairs
+    cfg = get_config("simu")["render"]
+    t = tables.RenderTables(cfg, 1600, "cpu")
+    step = (cfg["far"] - cfg["near"]) / (cfg["n_samples"] - 1) / (cfg["xyz_max"] - cfg["xyz_min"])
+    assert abs(t.sample_step - step) < 1e-12 and t.dev["sample_step"] == t.sample_step
+    # levels whose cells hold >= 2 consecutive samples (scale * step < 0.5) get the merged scatter: 0..2 at simu
+    geo = field_ref.hashgrid_geometry(get_config("simu")["model"]["pos_encoding_sigma"])
+    assert sum(1 for s in geo["scale"] if s * step < 0.5) == 3
