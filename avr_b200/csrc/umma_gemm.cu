@@ -3,19 +3,21 @@
 // Replaces the tiny-cuda-nn FullyFusedMLP / CutlassMLP kernels of model.py:117,146,176 (and their backward).
 // tcnn computes in fp16 with fp16 accumulators; the parity target here is the fp32 oracle (1e-4 rel-L2 on
 // the IR and on every parameter gradient), which single-pass bf16/tf32 products cannot meet.  Operands are
-// therefore stored as an error-compensated PAIR of bf16 planes, x = hi + lo with hi = bf16(x),
-// lo = bf16(x - hi) (16 mantissa bits, the same 4 bytes/element as fp32), and every product is evaluated as
-//        A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (three tcgen05.mma into one fp32 TMEM accumulator)
-// which leaves a relative error of ~2^-17 per product -- fp32-grade for this network -- at 1/3 of the bf16
-// tensor rate instead of the ~1/50 an fp32 SIMT GEMM gets.
+// therefore error-compensated SETS of 16-bit planes (include/avr_b200.h, plane-set kinds):
+//   bf16 pair    x = hi + mid                  A*B ~= hi*hi + hi*mid + mid*hi                 (16 bits: gradients)
+//   bf16 triple  x = hi + mid + lo             + hi*lo + lo*hi + mid*mid                      (24 bits: forward)
+//   fp16 pair    x = hi + lo' * 2^-11          hi*hi  +  2^-11 * (hi*lo' + lo'*hi)            (24 bits in fp16's range)
+// Each tcgen05.mma truncates the fp32 accumulator once, so the 24-bit modes keep TWO accumulators per tile in TMEM --
+// hi*hi in one, the small products in the other -- and the epilogue adds them (scaled for fp16 pairs).
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of both planes of the A and B tiles into
+// Kernel anatomy (one persistent CTA per SM, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) of every plane of the A and B tiles into
 //               a ring of shared-memory stages, completion on mbarriers
-//   warp 1      TMEM allocator + MMA issuer: one elected lane issues 12 tcgen05.mma (4 k16 steps x 3 products)
-//               per 64-wide k-block, tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's MMAs
-//               overlap), apply mask / accumulate / ReLU, split into hi/lo planes (or write fp32), store
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues the 3 or 6 tcgen05.mma of every k16 step
+//               (descriptors built once per 64-wide k-block), tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-9   epilogue, one or two warps per TMEM lane group: tcgen05.ld the accumulators (double-buffered in TMEM
+//               so the next tile's MMAs overlap), apply bias / mask / accumulate / ReLU, split into planes of the
+//               output kind (or write fp32), stage in swizzled shared memory, TMA-store
 // Two operand modes: K-major x K-major (forward, backward-data with a pre-transposed weight) and
 // MN-major x MN-major with split-K over the sample points (weight gradients, deterministic second pass).
 #include <cuda.h>

@@ -3,8 +3,9 @@
 Same contract as ``fused.FusedRenderFunction`` (SURVEY 8a rows a1-a11 in one autograd node) with two
 B200-first changes:
 
-* every activation is an error-compensated bf16 hi/lo plane pair and every dense layer runs on
-  ``tcgen05.mma`` with TMEM accumulators (``csrc/umma_gemm.cu``): fp32-grade accuracy at tensor-core rate;
+* every activation is an error-compensated set of 16-bit planes (bf16 triples / pairs, fp16 pairs: DESIGN.md 4) and
+  every dense layer runs on ``tcgen05.mma`` with TMEM accumulators (``csrc/umma_gemm.cu``): fp32-grade accuracy at
+  tensor-core rate;
 * the ``width -> T`` output layer of the signal network is never evaluated per sample point: it is fused with
   the delay-masked ray reduction as a prefix sum over delay-sorted rays (``csrc/collapse.cu``), so the
   ``[bs,R,S,T]`` signal tensor and its gradient (0.84 GB / receiver each at simu) do not exist.

@@ -45,7 +45,7 @@ class AVRRender(nn.Module):
         self.xyz_max = kwargs["xyz_max"]
         #: receivers rendered per kernel pass (bounds the activation memory of large inference batches)
         self.max_receivers_per_pass = int(kwargs.get("max_receivers_per_pass", 8))
-        #: "tc": dense layers on tcgen05 tensor cores (3 x bf16 error-compensated) + collapsed output layer;
+        #: "tc": dense layers on tcgen05 tensor cores (error-compensated 16-bit plane sets) + collapsed output layer;
         #: "simt": exact-fp32 FMA GEMMs and the literal signal tensor (slower; kept as an independent check)
         self.dense = kwargs.get("dense", "tc")
         if self.dense not in ("tc", "simt"):
