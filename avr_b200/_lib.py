@@ -10,6 +10,7 @@ import ctypes as C
 import os
 
 MAX_LEVELS = 32
+ABI_VERSION = 2
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libavr_b200.so")
 
 GEMM_RELU, GEMM_ACCUM, GEMM_MASK, GEMM_RELU_A, GEMM_RELU_B = 1, 2, 4, 8, 16
@@ -31,7 +32,7 @@ class GridMeta(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("n_feat", C.c_int32),
                 ("scale", C.c_float * MAX_LEVELS), ("res", C.c_uint32 * MAX_LEVELS),
                 ("size", C.c_uint32 * MAX_LEVELS), ("offset", C.c_uint32 * MAX_LEVELS),
-                ("total", C.c_uint32)]
+                ("total", C.c_uint32), ("stride32", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -118,7 +119,7 @@ def load() -> C.CDLL:
         except AttributeError as exc:
             raise AVRLibraryError(f"{LIB_PATH} does not export {name}") from exc
         fn.restype, fn.argtypes = res, args
-    if lib.avr_abi_version() != 1:
+    if lib.avr_abi_version() != ABI_VERSION:
         raise AVRLibraryError("libavr_b200.so ABI version mismatch")
     _lib = lib
     return lib

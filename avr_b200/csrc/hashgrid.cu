@@ -20,10 +20,20 @@ struct GridDev {
     uint32_t res[AVR_MAX_LEVELS];
     uint32_t size[AVR_MAX_LEVELS];
     uint32_t offset[AVR_MAX_LEVELS];
-    uint32_t kind[AVR_MAX_LEVELS];     // 0: generic index arithmetic, 1: dense level (res^3 <= size), 2: hashed, size = 2^k
+    // 0: generic (strides below, optional hash, % size)   1: dense level (res^3 <= size)
+    // 2: hashed, size = 2^k (mask)                          3: NOT hashed, size = 2^k: (x + y*s1 + z*s2) & (size - 1)
+    uint32_t kind[AVR_MAX_LEVELS];
+    uint32_t s1[AVR_MAX_LEVELS], s2[AVR_MAX_LEVELS];   // dense-index strides of y and z (0: dimension not reached / wrapped)
+    uint32_t hashed[AVR_MAX_LEVELS];
     int pair;                          // 16-byte accesses to x-neighbour entry pairs are aligned (even offsets, aligned base)
 };
 
+// tiny-cuda-nn's grid_index: `stride = 1; for d < 3 while stride <= size: index += pos[d] * stride;
+// stride *= res`, then the hash if size < stride, then % size.  tcnn keeps `stride` in a uint32: for res >= 2^16 the
+// second multiplication wraps to 0, the loop runs on with stride 0 and `size < stride` is false -- the level is NOT
+// hashed although res^3 > size (levels 12..14 of the 2^18 grids, 12..16 of MeshRIR's 2^20 one: index = (x + y*res) %
+// size).  stride32 = 1 reproduces that (what a tcnn-trained checkpoint expects); stride32 = 0 keeps the stride exact.
+// The per-level outcome (strides reached, hashed or not) is decided once here on the host.
 static GridDev make_grid(const avr_grid_meta* g, const void* table_base) {
     GridDev d;
     d.n_levels = g->n_levels;
@@ -32,12 +42,19 @@ static GridDev make_grid(const avr_grid_meta* g, const void* table_base) {
         if (g->offset[l] & 1u) d.pair = 0;
     for (int l = 0; l < AVR_MAX_LEVELS; ++l) {
         d.scale[l] = g->scale[l]; d.res[l] = g->res[l]; d.size[l] = g->size[l]; d.offset[l] = g->offset[l];
-        const uint64_t res = g->res[l], size = g->size[l], cube = res * res * res;
-        d.kind[l] = 0;
-        if (size > 0 && res > 0 && res < (1u << 20)) {
-            if (cube <= size) d.kind[l] = 1;
-            else if ((size & (size - 1)) == 0) d.kind[l] = 2;
+        const uint64_t res = g->res[l], size = g->size[l];
+        uint64_t stride = 1, st[3] = {0, 0, 0};
+        for (int dim = 0; dim < 3 && stride <= size; ++dim) {
+            st[dim] = stride;
+            stride *= res;                                     // <= 2^32 * 2^32: no 64-bit overflow
+            if (g->stride32) stride &= 0xFFFFFFFFull;
         }
+        d.s1[l] = (uint32_t)st[1]; d.s2[l] = (uint32_t)st[2];
+        d.hashed[l] = size < stride ? 1u : 0u;
+        d.kind[l] = 0;
+        const bool pow2 = size > 0 && (size & (size - 1)) == 0;
+        if (size > 0 && res > 0 && res < (1u << 20) && res * res * res <= size) d.kind[l] = 1;
+        else if (pow2) d.kind[l] = d.hashed[l] ? 2 : 3;
     }
     return d;
 }
@@ -45,33 +62,36 @@ static GridDev make_grid(const avr_grid_meta* g, const void* table_base) {
 constexpr int ENC_PTS = 128;   // points per CTA
 constexpr int ENC_LG = 4;      // level groups (threadIdx.y)
 
-__device__ __forceinline__ uint32_t grid_index(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t res, uint32_t size) {
-    uint64_t stride = 1;
-    uint32_t index = cx;                          // stride 1 <= size always
-    stride *= res;
-    if (stride <= size) {
-        index += cy * (uint32_t)stride;
-        stride *= res;
-        if (stride <= size) {
-            index += cz * (uint32_t)stride;
-            stride *= res;
-        }
-    }
-    if (size < stride) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+// generic form: strides and the hashed / not hashed outcome come from make_grid
+__device__ __forceinline__ uint32_t grid_index(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t s1, uint32_t s2,
+                                               uint32_t hashed, uint32_t size) {
+    uint32_t index = cx + cy * s1 + cz * s2;                 // uint32 wrap-around, as in tcnn
+    if (hashed) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
     return index % size;
 }
 
-// Same index, without the runtime division in the common cases (the level kind is warp-uniform): a hashed level
-// with a power-of-two table masks; a dense level's index exceeds its table only for corners outside the grid.
+// Same index, without the runtime division in the common cases (the level kind is warp-uniform): a power-of-two
+// table masks; a dense level's index exceeds its table only for corners outside the grid.
 template <int KIND>
-__device__ __forceinline__ uint32_t grid_index_k(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t res, uint32_t size) {
+__device__ __forceinline__ uint32_t grid_index_k(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t s1, uint32_t s2,
+                                                 uint32_t hashed, uint32_t size) {
     if (KIND == 2) return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) & (size - 1u);
+    if (KIND == 3) return (cx + cy * s1 + cz * s2) & (size - 1u);
     if (KIND == 1) {
-        uint32_t index = cx + cy * res + cz * (res * res);
+        uint32_t index = cx + cy * s1 + cz * s2;
         if (index >= size) index %= size;
         return index;
     }
-    return grid_index(cx, cy, cz, res, size);
+    return grid_index(cx, cy, cz, s1, s2, hashed, size);
+}
+
+// level-kind dispatch (warp-uniform)
+__device__ __forceinline__ uint32_t grid_index_any(uint32_t kind, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t s1,
+                                                   uint32_t s2, uint32_t hashed, uint32_t size) {
+    return kind == 2 ? grid_index_k<2>(cx, cy, cz, s1, s2, hashed, size)
+         : kind == 1 ? grid_index_k<1>(cx, cy, cz, s1, s2, hashed, size)
+         : kind == 3 ? grid_index_k<3>(cx, cy, cz, s1, s2, hashed, size)
+                     : grid_index(cx, cy, cz, s1, s2, hashed, size);
 }
 
 struct Cell {
@@ -98,15 +118,15 @@ __device__ __forceinline__ float corner_weight(const Cell& c, int corner) {
 __device__ __forceinline__ float2 encode_level(const GridDev& g, int l, const float2* __restrict__ table,
                                                float ux, float uy, float uz) {
     const Cell c = locate(g.scale[l], ux, uy, uz);
-    const uint32_t res = g.res[l], size = g.size[l];
+    const uint32_t s1 = g.s1[l], s2 = g.s2[l], hashed = g.hashed[l], size = g.size[l];
     const float2* base = table + g.offset[l];
     float2 v[8];
     const uint32_t kind = g.kind[l];
     // (pairing the x-neighbour corners into one 16-byte load when they share a slot was measured: no gain, 0.25 ms)
 #define AVR_GATHER(KIND)                                                                                              \
     _Pragma("unroll") for (int k = 0; k < 8; ++k)                                                                      \
-        v[k] = __ldg(base + grid_index_k<KIND>(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), res, size));
-    if (kind == 2) { AVR_GATHER(2) } else if (kind == 1) { AVR_GATHER(1) } else { AVR_GATHER(0) }
+        v[k] = __ldg(base + grid_index_k<KIND>(c.gx + (k & 1), c.gy + ((k >> 1) & 1), c.gz + ((k >> 2) & 1), s1, s2, hashed, size));
+    if (kind == 2) { AVR_GATHER(2) } else if (kind == 1) { AVR_GATHER(1) } else if (kind == 3) { AVR_GATHER(3) } else { AVR_GATHER(0) }
 #undef AVR_GATHER
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
@@ -132,7 +152,7 @@ __device__ __forceinline__ int fixed_exponent(uint32_t gmax_bits, int headroom, 
 __device__ __forceinline__ void scatter_level(const GridDev& g, int l, float ux, float uy, float uz, float g0,
                                               float g1, float sc, unsigned long long* __restrict__ acc) {
     const Cell c = locate(g.scale[l], ux, uy, uz);
-    const uint32_t res = g.res[l], size = g.size[l];
+    const uint32_t s1 = g.s1[l], s2 = g.s2[l], hashed = g.hashed[l], size = g.size[l];
     unsigned long long* base = acc + 2ull * g.offset[l];
     // all sixteen addends first, then sixteen back-to-back reductions from distinct registers: a RED holds its
     // source registers until the LSU has taken them, so interleaving address math with REDs serialises on that
@@ -142,8 +162,7 @@ __device__ __forceinline__ void scatter_level(const GridDev& g, int l, float ux,
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
-        idx[k] = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
-                                                                                 : grid_index(cx, cy, cz, res, size);
+        idx[k] = grid_index_any(kind, cx, cy, cz, s1, s2, hashed, size);
         const float w = corner_weight(c, k);
         q0[k] = __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc));
         q1[k] = __float2ll_rn(__fmul_rn(__fmul_rn(w, g1), sc));
@@ -162,7 +181,7 @@ __device__ __forceinline__ void scatter_level(const GridDev& g, int l, float ux,
 __device__ __forceinline__ void scatter_level_f32(const GridDev& g, int l, float ux, float uy, float uz, float g0,
                                                   float g1, float* __restrict__ grad) {
     const Cell c = locate(g.scale[l], ux, uy, uz);
-    const uint32_t res = g.res[l], size = g.size[l];
+    const uint32_t s1 = g.s1[l], s2 = g.s2[l], hashed = g.hashed[l], size = g.size[l];
     float* base = grad + 2ull * g.offset[l];
     const uint32_t kind = g.kind[l];
     uint32_t idx[8];
@@ -170,8 +189,7 @@ __device__ __forceinline__ void scatter_level_f32(const GridDev& g, int l, float
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
-        idx[k] = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
-                                                                                 : grid_index(cx, cy, cz, res, size);
+        idx[k] = grid_index_any(kind, cx, cy, cz, s1, s2, hashed, size);
         wv[k] = corner_weight(c, k);
     }
     // x-neighbour corners that share a 16-byte slot (half of the pairs) go out as ONE red.global.add.v4.f32: the LSU
@@ -199,15 +217,14 @@ __device__ __forceinline__ void scatter_level_f32(const GridDev& g, int l, float
 __device__ __forceinline__ void scatter_level_f32_merged(const GridDev& g, int l, float ux, float uy, float uz, float g0,
                                                          float g1, bool ok, float* __restrict__ grad) {
     const Cell c = locate(g.scale[l], ux, uy, uz);
-    const uint32_t res = g.res[l], size = g.size[l];
+    const uint32_t s1 = g.s1[l], s2 = g.s2[l], hashed = g.hashed[l], size = g.size[l];
     float* base = grad + 2ull * g.offset[l];
     const uint32_t kind = g.kind[l];
     const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
-        uint32_t idx = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
-                                                                                     : grid_index(cx, cy, cz, res, size);
+        uint32_t idx = grid_index_any(kind, cx, cy, cz, s1, s2, hashed, size);
         if (!ok) idx = 0xFFFFFFFFu;                                       // never equal to a valid neighbour's index
         const float w = corner_weight(c, k);
         float v0 = ok ? __fmul_rn(w, g0) : 0.f, v1 = ok ? __fmul_rn(w, g1) : 0.f;
@@ -230,15 +247,14 @@ __device__ __forceinline__ void scatter_level_f32_merged(const GridDev& g, int l
 __device__ __forceinline__ void scatter_level_i64_merged(const GridDev& g, int l, float ux, float uy, float uz, float g0,
                                                          float g1, float sc, bool ok, unsigned long long* __restrict__ acc) {
     const Cell c = locate(g.scale[l], ux, uy, uz);
-    const uint32_t res = g.res[l], size = g.size[l];
+    const uint32_t s1 = g.s1[l], s2 = g.s2[l], hashed = g.hashed[l], size = g.size[l];
     unsigned long long* base = acc + 2ull * g.offset[l];
     const uint32_t kind = g.kind[l];
     const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t cx = c.gx + (k & 1), cy = c.gy + ((k >> 1) & 1), cz = c.gz + ((k >> 2) & 1);
-        uint32_t idx = kind == 2 ? grid_index_k<2>(cx, cy, cz, res, size) : kind == 1 ? grid_index_k<1>(cx, cy, cz, res, size)
-                                                                                     : grid_index(cx, cy, cz, res, size);
+        uint32_t idx = grid_index_any(kind, cx, cy, cz, s1, s2, hashed, size);
         if (!ok) idx = 0xFFFFFFFFu;
         const float w = corner_weight(c, k);
         long long q0 = ok ? __float2ll_rn(__fmul_rn(__fmul_rn(w, g0), sc)) : 0ll;
@@ -558,7 +574,9 @@ static int encode_bwd_common(bool raygen, const Geom& geo, const avr_grid_meta* 
     int merge_levels = 0;
     if (raygen && sample_step > 0.f) {
         for (int l = 0; l < grid->n_levels && grid->scale[l] * sample_step < 0.5f; ++l) merge_levels = l + 1;
+#ifdef AVR_EXPERIMENTS
         if (const char* e = getenv("AVR_SCATTER_MERGE_LEVELS")) merge_levels = atoi(e);      // A/B measurements
+#endif
         if (merge_levels > grid->n_levels) merge_levels = grid->n_levels;
         if (merge_levels < 0) merge_levels = 0;
     }

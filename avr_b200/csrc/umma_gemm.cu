@@ -22,13 +22,25 @@
 // MN-major x MN-major with split-K over the sample points (weight gradients, deterministic second pass).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <stdlib.h>
 #include "common.cuh"
 
 namespace avr {
 
 enum { UF_RELU = 1, UF_ACCUM = 2, UF_MASK = 4, UF_OUT_F32 = 8, UF_DUAL_RELU = 16, UF_BITS = 32, UF_BIAS = 64, UF_DUAL_COPY = 2048, UF_DEBUG_NOWAIT = 128, UF_DEBUG_NOSTORE = 256, UF_DEBUG_NOSTAGE = 512, UF_DEBUG_NOFENCE = 1024 };
+// Timing experiments (epilogue stages switched off, tile shapes forced through environment variables) exist only in
+// builds made with -DAVR_EXPERIMENTS (python -m avr_b200.build --experiments); the shipped library reads no
+// environment variable and its numerics cannot be changed from outside.
+#ifdef AVR_EXPERIMENTS
+#define UF_DBG(flags, f) ((flags) & (f))
+#define AVR_EXP_ENV(name) getenv(name)
+#else
+#define UF_DBG(flags, f) 0
+#define AVR_EXP_ENV(name) ((const char*)nullptr)
+#endif
 
 struct UmmaParams {
     int M, N, K;            // K-major: rows, cols, reduction.  MN-major: A extent, B extent, reduction (points)
@@ -591,12 +603,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int kind_o = o == 0 ? p.kc : p.kc2;
                         const int n_o = planes_count(kind_o);
                         pack_planes32(v, (o == 1 && (p.flags & UF_DUAL_RELU)) || (p.flags & UF_RELU), kind_o, ph, pm, pl);
-                        if (lane == 0 && !(p.flags & UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
+                        if (lane == 0 && !UF_DBG(p.flags, UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
                         __syncwarp();
-                        if (!(p.flags & UF_DEBUG_NOSTAGE)) stage_packed32(stage, lane, n_o, ph, pm, pl);
-                        if (!(p.flags & UF_DEBUG_NOFENCE)) fence_async_smem();
+                        if (!UF_DBG(p.flags, UF_DEBUG_NOSTAGE)) stage_packed32(stage, lane, n_o, ph, pm, pl);
+                        if (!UF_DBG(p.flags, UF_DEBUG_NOFENCE)) fence_async_smem();
                         __syncwarp();
-                        if (lane == 0 && !(p.flags & UF_DEBUG_NOSTORE)) {
+                        if (lane == 0 && !UF_DBG(p.flags, UF_DEBUG_NOSTORE)) {
                             const CUtensorMap* map = o == 0 ? &tmC : &tmC2;
                             for (int q = 0; q < n_o; ++q)
                                 tma_store_3d(map, stage + q * EPI_PLANE_BYTES, n0 + c0, m0 + lane_grp * 32, q);
@@ -740,8 +752,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // plane-pair tensor [2][rows][ld] of bf16, logical width `cols`; box = (64 cols, box_rows, 2 planes), 128B swizzle
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
-                    int box_rows, int nplanes, bool store_map = false) {
+static int encode_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
+                      int box_rows, int nplanes, bool store_map) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(AVR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld * 2) % 16 || (plane * 2) % 16)
@@ -756,6 +768,54 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
                      store_map ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(AVR_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+    return AVR_OK;
+}
+
+// A tensor map is a pure function of (base, shape, pitches, box): the caller's allocator hands the same buffers back
+// step after step, so the four driver calls per GEMM (and their ~1.5 us each on the launching thread) are paid once per
+// distinct operand.  Guarded by a mutex (concurrent callers: nn.DataParallel threads, autograd's device threads);
+// bounded: the cache is dropped when it reaches 4096 entries.
+struct MapKey {
+    const void* base; long long rows, cols, ld, plane; int box_rows, nplanes, store;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && plane == o.plane && box_rows == o.box_rows &&
+               nplanes == o.nplanes && store == o.store;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        auto mix = [&h](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+        mix((uint64_t)k.rows); mix((uint64_t)k.cols); mix((uint64_t)k.ld); mix((uint64_t)k.plane);
+        mix(((uint64_t)k.box_rows << 8) | ((uint64_t)k.nplanes << 1) | (uint64_t)k.store);
+        return (size_t)h;
+    }
+};
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
+                    int box_rows, int nplanes, bool store_map = false) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{base, rows, cols, ld, plane, box_rows, nplanes, store_map ? 1 : 0};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *map = it->second; return AVR_OK; }
+    }
+    if (int rc = encode_map(map, base, rows, cols, ld, plane, box_rows, nplanes, store_map)) return rc;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 4096) cache.clear();
+    cache.emplace(key, *map);
+    return AVR_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device) state: raised to the 227 KB opt-in limit once
+template <typename K>
+static int allow_max_smem(K kernel, int device) {
+    static std::atomic<uint64_t> done{0};
+    const uint64_t bit = 1ull << (device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return AVR_OK;
+    AVR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    done.fetch_or(bit, std::memory_order_release);
     return AVR_OK;
 }
 
@@ -865,7 +925,7 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     // fp16 pairs, wide layers: three products make a 128 x 128 tile L2-feed-bound (512 KB of operands per 10 k clk of
     // MMAs); a 128 x 256 tile moves 25 % fewer bytes per flop.  Its two accumulators fill TMEM, so tiles are not
     // double-buffered there.
-    if (a_f16 && N % 256 == 0 && K >= 256 && !(flags & UF_BIAS) && !getenv("AVR_UMMA_F16_BN128")) { p.BN = 256; p.acc_bufs = 1; }
+    if (a_f16 && N % 256 == 0 && K >= 256 && !(flags & UF_BIAS) && !AVR_EXP_ENV("AVR_UMMA_F16_BN128")) { p.BN = 256; p.acc_bufs = 1; }
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
     // long reductions into an fp32 output (the DFT and its adjoint, K = T or 2F): the accumulator is truncated once per
@@ -879,9 +939,9 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         AVR_REQUIRE(splitk_workspace_bytes >= splits * M * splitk_ld * (int64_t)sizeof(float), "split-K workspace too small");
         p.k_splits = (int)splits;
     }
-    p.dual_acc = (a_f16 || (p.na == 3 && p.nb == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
+    p.dual_acc = (a_f16 || (p.na == 3 && p.nb == 3 && 4 * p.BN <= 512 && !AVR_EXP_ENV("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
     p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc, p.acc_bufs);
-    p.flags = flags;
+    p.flags = flags & ~(UF_DEBUG_NOWAIT | UF_DEBUG_NOSTORE | UF_DEBUG_NOSTAGE | UF_DEBUG_NOFENCE);
     p.c = (__nv_bfloat16*)c_planes; p.ldc = ldc; p.c_plane = c_plane;
     p.c2 = (__nv_bfloat16*)c2_planes; p.ldc2 = ldc2; p.c2_plane = c2_plane;
     p.mask = mask_bits; p.ldmask = ldmask;
@@ -893,8 +953,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     }
     p.bias_ray = bias_ray; p.bias_rcv = bias_rcv; p.ld_bias_ray = ld_bias_ray; p.ld_bias_rcv = ld_bias_rcv;
     p.geo_R = geo_R; p.geo_S = geo_S;
-    if (getenv("AVR_UMMA_NOWAIT")) p.flags |= UF_DEBUG_NOWAIT;       // timing experiments only: results are garbage
-    if (const char* dbg = getenv("AVR_UMMA_DEBUG")) p.flags |= (atoi(dbg) & (UF_DEBUG_NOWAIT | UF_DEBUG_NOSTORE | UF_DEBUG_NOSTAGE | UF_DEBUG_NOFENCE));
+    if (AVR_EXP_ENV("AVR_UMMA_NOWAIT")) p.flags |= UF_DEBUG_NOWAIT;       // timing experiments only: results are garbage
+    if (const char* dbg = AVR_EXP_ENV("AVR_UMMA_DEBUG")) p.flags |= (atoi(dbg) & (UF_DEBUG_NOWAIT | UF_DEBUG_NOSTORE | UF_DEBUG_NOSTAGE | UF_DEBUG_NOFENCE));
     p.c32 = c_f32; p.ldc32 = ldc32;
     if (p.k_splits > 1) { p.c32 = (float*)splitk_workspace; p.ldc32 = splitk_ld; }
     p.near_list = (uint2*)near_list; p.near_cap = (uint32_t)near_cap; p.near_count = near_count; p.near_tau = near_tau;
@@ -920,7 +980,7 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         if (p.stages >= 2) break;
     }
     if (p.epi_split < 1 || p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
-    if (const char* e = getenv("AVR_UMMA_EPI_SPLIT")) {                   // A/B experiments: force one warp per lane group
+    if (const char* e = AVR_EXP_ENV("AVR_UMMA_EPI_SPLIT")) {                   // A/B experiments: force one warp per lane group
         if (atoi(e) == 1 && p.epi_split == 2) p.epi_split = 1;
     }
     const size_t smem = (size_t)bres_total + (size_t)p.stages * stage_bytes + 2048 + epi_bytes;
@@ -934,7 +994,7 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         if (dual)
             if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, nc2, true)) return rc;
     }
-    AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = allow_max_smem(umma_gemm_kernel<false>, device)) return rc;
     const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
     const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
     umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, tc, tc2, p);
@@ -999,11 +1059,11 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.k_per_split = (int)(ceil_div(ceil_div(K, splits), UBK) * UBK);
     if (p.k_per_split < UBK) p.k_per_split = UBK;
     p.k_splits = (int)(K > 0 ? ceil_div(K, p.k_per_split) : 1);
-    p.dual_acc = (b_f16 || (nplanes == 3 && 4 * p.BN <= 512 && !getenv("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
+    p.dual_acc = (b_f16 || (nplanes == 3 && 4 * p.BN <= 512 && !AVR_EXP_ENV("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
     p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
     p.c32 = (float*)workspace; p.ldc32 = ldp;
     p.epi_split = 2; p.epi_warp_bytes = 0;
-    if (const char* e = getenv("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = AVR_EXP_ENV("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
     const int bn_rows = (p.BN + 63) / 64 * 64;
     const uint32_t stage_bytes = (uint32_t)na * A_PLANE_BYTES + (uint32_t)nb * (uint32_t)bn_rows * 128u;
     p.stages = (int)((220 * 1024) / stage_bytes);
@@ -1015,7 +1075,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
         CUtensorMap ta, tb;
         if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, na)) return rc;
         if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nb)) return rc;
-        AVR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (int rc = allow_max_smem(umma_gemm_kernel<true>, device)) return rc;
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
         umma_gemm_kernel<true><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, p);

@@ -1,25 +1,64 @@
-"""Data-parallel gradient exchange: one flat fp32 arena, one all-reduce per step.
+"""Data-parallel gradient exchange: one flat fp32 arena, one all-reduce per step (+ a row all-gather).
 
 Replaces the DDP reducer of ``avr_runner_ddp.py:98,257`` (25 MB buckets + a used-parameter bitmap
 all-reduce per step because of ``find_unused_parameters=True``).  Receivers are independent, every rank
 holds a full replica, and the only exchange is the mean of the parameter gradients: all
 ``.grad`` tensors are views into one contiguous buffer, so the exchange is a single NCCL all-reduce
 (NVLS in-switch reduction on NVSwitch) issued on the compute stream right after the backward kernels
-(``all_reduce_mean``) -- or, with ``attach(renderer)``, one all-reduce per parameter tensor issued from INSIDE the
-backward pass the moment that tensor's gradient is final: the signal network and the per-ray / per-receiver hash
-tables (2/3 of the bytes) are reduced while the density path and the sigma encoder are still back-propagating,
-and only the last table's exchange (38 of 120 MB at simu) is exposed.  Measured on 8 x B200 (``profiles/ddp_overlap_check.py``,
-``profiles/r1/ddp_overlap.md``): bit-identical gradients at 2 ranks, but NOT faster -- 15.17 -> 15.10 ms at 2 GPUs,
-15.44 -> 15.63 ms at 8: the persistent GEMM CTAs own every SM, so NCCL's kernels only make progress between them
-and nine small all-reduces cost more latency than one large one.  ``attach`` therefore stays opt-in.
+(``all_reduce_mean``).
 
-The reference's stock wrapper also works on ``avr_b200.AVRRender`` (it is an ordinary ``nn.Module``);
-this arena is the B200-first path used by ``bench.py``.
+``attach(renderer)`` cuts that all-reduce to the gradients that are dense.  The per-ray and per-receiver hash
+tables (``_dir_encoding``, ``_tx_encoding``: 76 of the 120 MB at simu, 183 of 229 MB at MeshRIR, 152 of 236 MB at RAF)
+are touched by R = 650..3202 resp. bs points per step, so > 93 % of what the flat all-reduce ships for them is zeros.
+With ``attach`` the backward pass all-gathers the pre-scatter rows instead (``[R, 3 + 40]`` floats per rank and table,
+~350 KB; started inside the backward pass, finished at its end) and every rank scatters the rows of ALL ranks into its
+own table gradient with the int64 fixed-point accumulator -- integer sums, so every replica holds the bit-identical
+mean, exactly what an all-reduce guarantees.  Those tables then sit behind ``reduce_numel`` in the arena and the
+all-reduce covers the dense prefix only (the per-point tables, the MLPs, channel embeddings).
+
+The reference's stock ``DDP(...)`` wrapper also works on ``avr_b200.AVRRender`` (an ordinary ``nn.Module``,
+``tests/test_ddp_gloo.py``); this arena is the B200-first path used by ``bench.py``.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+
+def _active(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+class RowExchange:
+    """All-gather of the ``(unit-cube input, gradient row)`` pairs of a per-ray / per-receiver encoding."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def start(self, u: torch.Tensor, rows: torch.Tensor):
+        """``u[n,3]``, ``rows[n,w]`` of this rank -> handle; every rank must call with the same ``n`` and ``w``."""
+        packed = torch.cat([u, rows], dim=1).contiguous()
+        if not _active(self.group):
+            return None, packed, 1, packed.device
+        world = dist.get_world_size(self.group)
+        staged = packed
+        if packed.is_cuda and dist.get_backend(self.group) != "nccl":      # gloo (tests): gather through host copies
+            staged = packed.cpu()
+        out = torch.empty(world * staged.shape[0], staged.shape[1], dtype=staged.dtype, device=staged.device)
+        work = dist.all_gather_into_tensor(out, staged, group=self.group, async_op=True)
+        return work, out, world, packed.device
+
+    def finish(self, handle):
+        """-> ``(u_all[W*n,3], rows_all[W*n,w] / W)`` in rank order (stream-level wait on NCCL: the host does not block)."""
+        work, out, world, dev = handle
+        if work is not None:
+            work.wait()
+        out = out.to(dev)
+        u_all = out[:, :3].contiguous()
+        rows_all = out[:, 3:].contiguous()
+        if world > 1:
+            rows_all = rows_all * (1.0 / world)                             # gradients are averaged over ranks (DDP)
+        return u_all, rows_all
 
 
 class GradArena:
@@ -29,13 +68,21 @@ class GradArena:
         self.params = [p for p in parameters if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
-        dev, dtype = self.params[0].device, self.params[0].dtype
-        self.offsets, n = [], 0
-        for p in self.params:
+        self._layout(self.params)
+
+    def _layout(self, params, n_reduced=None):
+        dev, dtype = params[0].device, params[0].dtype
+        self.params, self.offsets, n = list(params), [], 0
+        self.reduce_numel = None
+        for k, p in enumerate(self.params):
             if p.device != dev or p.dtype != dtype:
                 raise ValueError("all parameters must share device and dtype")
+            if n_reduced is not None and k == n_reduced:
+                self.reduce_numel = n
             self.offsets.append(n)
             n += (p.numel() + 3) // 4 * 4                       # keep every view 16-byte aligned
+        if self.reduce_numel is None:
+            self.reduce_numel = n
         self.flat = torch.zeros(n, device=dev, dtype=dtype)
         self.bind()
 
@@ -52,50 +99,53 @@ class GradArena:
         return self.flat.numel()
 
     def all_reduce_mean(self, group=None, async_op=False):
-        """grad <- mean over ranks (DistributedDataParallel semantics)."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        """grad <- mean over ranks (DistributedDataParallel semantics); covers ``flat[:reduce_numel]``, the rest was
+        exchanged as rows inside the backward pass (``attach``)."""
+        if not _active(group):
             return None
         world = dist.get_world_size(group)
-        if self.flat.is_cuda and dist.get_backend(group) == "nccl":
-            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=False)
-        self.flat.div_(world)
+        buf = self.flat[:self.reduce_numel]
+        if buf.is_cuda and dist.get_backend(group) == "nccl":
+            return dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=False)
+        buf.div_(world)
         return work
 
-
-    # -- exchange overlapped with the backward pass -------------------------------------------------------------
+    # -- row exchange for the per-ray / per-receiver tables ----------------------------------------------------------
     def attach(self, renderer, group=None):
-        """Reduce every gradient inside ``renderer``'s backward pass (tensor-core path) instead of after it.
-
-        The renderer announces ``(parameter, gradient)`` as soon as the producing kernels are enqueued; the all-reduce
-        (mean) of that tensor starts on NCCL's stream behind them and runs next to the remaining backward kernels.
-        ``done`` makes the compute stream wait for all of them before autograd accumulates the (already averaged)
-        gradients into ``.grad``.  Do not call ``all_reduce_mean`` as well."""
-        self._works = []
-
-        def ready(param, grad):
-            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-                return
-            if grad.is_cuda and dist.get_backend(group) == "nccl":
-                self._works.append(dist.all_reduce(grad, op=dist.ReduceOp.AVG, group=group, async_op=True))
-            else:
-                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
-                grad.div_(dist.get_world_size(group))
-
-        def done():
-            for w in self._works:
-                w.wait()                                         # stream-level wait, the host does not block
-            self._works.clear()
-
-        renderer.grad_ready_hook, renderer.grad_done_hook = ready, done
+        """Exchange the per-ray / per-receiver table gradients as rows (see the module docstring): re-lays the arena out
+        with those tables last and installs the exchange on ``renderer`` (tensor-core path, ``avr_b200`` fields).
+        Call ``all_reduce_mean`` after backward as before; it now covers the dense prefix only."""
+        net = renderer.network_fn
+        if getattr(renderer, "dense", "tc") != "tc" or not hasattr(net, "small_table_modules"):
+            raise NotImplementedError("GradArena.attach needs an avr_b200 field rendered on the tensor-core path")
+        small = {id(m.params) for m in net.small_table_modules()}
+        dense = [p for p in self.params if id(p) not in small]
+        rows = [p for p in self.params if id(p) in small]
+        self._layout(dense + rows, n_reduced=len(dense))
+        renderer.row_exchange = RowExchange(group)
         return self
 
     @staticmethod
     def detach(renderer):
-        renderer.grad_ready_hook = renderer.grad_done_hook = None
+        renderer.row_exchange = None
+
+    def checksum(self) -> float:
+        """float64 sum of the arena -- equal on every rank after the exchange (bench.py asserts it)."""
+        return float(self.flat.double().sum())
 
 
-def shard_receivers(n_receivers: int, rank: int, world: int):
-    """Indices of the receivers rank ``rank`` renders: ``rank, rank+world, ...``
-    (``DistributedSampler`` order without shuffling, avr_runner_ddp.py:131-137)."""
-    return list(range(rank, n_receivers, world))
+def shard_receivers(n_receivers: int, rank: int, world: int, drop_last: bool = False):
+    """Indices of the receivers rank ``rank`` renders: ``rank, rank+world, ...`` over the index list padded by wrapping
+    around to a multiple of ``world`` -- ``DistributedSampler(shuffle=False)`` order and padding
+    (avr_runner_ddp.py:131-137), so every rank gets the same number of steps; ``drop_last`` truncates instead."""
+    if n_receivers <= 0:
+        return []
+    idx = list(range(n_receivers))
+    if drop_last:
+        idx = idx[: n_receivers - n_receivers % world]
+    else:
+        total = (n_receivers + world - 1) // world * world
+        while len(idx) < total:                                  # DistributedSampler: indices += indices[:padding]
+            idx += idx[: total - len(idx)]
+    return idx[rank::world]

@@ -12,8 +12,6 @@ B200-first changes:
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import ops
@@ -22,14 +20,15 @@ from .ops import PlanePair
 
 
 FWD_KIND = ops.PLANES_BF16x3  # forward operands carry 24 mantissa bits (six products): ReLU decisions must match fp32
-SIG_HIDDEN_F16 = os.environ.get("AVR_SIG_F16", "1") != "0"
+SIG_HIDDEN_F16 = True
 # The 512 x 512 hidden layers of the signal network (tensor-bound, half of the forward MMA time) take fp16
 # (hi, lo' * 2^11) pairs: 24 bits in two planes, THREE products instead of six.  The producing layer writes each hidden
 # activation twice (ops.UMMA_DUAL_COPY): as an fp16 pair for the next layer / the collapsed output layer, and as a bf16
 # (hi, mid) pair for the weight-gradient GEMM (gradients need bf16's range, and tcgen05.mma faults on a bf16 x f16 mix).
 # Measured on one box, same run: 14.6 -> 14.1 ms per step; the layers become L2-feed-bound (512 KB of operands per
 # 128 x 128 tile) instead of MMA-bound, hence not the full 2x.  Range: fp16's -- like tiny-cuda-nn's own activations --
-# inf / NaN beyond 65504 (loud), absolute error <= 1.5e-11 below 6e-5.  AVR_SIG_F16=0 keeps bf16 triples everywhere.
+# inf / NaN beyond 65504 (loud), absolute error <= 1.5e-11 below 6e-5.  False keeps bf16 triples everywhere (a module
+# constant, not an environment switch: tests set it explicitly).
 BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough ...
 DENSITY_BWD_PLANES = 3   # ... except along the sigma decoder: the density gradient of a ray sums to ~0 over its samples
                          # (sum_s w_s = 1), so the decoder's weight-gradient sums cancel to ~1/50 of their terms
@@ -242,15 +241,12 @@ class FusedRenderTC(torch.autograd.Function):
         n_rows = geom.bs * geom.R * geom.S
         d_vals = tables["d"]
         grads = {}
-        # A gradient is announced as soon as the kernels that produce it are enqueued, so that a data-parallel caller can
-        # start its all-reduce while the rest of the backward pass runs (ddp.GradArena.attach): the signal network and
-        # the per-ray / per-receiver hash tables (2/3 of all gradient bytes) are final before the density path starts.
-        ready = plan.get("grad_ready")
-        index_of = {id(m): i for i, m in enumerate(mods)}
-
-        def announce(mod):
-            if ready is not None:
-                ready(index_of[id(mod)], grads[id(mod)])
+        # Data-parallel runs (ddp.GradArena.attach): the per-ray / per-receiver tables receive gradient from only R / bs
+        # points, so instead of all-reducing their (almost all-zero) 38-145 MB gradients the ranks all-gather the few
+        # pre-scatter rows and every rank scatters all of them locally.  The gather starts as soon as the rows exist and
+        # the scatter is deferred to the end of the pass, behind the remaining backward kernels.
+        exchange = plan.get("row_exchange")
+        deferred = []
 
         grids = [m for (m, kind) in plan["x0"] + plan["tail"] if kind != "receiver_rows" and m.grid_grad == "deterministic"]
         scratch = torch.empty(max(int(m.meta.total) * 2 for m in grids), dtype=torch.int64, device=dev) if grids else None
@@ -270,11 +266,14 @@ class FusedRenderTC(torch.autograd.Function):
                     acc.add_rays(geom, rays_o, dirs, d_vals, d_buf, col, sample_step=tables.get("sample_step", 0.0))
                 else:
                     small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
+                    if exchange is not None:
+                        deferred.append((mod, exchange.start(ctx.small_in[kind], small)))
+                        col += wdt
+                        continue
                     acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch, mod.grid_grad)
                     acc.observe(small, 0, wdt)
                     acc.add_points(ctx.small_in[kind], small)
                 grads[id(mod)] = acc.finalize()
-                announce(mod)
                 col += wdt
 
         ws_bytes = max(ops.umma_tn_workspace_bytes(o, i, n_rows) for n in (enc_net, dec_net, sig_net) for (o, i) in n.shapes)
@@ -310,7 +309,6 @@ class FusedRenderTC(torch.autograd.Function):
         sig_in, dec_in = B["sig_in"], B["dec_in"]
         g, wt_sig, _ = hidden_backward(sig_net, "sig", g, B["acts_sig"], B["bits_sig"], sig_in, g_sig)
         grads[id(sig_net)] = g_sig
-        announce(sig_net)
         d_feat = PlanePair.empty(n_rows, feat_dim, dev)
         wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
         if plan["sig_relu_feat"]:
@@ -349,7 +347,6 @@ class FusedRenderTC(torch.autograd.Function):
             d_dec_tail = PlanePair.empty(n_rows, dec_net.in_pad - feat_dim, dev)
             ops.umma_nt(g, wt_dec[0].row_window(feat_dim, dec_net.in_pad - feat_dim), 0, d_dec_tail)
         grads[id(dec_net)] = g_dec
-        announce(dec_net)
         scatter_segments(plan.get("dec_tail", []), d_dec_tail)
 
         # ---- sigma encoder -----------------------------------------------------------------------------------
@@ -370,11 +367,14 @@ class FusedRenderTC(torch.autograd.Function):
         d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev)
         ops.umma_nt(g, wt_enc[0], 0, d_x0)
         grads[id(enc_net)] = g_enc
-        announce(enc_net)
         scatter_segments(plan["x0"], d_x0)
-        if ready is not None:
-            for k, r in enumerate(ctx.roles):
-                ready(len(mods) + k, extra_grads[tuple(r)])
-            plan["grad_done"]()
+        for mod, handle in deferred:
+            # rows of ALL ranks (already scaled to the mean), scattered in rank order with the int64 accumulator: every
+            # replica gets the bit-identical gradient, like after an all-reduce
+            u_all, rows_all = exchange.finish(handle)
+            acc = ops.GridGradAccumulator(mod.meta, dev, rows_all.shape[0], None, "deterministic")
+            acc.observe(rows_all, 0, rows_all.shape[1])
+            acc.add_points(u_all, rows_all)
+            grads[id(mod)] = acc.finalize()
         ctx.bufs = None
         return (None,) * 8 + tuple(grads[id(m)] for m in mods) + tuple(extra_grads[tuple(r)] for r in ctx.roles)

@@ -26,8 +26,17 @@ def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+INDEX_STRIDES = ("uint32", "exact")
+
+
 def hashgrid_geometry(cfg: dict) -> dict:
-    """Level table of a tcnn ``HashGrid`` config (tcnn defaults for absent keys)."""
+    """Level table of a tcnn ``HashGrid`` config (tcnn defaults for absent keys).
+
+    ``index_stride`` (not a tcnn key; default ``"uint32"``) selects the arithmetic of the dense-index stride in
+    ``grid_index``: ``"uint32"`` wraps like tiny-cuda-nn's own ``uint32_t stride`` -- levels with
+    ``2^16 <= res <= hashmap size`` (12..14 of the 2^18 grids, 12..16 of a 2^20 grid) are then indexed
+    ``(x + y*res) % size`` instead of being hashed, which is what a tcnn-trained checkpoint expects; ``"exact"``
+    keeps the stride in 64 bits (those levels are hashed)."""
     if cfg.get("otype", "HashGrid") not in ("HashGrid", "Grid"):
         raise NotImplementedError(f"encoding otype {cfg.get('otype')!r} is not built")
     n_levels = int(cfg.get("n_levels", 16))
@@ -42,17 +51,23 @@ def hashgrid_geometry(cfg: dict) -> dict:
         n = min(_round_up(r ** 3, 8), 1 << log2_size)
         scale.append(float(s)); res.append(r); size.append(n); offset.append(off)
         off += n
+    index_stride = cfg.get("index_stride", "uint32")
+    if index_stride not in INDEX_STRIDES:
+        raise ValueError(f"index_stride must be one of {INDEX_STRIDES}")
     return {"n_levels": n_levels, "n_feat": n_feat, "scale": scale, "res": res, "size": size, "offset": offset,
-            "total": off}
+            "total": off, "index_stride": index_stride}
 
 
 class Encoding(nn.Module):
     """Multiresolution hash grid on 3-D unit-cube inputs (``tcnn.Encoding(3, cfg)``)."""
 
-    def __init__(self, n_input_dims: int, encoding_config: dict, dtype=torch.float32, seed: int = 1337):
+    def __init__(self, n_input_dims: int, encoding_config: dict, dtype=torch.float32, seed: int = 1337,
+                 index_stride: str = None):
         super().__init__()
         if n_input_dims != 3:
             raise NotImplementedError("only 3-D hash grids are built")
+        if index_stride is not None:
+            encoding_config = dict(encoding_config, index_stride=index_stride)
         self.geom = hashgrid_geometry(encoding_config)
         self.n_input_dims = 3
         self.n_output_dims = self.geom["n_levels"] * self.geom["n_feat"]
@@ -60,9 +75,10 @@ class Encoding(nn.Module):
         n = self.geom["total"] * self.geom["n_feat"]
         self.params = nn.Parameter((torch.rand(n, generator=g) * 2 - 1) * 1e-4)      # tcnn: U(-1e-4, 1e-4)
         self._meta = None
-        #: how the table gradient is accumulated: "atomic" (fp32 vector reductions, fastest, run-to-run
-        #: differences in the last bits like tcnn) or "deterministic" (int64 fixed point, bit-reproducible)
-        self.grid_grad = "atomic"
+        #: how the table gradient is accumulated: "deterministic" (default; int64 fixed point, bit-reproducible, as the
+        #: north_star asks) or "atomic" (fp32 vector reductions: faster, run-to-run differences in the last bits like
+        #: tcnn's own atomics)
+        self.grid_grad = "deterministic"
 
     @property
     def meta(self):
@@ -255,6 +271,11 @@ class AVRModel(nn.Module):
         attn = torch.abs(torch.nn.functional.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)
         return attn, signal.view(bs, n_pts, self.signal_output_dim)
 
+    def small_table_modules(self):
+        """Encodings evaluated on R / bs points only (per ray, per receiver): their table gradients are a few rows, which
+        data-parallel runs all-gather instead of all-reducing the tables (``ddp.GradArena.attach``)."""
+        return [self._dir_encoding, self._tx_encoding]
+
     def fused_plan(self, ch_idx=None) -> dict:
         """What the fused render step needs.  With a channel embedding the per-receiver rows (gathered here, under
         autograd) ride along as ``extra_tensors``: ``('bias', net, layer)`` rows are added to a hidden layer's
@@ -314,6 +335,9 @@ class AVRModel_complex(nn.Module):
         signal = self._model_signal(feat)
         attn = torch.abs(torch.nn.functional.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)
         return attn, signal.reshape(bs, n_pts, self.signal_output_dim)
+
+    def small_table_modules(self):
+        return [self._tx_pos_encoding, self._dir_encoding, self._tx_dir_encoding, self._tx_pos_signal_encoding]
 
     def fused_plan(self) -> dict:
         return {

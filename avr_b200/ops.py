@@ -166,6 +166,7 @@ def make_grid_meta(geom: dict) -> GridMeta:
     """``geom`` from ``hashgrid_geometry`` (model.py)."""
     m = GridMeta()
     m.n_levels, m.n_feat, m.total = geom["n_levels"], geom["n_feat"], geom["total"]
+    m.stride32 = 1 if geom.get("index_stride", "uint32") == "uint32" else 0
     for l in range(geom["n_levels"]):
         m.scale[l], m.res[l], m.size[l], m.offset[l] = geom["scale"][l], geom["res"][l], geom["size"][l], geom["offset"][l]
     return m

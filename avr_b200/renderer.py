@@ -62,11 +62,10 @@ class AVRRender(nn.Module):
                 if isinstance(m, Encoding):
                     m.grid_grad = grid_grad
         self._tables = {}
-        #: ``hook(parameter, gradient)`` called INSIDE the backward pass as soon as a parameter's gradient is final
-        #: (tensor-core path), and ``done()`` at its end -- installed by ``ddp.GradArena.attach`` to overlap the
-        #: gradient all-reduce with the rest of the backward kernels
-        self.grad_ready_hook = None
-        self.grad_done_hook = None
+        #: data-parallel runs: exchange object installed by ``ddp.GradArena.attach`` -- the backward pass all-gathers the
+        #: pre-scatter gradient rows of the per-ray / per-receiver tables instead of leaving their (almost all-zero)
+        #: table gradients to the all-reduce (tensor-core path)
+        self.row_exchange = None
 
     # -- configuration -----------------------------------------------------------------------------
     def render_cfg(self) -> dict:
@@ -110,8 +109,15 @@ class AVRRender(nn.Module):
     def _render_pass(self, rays_o, position_tx, direction_tx, ch_idx, dirs):
         net = self.network_fn
         bs = rays_o.size(0)
+        plan = None
         if hasattr(net, "fused_plan"):
             plan = net.fused_plan(ch_idx) if "ch_idx" in inspect.signature(net.fused_plan).parameters else net.fused_plan()
+            if plan.get("extras") and self.dense != "tc":
+                # channel embeddings on the fp32 SIMT path: the field is evaluated on explicit points (its own forward:
+                # hash-grid gather + fp32 FMA GEMMs, embedding rows added / concatenated by torch) and composited by the
+                # generic path below -- an independent check of the tensor-core path's bias epilogue / row broadcasts
+                plan = None
+        if plan is not None:
             if plan["needs_dir_tx"] and direction_tx is None:
                 raise ValueError("this field needs direction_tx (AVRModel_complex, model.py:291)")
             T = int(net.signal_output_dim)
@@ -119,15 +125,14 @@ class AVRRender(nn.Module):
             geom = ops.make_geom(self.render_cfg(), bs, T)
             params = [m.params for m in plan_modules(plan)] + list(plan.get("extra_tensors", []))
             dtx = direction_tx if plan["needs_dir_tx"] else None
-            if plan.get("extras") and self.dense != "tc":
-                raise NotImplementedError("channel embeddings are built on the tensor-core path only (dense='tc')")
             if self.dense == "tc":
-                if self.grad_ready_hook is not None:                           # ddp.GradArena.attach: overlapped all-reduce
+                if self.row_exchange is not None:                              # ddp.GradArena.attach
                     plan = dict(plan)
-                    plan["grad_ready"] = lambda i, g, _p=params: self.grad_ready_hook(_p[i], g)
-                    plan["grad_done"] = self.grad_done_hook or (lambda: None)
+                    plan["row_exchange"] = self.row_exchange
                 return FusedRenderTC.apply(plan, geom, tab.dev, ops.collapse_tspan(self.render_cfg()), rays_o,
                                            position_tx, dtx, dirs, *params)
+            if self.row_exchange is not None:
+                raise NotImplementedError("GradArena.attach (row exchange) is built on the tensor-core path (dense='tc')")
             return FusedRenderFunction.apply(plan, geom, tab.dev, rays_o, position_tx, dtx, dirs, *params)
 
         # generic networks_fn: build what renderer.py:54-62 builds, call the network, composite.
@@ -142,6 +147,8 @@ class AVRRender(nn.Module):
         kwargs = {}
         if ch_idx is not None and "ch_idx" in inspect.signature(net.forward).parameters:
             kwargs["ch_idx"] = ch_idx
+        if self.row_exchange is not None:
+            raise NotImplementedError("GradArena.attach (row exchange) needs an avr_b200 field on the tensor-core path")
         attn, signal = net(*args, **kwargs)
         T = signal.size(-1)
         geom = ops.make_geom(cfg, bs, T)

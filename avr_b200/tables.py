@@ -22,6 +22,8 @@ def direction_table(n_azi: int, n_ele: int, azi_rand: torch.Tensor | None = None
     if azi_rand is None:
         azi_rand = torch.rand(n_azi)
         torch.rand(n_ele)
+    elif not torch.is_tensor(azi_rand):             # a plain sequence of floats (nn.DataParallel scatters tensors)
+        azi_rand = torch.tensor(list(azi_rand), dtype=torch.float32)
     azi = torch.linspace(0, np.pi * 2, n_azi + 1)[:-1] + (np.pi * 2 / n_azi) * azi_rand.to("cpu", torch.float32)
     ele = torch.acos(2 * torch.linspace(0, 1, n_ele + 2)[1:-1] - 1)
     azi = azi[:, None].expand(n_azi, n_ele).reshape(-1)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVR_B200_ABI_VERSION 1
+#define AVR_B200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define AVR_API __attribute__((visibility("default")))
 #else
@@ -58,6 +58,10 @@ typedef struct avr_grid_meta {
     uint32_t size[AVR_MAX_LEVELS];        /* entries in level l                          */
     uint32_t offset[AVR_MAX_LEVELS];      /* first entry of level l in the flat table    */
     uint32_t total;                       /* sum(size)                                   */
+    int32_t stride32;                     /* 1: tiny-cuda-nn's grid_index arithmetic -- the dense-index stride is a uint32
+                                           * that wraps (levels with 2^16 <= res <= size are then NOT hashed:
+                                           * index = (x + y*res mod 2^32) % size); 0: exact (64-bit) stride, such levels
+                                           * are hashed.  See DESIGN.md 2 "grid_index". */
 } avr_grid_meta;
 
 /* Epilogue / operand flags of avr_gemm */

@@ -52,9 +52,11 @@ def hashgrid_geometry(cfg: dict):
         sizes.append(entries)
         offsets.append(off)
         off += entries
+    index_stride = cfg.get("index_stride", "uint32")
+    assert index_stride in ("uint32", "exact")
     return {
         "n_levels": n_levels, "n_feat": n_feat, "scale": scales, "res": ress,
-        "size": sizes, "offset": offsets, "total": off,
+        "size": sizes, "offset": offsets, "total": off, "index_stride": index_stride,
     }
 
 
@@ -92,11 +94,17 @@ class HashGridRef(nn.Module):
                 bit = (corner >> d) & 1
                 w = w * (frac[:, d] if bit else (1 - frac[:, d]))
                 cs.append((grid[:, d] + bit) & _U32)
+            # tcnn grid_index: `uint32_t stride` -- for res >= 2^16 the second `stride *= res` wraps to 0, the loop
+            # runs on and `size < stride` is false, so such a level is NOT hashed ("uint32", the default: what real
+            # tiny-cuda-nn computes, recalled from its source -- parity unpinned); "exact" keeps an unbounded stride
+            wrap = geo.get("index_stride", "uint32") == "uint32"
             stride, index = 1, torch.zeros_like(cs[0])
             d = 0
             while d < 3 and stride <= size:
                 index = (index + _mul_u32(cs[d], stride & _U32)) & _U32
                 stride *= res
+                if wrap:
+                    stride &= _U32
                 d += 1
             if size < stride:
                 index = cs[0] ^ _mul_u32(cs[1], _PRIME_Y) ^ _mul_u32(cs[2], _PRIME_Z)

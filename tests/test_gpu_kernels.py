@@ -73,9 +73,12 @@ GRID_CFGS = {
 }
 
 
+@pytest.mark.parametrize("stride", ["uint32", "exact"])
 @pytest.mark.parametrize("which,n", [("tiny", 1000), ("simu", 4099), ("mesh_dir", 513)])
-def test_grid_encode_fwd_bwd_vs_oracle(built_library, which, n):
-    cfg = GRID_CFGS[which]
+def test_grid_encode_fwd_bwd_vs_oracle(built_library, which, n, stride):
+    """Both grid_index arithmetics (tiny-cuda-nn's wrapping uint32 stride -- levels 12..14 / 12..16 of the 2^18 / 2^20
+    grids not hashed -- and the exact stride) against the oracle's restatement of each."""
+    cfg = dict(GRID_CFGS[which], index_stride=stride)
     enc = field_ref.HashGridRef(cfg, seed=3)
     with torch.no_grad():
         enc.params.copy_(torch.randn(enc.params.shape, generator=torch.Generator().manual_seed(1)) * 0.1)

@@ -21,7 +21,7 @@ def test_header_symbols_exported_and_bound(built_library):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(built_library, name)
-    assert built_library.avr_abi_version() == 1
+    assert built_library.avr_abi_version() == 2
 
 
 def test_renderer_refuses_cpu_tensors():
@@ -80,6 +80,34 @@ def test_grid_geometry_matches_oracle_and_survey(name):
                 assert a["size"][:4] == [4096, 32768, 262144, 262144]
             else:
                 assert a["total"] * 2 == 36249600
+
+
+@pytest.mark.parametrize("log2_size,wrapped", [(18, (12, 13, 14)), (20, (12, 13, 14, 15, 16))])
+def test_grid_index_stride_modes_known_answers(log2_size, wrapped):
+    """tiny-cuda-nn keeps the dense-index stride of ``grid_index`` in a uint32: at res = 2^16 .. hashmap size the second
+    ``stride *= res`` wraps to 0 and the level is NOT hashed (index = (x + y*res mod 2^32) % size).  Hand-computed
+    expectations for both modes of the oracle, level by level (the GPU kernels are checked against the oracle in
+    tests/test_gpu_kernels.py::test_grid_encode_fwd_bwd_vs_oracle)."""
+    base = {"base_resolution": 16, "log2_hashmap_size": log2_size, "n_features_per_level": 2, "n_levels": 20, "otype": "HashGrid"}
+    u = torch.tensor([[0.3, 0.6, 0.9], [0.123, 0.987, 0.5]])
+    size = 1 << log2_size
+    for mode in ("uint32", "exact"):
+        enc = field_ref.HashGridRef(dict(base, index_stride=mode))
+        for lvl in range(20):
+            res, scale = enc.geom["res"][lvl], enc.geom["scale"][lvl]
+            idx, _ = enc.corner_indices(u, lvl)
+            g = torch.floor((u.double() * scale + 0.5).float()).to(torch.int64)
+            x, y, z = g[:, 0], g[:, 1], g[:, 2]
+            h = ((x ^ ((y * 2654435761) & 0xFFFFFFFF) ^ ((z * 805459861) & 0xFFFFFFFF)) & 0xFFFFFFFF) % size
+            dense = res ** 3 <= size
+            if dense:
+                want = x + y * res + z * res * res
+            elif mode == "uint32" and lvl in wrapped:
+                want = ((x + y * res) & 0xFFFFFFFF) % size
+            else:
+                want = h
+            assert torch.equal(idx[:, 0], want), (mode, lvl)
+        assert [l for l in range(20) if 2 ** 16 <= enc.geom["res"][l] <= size] == list(wrapped)
 
 
 def test_parameter_counts_match_survey():
