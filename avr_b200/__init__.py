@@ -9,6 +9,7 @@ Public surface (mirrors the reference's ``renderer.py`` / ``model.py``):
 * ``FusedAdam``                                   <- clip / NaN scrub / Adam of avr_runner.py:192-200
 * ``Criterion(cfg_train, cfg_render)``            <- utils/criterion.py:7 (the training loss on rendered spectra)
 * ``save_checkpoint`` / ``load_checkpoint``       <- avr_runner.py:104-154 (same file format, both directions)
+* ``WaveLoader(base_folder, dataset_type, ...)``  <- datasets_loader.py:10 (the four on-disk dataset formats)
 
 The compute path is hand-written CUDA behind the C-ABI of ``include/avr_b200.h``
 (``avr_b200/libavr_b200.so``); there is no CPU or PyTorch fallback.
@@ -21,3 +22,4 @@ from .ddp import GradArena                                            # noqa: E4
 from .optim import FusedAdam                                          # noqa: E402,F401
 from .criterion import Criterion                                      # noqa: E402,F401
 from .checkpoint import load_checkpoint, save_checkpoint, latest_checkpoint   # noqa: E402,F401
+from .datasets import WaveLoader                                      # noqa: E402,F401

@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libavr_b200.so")
-SOURCES = ["abi.cu", "hashgrid.cu", "gemm.cu", "composite.cu", "umma_gemm.cu", "collapse.cu", "optim.cu", "criterion.cu"]
+SOURCES = ["abi.cu", "hashgrid.cu", "gemm.cu", "composite.cu", "umma_gemm.cu", "mlp_chain.cu", "collapse.cu", "optim.cu", "criterion.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -37,12 +37,14 @@ def save_checkpoint(path, renderer, optimizer=None, scheduler=None, current_iter
     return path
 
 
-def load_checkpoint(path, renderer, optimizer=None, scheduler=None, map_location=None) -> int:
+def load_checkpoint(path, renderer, optimizer=None, scheduler=None, map_location=None, trusted: bool = False) -> int:
     """Load a checkpoint written by the reference runners or by ``save_checkpoint``; -> ``current_iteration``.
 
     Network keys may carry the ``module.`` prefix of ``DataParallel`` / ``DDP``; shapes must match the configured
-    field exactly (a mismatch is an error, never a silent partial load)."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    field exactly (a mismatch is an error, never a silent partial load).  The file is read with
+    ``weights_only=True`` (tensors and plain containers -- all a reference checkpoint holds); ``trusted=True`` allows
+    arbitrary pickled objects for files of known origin."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=not trusted)
     state = ckpt[KEY_NET]
     if state and all(k.startswith("module.") for k in state):
         state = {k[len("module."):]: v for k, v in state.items()}

@@ -221,7 +221,9 @@ prefix_dot_kernel(const Geom geo, int width, PrefixWs ws, int tspan, const float
     for (int t = t_beg + warp; t < t_end; t += n_warps) {
         float p = 0.f;
         if (t >= dmin) {
-            const float* g = t < dmax ? gp_cell + (long long)(t - dmin) * width : gt;
+            // a cell whose delay spread exceeds tspan has no snapshots (they would lie outside its slice of the
+            // workspace): it reads the poisoned total instead -> NaN, never an out-of-bounds access
+            const float* g = (t < dmax && dmax - dmin <= tspan) ? gp_cell + (long long)(t - dmin) * width : gt;
             const float* wr = w_out + (long long)t * ldw;
             for (int c = lane * 4; c < width; c += 128) {
                 const float4 a = *reinterpret_cast<const float4*>(g + c);
@@ -247,7 +249,8 @@ __global__ void dwout_reduce_kernel(const Geom geo, int width, const float* __re
         const int dmin = __ldg(ws.range + 2 * i), dmax = __ldg(ws.range + 2 * i + 1);
         if (t < dmin) continue;
         const float g = __ldg(d_y + (long long)i * geo.T + t);
-        const float* src = t < dmax ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c : ws.gtot + (long long)i * width + c;
+        const float* src = (t < dmax && dmax - dmin <= tspan) ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c
+                                                              : ws.gtot + (long long)i * width + c;
         const float4 a = *reinterpret_cast<const float4*>(src);
         v.x = fmaf(g, a.x, v.x); v.y = fmaf(g, a.y, v.y); v.z = fmaf(g, a.z, v.z); v.w = fmaf(g, a.w, v.w);
     }

@@ -27,6 +27,7 @@
 #include <unordered_map>
 #include <stdlib.h>
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace avr {
 
@@ -74,157 +75,6 @@ struct UmmaParams {
     const __nv_bfloat16* b_raw; long long ldb, b_plane;
 };
 
-constexpr int UM = 128;            // UMMA_M
-constexpr int UBK = 64;            // k-block: 64 bf16 = one 128-byte swizzle row
-constexpr int UTHREADS = 320;       // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane group)
-constexpr uint32_t A_PLANE_BYTES = UM * 128;          // 16 KB
-constexpr uint32_t A_TILE_BYTES = 2 * A_PLANE_BYTES;  // hi + lo
-
-// ---------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// two TMEM loads in flight, one wait: the load latency is paid once per pair (each tcgen05.wait::ld stalls the warp)
-__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
-          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(ta), "r"(tb)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
-}
-
-// 32 columns of the main and of the small accumulator: two x32 loads, one wait; v = main + small * scale
-__device__ __forceinline__ void tmem_ld32_dual(uint32_t ta, uint32_t tb, float scale, float (&v)[32]) {
-    uint32_t r[64];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(ta), "r"(tb)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[32 + i]), scale, __uint_as_float(r[i]));
-}
-
-// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
-
-// store 8 consecutive values of one row as 2 (hi,mid) or 3 (hi,mid,lo) bf16 planes, 16 B per plane
-__device__ __forceinline__ void store_planes8(__nv_bfloat16* base, long long plane, const float* v, bool relu, int nplanes) {
-    uint32_t h[4], m[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float a = v[2 * i], b = v[2 * i + 1];
-        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-        const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
-        const __nv_bfloat16 am = __float2bfloat16_rn(ar), bm = __float2bfloat16_rn(br);
-        h[i] = pack2(ah, bh);
-        m[i] = pack2(am, bm);
-        l[i] = pack2(__float2bfloat16_rn(ar - __bfloat162float(am)), __float2bfloat16_rn(br - __bfloat162float(bm)));
-    }
-    *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + plane) = make_uint4(m[0], m[1], m[2], m[3]);
-    if (nplanes == 3) *reinterpret_cast<uint4*>(base + 2 * plane) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-constexpr int EPI_COLS = 32;                              // columns per staged chunk (64-byte rows, SWIZZLE_64B)
-constexpr uint32_t EPI_PLANE_BYTES = 32 * EPI_COLS * 2;   // 32 rows x 64 B = 2 KB per plane per warp
-
-// Split 32 fp32 values of one row into nplanes bf16 planes (packed pairs, registers only) ...
-template <int KIND>
-__device__ __forceinline__ void pack_planes32_k(const float* v, bool relu, uint32_t (&h)[16], uint32_t (&m)[16], uint32_t (&l)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float a = v[2 * i], b = v[2 * i + 1];
-        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        // packed conversions (cvt.rn.{bf16x2,f16x2}.f32): one instruction per pair and per plane; the epilogue is bound
-        // by the issue rate of its warps, so instruction count is what matters here
-        planes_pack2(KIND, a, b, h[i], m[i], l[i]);
-    }
-}
-__device__ __forceinline__ void pack_planes32(const float* v, bool relu, int kind, uint32_t (&h)[16], uint32_t (&m)[16],
-                                              uint32_t (&l)[16]) {
-    if (kind == AVR_PLANES_F16x2) pack_planes32_k<AVR_PLANES_F16x2>(v, relu, h, m, l);          // one branch per chunk,
-    else if (kind == AVR_PLANES_BF16x3) pack_planes32_k<AVR_PLANES_BF16x3>(v, relu, h, m, l);   // straight-line bodies
-    else pack_planes32_k<AVR_PLANES_BF16x2>(v, relu, h, m, l);
-}
 // ... and write them into the warp's staging tiles ([plane][32 rows][64 B], 64-byte swizzle: 16-byte chunk c of row r
 // lives at chunk c ^ ((r >> 1) & 3)).  Kept apart so that the conversions run BEFORE the warp waits for the previous
 // chunk's bulk store to release the staging tiles.
@@ -791,8 +641,8 @@ struct MapKeyHash {
         return (size_t)h;
     }
 };
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
-                    int box_rows, int nplanes, bool store_map = false) {
+int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
+             int box_rows, int nplanes, bool store_map) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     const MapKey key{base, rows, cols, ld, plane, box_rows, nplanes, store_map ? 1 : 0};
@@ -809,9 +659,10 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device) state: raised to the 227 KB opt-in limit once
-template <typename K>
-static int allow_max_smem(K kernel, int device) {
-    static std::atomic<uint64_t> done{0};
+template <bool MN_MAJOR>
+static int allow_max_smem(int device) {
+    static std::atomic<uint64_t> done{0};                        // one flag word per kernel instantiation
+    auto kernel = umma_gemm_kernel<MN_MAJOR>;
     const uint64_t bit = 1ull << (device & 63);
     if (done.load(std::memory_order_acquire) & bit) return AVR_OK;
     AVR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -839,7 +690,7 @@ static int tmem_cols_for(int bn, int dual = 0, int bufs = 2) {
     return c;
 }
 
-static int num_sms(int device) {
+int num_sms(int device) {
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
     return n > 0 ? n : 148;
@@ -994,7 +845,7 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         if (dual)
             if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, nc2, true)) return rc;
     }
-    if (int rc = allow_max_smem(umma_gemm_kernel<false>, device)) return rc;
+    if (int rc = allow_max_smem<false>(device)) return rc;
     const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
     const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
     umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, tc, tc2, p);
@@ -1075,7 +926,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
         CUtensorMap ta, tb;
         if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, na)) return rc;
         if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nb)) return rc;
-        if (int rc = allow_max_smem(umma_gemm_kernel<true>, device)) return rc;
+        if (int rc = allow_max_smem<true>(device)) return rc;
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
         umma_gemm_kernel<true><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, p);

@@ -38,7 +38,15 @@ NEAR_ZERO_GUARD = False  # forward layers: re-evaluate pre-activations too close
                          # (error ~6e-9*K, 3-5 flipped ReLU decisions per 1e7 vs 0-1 for fp32); with the main/small
                          # accumulator pair the forward is fp32-grade (2.1e-7 at K = 512, cuBLAS fp32: 2.4e-7) and the
                          # guard changes nothing measurable (profiles/r1/parity_real_networks.md), so it is off
+FUSE_SIGMA_CHAIN = True   # sigma encoder -> sigma decoder (all 128-wide layers, the fp32 density head) in ONE launch with the
+                          # activation tile resident in shared memory (ops.mlp_chain_fwd, csrc/mlp_chain.cu) instead of one
+                          # GEMM launch per layer -- bit-identical outputs; False runs the layers one by one (A/B, tests)
 LAST_GUARD_COUNTS = None  # diagnostics: per-layer number of re-evaluated elements of the latest forward (device tensor)
+
+
+def _lib_chain_max():
+    from ._lib import CHAIN_MAX_LAYERS
+    return CHAIN_MAX_LAYERS
 
 
 def _weight_planes(net, params, transpose, n):
@@ -137,45 +145,63 @@ class FusedRenderTC(torch.autograd.Function):
         if delay_slot:
             _, _, _, delay = ops.sample_points(geom, rays_o, pos_tx, dirs, d_vals, want_pts=False)
         w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_KIND)
-        acts_enc, bits_enc, h = [], [], x0
-        for li in range(len(w_enc) - 1):
-            y = PlanePair.empty(n_rows, w_enc[li].rows, dev, kind=FWD_KIND)
-            bits = ops.relu_bits_empty(n_rows, y.cols, dev)
-            fl, kw = layer_flags("enc", li)
-            ops.umma_nt(h, w_enc[li], fl, y, bits_out=bits, guard=guard, **kw)
-            acts_enc.append(y)
-            bits_enc.append(bits)
-            h = y
-        # sigma_feat lands directly in the signal network's input buffer (no concat)
         sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev, kind=FWD_KIND)
-        feat_win = sig_in.window(0, feat_dim)
+        feat_win = sig_in.window(0, feat_dim)                                # sigma_feat lands directly in the signal network's input buffer (no concat)
         bits_feat = ops.relu_bits_empty(n_rows, feat_dim, dev)               # (sigma_feat > 0)
-        if plan["sig_relu_feat"]:
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat, guard=guard)        # both consumers read relu(feat)
-            dec_in = feat_win
+        chain = (FUSE_SIGMA_CHAIN and guard is None and not any(k[0] in ("enc", "dec") for k in bias_of) and not plan["sig_relu_feat"] and feat_dim == 128
+                 and dec_net.in_pad == feat_dim and not plan.get("dec_tail") and enc_net.in_pad <= 128
+                 and all(o == 128 for (o, _) in enc_net.shapes) and all(o == 128 for (o, _) in dec_net.shapes[:-1])
+                 and dec_net.out_pad <= 128 and len(enc_net.shapes) + len(dec_net.shapes) <= _lib_chain_max())
+        if chain:
+            # ---- sigma encoder -> [relu] -> sigma decoder -> density head: one launch ----------------------------------
+            w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND)
+            acts_enc = [PlanePair.empty(n_rows, 128, dev, kind=ops.PLANES_BF16x2) for _ in w_enc[:-1]]   # weight gradients read 16 bits
+            bits_enc = [ops.relu_bits_empty(n_rows, 128, dev) for _ in w_enc[:-1]]
+            acts_dec = [PlanePair.empty(n_rows, 128, dev, kind=FWD_KIND) for _ in w_dec[:-1]]             # ... 24 along the decoder
+            bits_dec = [ops.relu_bits_empty(n_rows, 128, dev) for _ in w_dec[:-1]]
+            dec_in = PlanePair.empty(n_rows, dec_net.in_pad, dev, kind=FWD_KIND)
+            dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
+            layers = [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_enc[:-1], acts_enc, bits_enc)]
+            layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win, save=dec_in, bits=bits_feat))   # raw feat + relu(feat)
+            layers += [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_dec[:-1], acts_dec, bits_dec)]
+            layers.append(dict(w=w_dec[-1], relu=False, out_f32=dec_out))                                 # the |leaky_relu| kink follows
+            ops.mlp_chain_fwd(x0, layers)
         else:
-            dec_buf = PlanePair.empty(n_rows, dec_net.in_pad, dev, kind=FWD_KIND)
-            ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_buf.window(0, feat_dim), bits_out=bits_feat, guard=guard)   # raw feat + relu(feat)
-            if dec_net.in_pad > feat_dim:                                    # decoder input = [relu(feat), embedding row]
-                _assemble(plan.get("dec_tail", []), dec_buf, feat_dim, dec_net.in_pad, geom, small_in, rays_o, pos_tx, dirs,
-                          d_vals, params_of, [], rows_of)
-            dec_in = dec_buf
-        if dec_in.cols != dec_net.in_pad:
-            raise NotImplementedError("sigma decoder input width does not match the sigma feature width")
+            acts_enc, bits_enc, h = [], [], x0
+            for li in range(len(w_enc) - 1):
+                y = PlanePair.empty(n_rows, w_enc[li].rows, dev, kind=FWD_KIND)
+                bits = ops.relu_bits_empty(n_rows, y.cols, dev)
+                fl, kw = layer_flags("enc", li)
+                ops.umma_nt(h, w_enc[li], fl, y, bits_out=bits, guard=guard, **kw)
+                acts_enc.append(y)
+                bits_enc.append(bits)
+                h = y
+            if plan["sig_relu_feat"]:
+                ops.umma_nt(h, w_enc[-1], ops.UMMA_RELU, feat_win, bits_out=bits_feat, guard=guard)        # both consumers read relu(feat)
+                dec_in = feat_win
+            else:
+                dec_buf = PlanePair.empty(n_rows, dec_net.in_pad, dev, kind=FWD_KIND)
+                ops.umma_nt(h, w_enc[-1], ops.UMMA_DUAL_RELU, feat_win, dec_buf.window(0, feat_dim), bits_out=bits_feat, guard=guard)   # raw feat + relu(feat)
+                if dec_net.in_pad > feat_dim:                                    # decoder input = [relu(feat), embedding row]
+                    _assemble(plan.get("dec_tail", []), dec_buf, feat_dim, dec_net.in_pad, geom, small_in, rays_o, pos_tx, dirs,
+                              d_vals, params_of, [], rows_of)
+                dec_in = dec_buf
+            if dec_in.cols != dec_net.in_pad:
+                raise NotImplementedError("sigma decoder input width does not match the sigma feature width")
 
-        # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
-        w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND)
-        acts_dec, bits_dec, h = [], [], dec_in
-        for li in range(len(w_dec) - 1):
-            y = PlanePair.empty(n_rows, w_dec[li].rows, dev, kind=FWD_KIND)
-            bits = ops.relu_bits_empty(n_rows, y.cols, dev)
-            fl, kw = layer_flags("dec", li)
-            ops.umma_nt(h, w_dec[li], fl, y, bits_out=bits, guard=guard, **kw)
-            acts_dec.append(y)
-            bits_dec.append(bits)
-            h = y
-        dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
-        ops.umma_nt(h, w_dec[-1], ops.UMMA_OUT_F32, c_f32=dec_out, guard=guard)   # the |leaky_relu| kink
+            # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
+            w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND)
+            acts_dec, bits_dec, h = [], [], dec_in
+            for li in range(len(w_dec) - 1):
+                y = PlanePair.empty(n_rows, w_dec[li].rows, dev, kind=FWD_KIND)
+                bits = ops.relu_bits_empty(n_rows, y.cols, dev)
+                fl, kw = layer_flags("dec", li)
+                ops.umma_nt(h, w_dec[li], fl, y, bits_out=bits, guard=guard, **kw)
+                acts_dec.append(y)
+                bits_dec.append(bits)
+                h = y
+            dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
+            ops.umma_nt(h, w_dec[-1], ops.UMMA_OUT_F32, c_f32=dec_out, guard=guard)   # the |leaky_relu| kink
         w, _ = ops.ray_weights_fwd(geom, dec_out, dec_out.stride(0), tables["delta"], plan["slope"])
 
         # ---- signal network hidden layers + collapsed output layer ---------------------------------

@@ -421,6 +421,39 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
             _p(ws), ws.numel() * 4 if ws is not None else 0, dev, st), "avr_umma_gemm_nt")
 
 
+def mlp_chain_fwd(x0: PlanePair, layers):
+    """Fused chain of 128-wide dense layers on one launch (``avr_mlp_chain_fwd``): ``y_{l+1} = act_l(y_l W_l^T)``.
+
+    ``x0``: BF16x3 plane set ``[M, k0]``.  ``layers``: dicts with ``w`` (BF16x3 planes of ``W[n_out, k_in]``), ``relu``
+    (bool) and the optional outputs ``save`` (PlanePair, rectified output), ``save_raw`` (PlanePair, raw output), ``bits``
+    (int32 ReLU bitmask), ``out_f32`` (fp32 ``[M, >= n_out]`` tensor; last layer only).  Bit-identical to running the
+    layers through ``umma_nt`` one by one."""
+    dev, st = _ctx(x0)
+    assert x0.kind == PLANES_BF16x3, "the chain input must be a bf16 triple"
+    n = len(layers)
+    arr = (_lib.ChainLayer * n)()
+    flops = 0.0
+    for a, L in zip(arr, layers):
+        w = L["w"]
+        assert w.kind == PLANES_BF16x3
+        a.w, a.ldw, a.w_plane, a.n_out, a.k_in = w.ptr.value, w.ld, w.plane, w.rows, w.cols
+        a.relu = 1 if L.get("relu") else 0
+        sv, raw, bits, o32 = L.get("save"), L.get("save_raw"), L.get("bits"), L.get("out_f32")
+        if sv is not None:
+            assert sv.rows == x0.rows and sv.cols == w.rows
+            a.save, a.ld_save, a.save_plane, a.save_kind = sv.ptr.value, sv.ld, sv.plane, sv.kind
+        if raw is not None:
+            assert raw.rows == x0.rows and raw.cols == w.rows
+            a.save_raw, a.ld_raw, a.raw_plane, a.raw_kind = raw.ptr.value, raw.ld, raw.plane, raw.kind
+        if bits is not None:
+            a.bits, a.ldbits = _p(bits, torch.int32).value, bits.stride(0)
+        if o32 is not None:
+            a.out_f32, a.ld_f32 = _p(o32).value, o32.stride(0)
+        flops += 2.0 * x0.rows * w.rows * w.cols
+    with _timed("mlp_chain", flops, "flop", 6.0 * flops):
+        _lib.check(_lib.load().avr_mlp_chain_fwd(x0.rows, x0.ptr, x0.ld, x0.plane, x0.cols, arr, n, dev, st), "avr_mlp_chain_fwd")
+
+
 def umma_tn_workspace_bytes(M, N, K) -> int:
     return int(_lib.load().avr_umma_gemm_tn_workspace_bytes(M, N, K))
 

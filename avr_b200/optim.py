@@ -21,6 +21,12 @@ class FusedAdam(torch.optim.Optimizer):
     A ``torch.optim.Optimizer``: ``param_groups[0]["lr"]`` is what ``step`` uses, so ``CosineAnnealingLR``
     (avr_runner.py:71,200) drives it unchanged, and ``state_dict`` / ``load_state_dict`` speak ``torch.optim.Adam``'s
     format, so the ``optimizer_state_dict`` of a reference checkpoint (avr_runner.py:122,150) loads and saves.
+
+    Known deviation: the update always covers the whole arena with ONE step count.  ``torch.optim.Adam`` skips a
+    parameter whose ``.grad`` is ``None`` (no moment decay, no weight decay, its own step count); here a parameter that
+    received no gradient in a step (``layer_embeddings`` when ``ch_idx`` is None) is updated with a zero gradient, like
+    ``torch.optim.Adam`` after ``zero_grad(set_to_none=False)``.  The fused render step produces a gradient for every
+    field parameter on every step, so the two agree whenever ``ch_idx`` is passed consistently.
     """
 
     def __init__(self, parameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0,

@@ -2,22 +2,34 @@
 """Headline benchmark: rendered IRs/sec (forward + backward) of the AVR render hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config simu] [--bs 4]
+                    [--mode train|infer] [--receivers M] [--no-other-configs] [--no-cpu-baseline]
 
 A *step* is one forward + backward pass of ``AVRRender`` (ray generation, hash-grid encode, MLPs,
 compositing, spectrum; loss = sum of squares of the ``[bs,F,2]`` IR spectrum) over one synthetic batch of
 ``bs`` receivers per GPU at the ``avr_simu.yml`` shape (BASELINE.json configs[1]), plus -- for N > 1 -- the
-gradient all-reduce of the data-parallel step (weak scaling: ``bs`` receivers per GPU).  No optimizer
+gradient exchange of the data-parallel step (weak scaling: ``bs`` receivers per GPU).  No optimizer
 update is part of the metric ("receivers*steps / time for forward+backward").
 
-Two numbers per run: ``value`` (inputs resident in HBM) and ``e2e`` (host buffers: pinned H2D of the
-receiver/transmitter positions and a D2H read of the rendered spectra every step).  ``--impl reference``
-times the CPU oracle (``oracle/``: restatement of renderer_cpu.py + the tcnn field in fp32 torch) on the
-host cores instead -- the reference is a Python repo whose own runner needs tiny-cuda-nn, so its CPU
-path is the oracle port.
+What the JSON line holds, and how each number was taken:
+
+* ``value``       K steps, inputs resident in HBM, NO per-kernel events, one CUDA-event pair around the K steps, max over ranks.
+* ``e2e``         the same K steps through ``AVRRender.forward`` with pinned HOST inputs: H2D of the positions (and the
+                  per-step direction table) and an asynchronous D2H of the spectra into a pinned buffer every step; the
+                  steps are not synchronised one by one (throughput, not latency), the region ends with a full sync.
+* ``kernels`` / ``roofline``   a THIRD pass with CUDA events around every library call (``ops.PROFILE``).
+* ``grid_grad_atomic``         the same workload with fp32-atomic table gradients instead of the deterministic default.
+* ``other_configs``            the other BASELINE shapes (configs[2..4]) measured in this very run, 5 steps each, through the
+                               same code path and -- under torchrun -- with the same gradient exchange.
+* ``cpu_baseline`` / ``--impl reference``   the CPU oracle (``oracle/``: restatement of renderer_cpu.py + the tcnn field in
+                  fp32 torch; the reference's own runner needs tiny-cuda-nn) on the host cores: ONE receiver per step at
+                  the FULL ray count, measured seconds, nothing extrapolated; ``config`` says so.
+* ``grad_checksums``           (N > 1) float64 sum of every rank's gradient arena after the exchange; the run fails unless
+                  they are equal.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -33,22 +45,28 @@ import torch  # noqa: E402
 
 METRIC = "rendered IRs/sec (fwd+bwd)"
 UNIT = "IR/s"
+WHICH = {"simu": 1, "raf_furnished": 2, "meshrir": 3, "real_exp_ch_emb_1": 4}
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="simu")
     ap.add_argument("--bs", type=int, default=4, help="receivers per GPU per step")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
-                    help="train: fwd+bwd (+ gradient all-reduce); infer: no_grad forward only (BASELINE configs[3])")
-    ap.add_argument("--overlap", action="store_true",
-                    help="per-tensor gradient all-reduces issued inside the backward pass (GradArena.attach) instead of "
-                         "one all-reduce of the flat arena after it; measured slower at 8 GPUs (DESIGN 7), off by default")
+                    help="train: fwd+bwd (+ gradient exchange); infer: no_grad forward only (BASELINE configs[3])")
+    ap.add_argument("--receivers", type=int, default=0,
+                    help="infer mode: render this many receivers in total (e.g. 3969 = MeshRIR S1-M3969), sharded over the "
+                         "ranks in DistributedSampler order, --bs receivers per pass; the result is all-gathered")
+    ap.add_argument("--grid-grad", default="deterministic", choices=["deterministic", "atomic"])
+    ap.add_argument("--flat-allreduce", action="store_true",
+                    help="N > 1: all-reduce the whole gradient arena (round-1 behaviour) instead of exchanging the per-ray / "
+                         "per-receiver table gradients as rows (GradArena.attach)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -74,18 +92,22 @@ def synthetic_inputs(render, bs, seed):
     return rx.float(), tx.float(), dtx.float()
 
 
+def meshrir_grid(n):
+    """receivers on a regular 63 x 63 grid over [-0.5, 0.5]^2 at z = 0, one transmitter at (2, 0, 0)."""
+    side = int(round(n ** 0.5))
+    if side * side == n:
+        ax = torch.linspace(-0.5, 0.5, side)
+        gx, gy = torch.meshgrid(ax, ax, indexing="ij")
+        rx = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.zeros(n)], 1)
+    else:
+        rx = torch.cat([torch.rand(n, 2, generator=torch.Generator().manual_seed(3)) - 0.5, torch.zeros(n, 1)], 1)
+    tx = torch.tensor([[2.0, 0.0, 0.0]]).expand(n, 3).contiguous()
+    return rx.float(), tx.float()
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline of the native line, and the whole --impl reference arm)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_config(cfg, ray_div):
-    """A bounded sample of the workload: same samples/ray, IR length and networks, 1/ray_div of the rays."""
-    import copy
-    c = copy.deepcopy(cfg)
-    c["render"]["n_azi"] = max(2, cfg["render"]["n_azi"] // ray_div[0])
-    c["render"]["n_ele"] = max(2, cfg["render"]["n_ele"] // ray_div[1])
-    return c
-
-
 def cpu_oracle_step_fn(cfg, bs, seed=0):
     from oracle import field_ref, render_ref
     cls = field_ref.AVRModelRef if cfg["model_class"] == "AVRModel" else field_ref.AVRModelComplexRef
@@ -102,24 +124,27 @@ def cpu_oracle_step_fn(cfg, bs, seed=0):
     return step
 
 
-def time_cpu_oracle(cfg, steps, warmup, ray_div=(4, 2)):
-    """-> (IR/s extrapolated to the full ray count, seconds per sample step, description)."""
+def time_cpu_oracle(cfg, steps, warmup, budget_s):
+    """ONE receiver per step at the FULL ray count through the oracle, fwd+bwd, all host threads.
+    -> (IR/s = 1 / seconds per step, seconds per step, steps actually timed, description).  Nothing is extrapolated;
+    the run stops early once ``budget_s`` seconds of timed work are spent (steps are 5-15 s each)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    full_rays = cfg["render"]["n_azi"] * cfg["render"]["n_ele"] + 2
-    sample = cpu_sample_config(cfg, ray_div)
-    rays = sample["render"]["n_azi"] * sample["render"]["n_ele"] + 2
-    step = cpu_oracle_step_fn(sample, 1)
-    for _ in range(warmup):
+    step = cpu_oracle_step_fn(cfg, 1)
+    for _ in range(min(warmup, 1)):                          # one full-size warm-up pays first-touch of the ~8 GB working set
         step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    done, t0 = 0, time.perf_counter()
+    while done < max(1, steps):
         step()
-    dt = (time.perf_counter() - t0) / max(1, steps)
-    ir_per_s = 1.0 / (dt * full_rays / rays)
-    desc = (f"1 receiver, {rays} of {full_rays} rays (n_azi={sample['render']['n_azi']}, n_ele={sample['render']['n_ele']}), "
-            f"S={cfg['render']['n_samples']}, T={cfg['model']['signal_output_dim']}, fwd+bwd through oracle/ (fp32 torch CPU), "
-            f"{dt:.2f} s per sample step, scaled linearly in rays")
-    return ir_per_s, dt, desc
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    r = cfg["render"]
+    rays = r["n_azi"] * r["n_ele"] + 2
+    desc = (f"1 receiver per step at the full ray count ({rays} rays x {r['n_samples']} samples, T={cfg['model']['signal_output_dim']}), "
+            f"fwd+bwd through oracle/ (fp32 torch CPU, {torch.get_num_threads()} threads), {done} timed step(s) of {dt:.2f} s, "
+            f"measured (no extrapolation)")
+    return 1.0 / dt, dt, done, desc
 
 
 def run_reference(args, cfg):
@@ -127,12 +152,15 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    val, dt, desc = time_cpu_oracle(cfg, args.steps, args.warmup, ray_div=(4, 2))
+    val, dt, done, desc = time_cpu_oracle(cfg, args.steps, args.warmup, budget_s=150.0)
+    ns = argparse.Namespace(**vars(args))
+    ns.bs, ns.mode = 1, "train"
+    config = workload_config(cfg, ns, 1)
+    config["sample"] = "the CPU arm renders 1 receiver per step (the GPU arm's step is %d receivers per GPU); rays, samples, IR length and networks are the full-size ones" % args.bs
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg, args, 1),
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -143,13 +171,14 @@ def run_reference(args, cfg):
 def workload_config(cfg, args, world):
     r = cfg["render"]
     R = r["n_azi"] * r["n_ele"] + 2
-    which = {"simu": 1, "raf_furnished": 2, "meshrir": 3, "real_exp_ch_emb_1": 4}.get(args.config, 1)
+    which = WHICH.get(args.config, 1)
     what = "fwd+bwd" if args.mode == "train" else "inference (no_grad forward)"
     return {"workload": f"avr_{args.config}.yml render step (BASELINE configs[{which}]): {what}, {args.bs} receivers/GPU",
             "rays": R, "samples_per_ray": r["n_samples"], "ir_len": cfg["model"]["signal_output_dim"],
             "receivers_per_gpu": args.bs, "global_receivers": args.bs * world, "field": cfg["model_class"],
             "parallelism": f"dp{world}", "weights": "random init (hash tables N(0,0.1))",
-            "l2": "per-step working set (activations + signal tensor, >10 GB) >> 126 MB L2; no explicit flush"}
+            "grid_grad": getattr(args, "grid_grad", "deterministic"),
+            "l2": "per-step working set (activations, >10 GB) >> 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,7 +192,7 @@ class ClockSampler:
         self.proc, self.path = None, f"/tmp/avr_clocks_{os.getpid()}.csv"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -200,11 +229,174 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
-def run_native(args, cfg):
+class Workload:
+    """One (config, batch, mode) on this rank's GPU: field, renderer, gradient arena, synthetic host + device inputs."""
+
+    def __init__(self, name, bs, mode, grid_grad, dev, rank, world, flat_allreduce=False):
+        import avr_b200
+        from avr_b200.configs import get_config
+        self.name, self.bs, self.mode, self.dev, self.world = name, bs, mode, dev, world
+        self.cfg = cfg = get_config(name)
+        cls = avr_b200.AVRModel if cfg["model_class"] == "AVRModel" else avr_b200.AVRModel_complex
+        field = cls(cfg["model"], seed=1337)                       # same init on every rank (DDP broadcast semantics)
+        with torch.no_grad():
+            g = torch.Generator().manual_seed(7)
+            for m in field.modules():
+                if isinstance(m, avr_b200.Encoding):
+                    m.params.copy_(torch.randn(m.params.shape, generator=g) * 0.1)
+        self.field = field.to(dev)
+        self.ren = avr_b200.AVRRender(self.field, **cfg["render"], max_receivers_per_pass=bs, grid_grad=grid_grad)
+        self.arena = avr_b200.GradArena(self.ren.parameters())
+        if world > 1 and mode == "train" and not flat_allreduce:
+            self.arena.attach(self.ren)
+        self.complex_field = cfg["model_class"] != "AVRModel"
+        rx_h, tx_h, dtx_h = synthetic_inputs(cfg["render"], bs, 100 + rank)
+        self.host = (rx_h.pin_memory(), tx_h.pin_memory(), dtx_h.pin_memory())
+        self.device = tuple(t.to(dev) for t in self.host)
+        self.ch = (torch.arange(bs, device=dev) % 8) if name == "real_exp_ch_emb_1" else None    # one 8-mic array (SURVEY 8d)
+        self.F = cfg["model"]["signal_output_dim"] // 2 + 1
+        self.out_h = torch.empty(bs, self.F, 2).pin_memory()
+
+    def step(self, host_io: bool):
+        dev = self.dev
+        self.arena.zero_()
+        if host_io:
+            rx, tx = self.host[0].to(dev, non_blocking=True), self.host[1].to(dev, non_blocking=True)
+            dtx = self.host[2].to(dev, non_blocking=True) if self.complex_field else None
+        else:
+            rx, tx, dtx = self.device[0], self.device[1], (self.device[2] if self.complex_field else None)
+        if self.mode == "infer":
+            with torch.no_grad():
+                out = self.ren(rx, tx, dtx, ch_idx=self.ch)
+        else:
+            out = self.ren(rx, tx, dtx, ch_idx=self.ch)
+            out.square().sum().backward()
+            self.arena.all_reduce_mean()
+        if host_io:
+            self.out_h.copy_(out.detach(), non_blocking=True)
+
+    def timed(self, host_io, steps, profile=False):
+        import torch.distributed as dist
+        from avr_b200 import _lib, ops
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.PROFILE = [] if profile else None
+        _lib.launch_count(reset=True)
+        e0.record()
+        for _ in range(steps):
+            self.step(host_io)
+        e1.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        launches = _lib.launch_count()
+        prof, ops.PROFILE = ops.PROFILE, None
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, prof
+
+    def h2d_bytes(self):
+        r = self.cfg["render"]
+        return int(self.host[0].numel() * 4 * (3 if self.complex_field else 2) + (r["n_azi"] * r["n_ele"] + 2) * 12)
+
+    def close(self):
+        self.ren = self.field = self.arena = None
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def kernel_table(prof, steps, ms_total, pk):
+    per = {}
+    for name, work, unit, s, e, executed in prof:
+        d = per.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0, "unit": unit, "executed": 0.0})
+        d["ms"] += s.elapsed_time(e); d["work"] += work; d["n"] += 1; d["executed"] += executed
+    kernels = {}
+    for name, d in per.items():
+        rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
+        if d["unit"] == "flop":
+            kernels[name] = {"bound": "tensor", "achieved": rate / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
+                             "frac": rate / 1e12 / pk["tensor"], "launches_per_step": d["n"] / steps,
+                             "ms_per_step": d["ms"] / steps, "share_of_step": d["ms"] / ms_total,
+                             "tensor_pipe_tflops": d["executed"] / (d["ms"] * 1e-3) / 1e12,
+                             "tensor_pipe_frac": d["executed"] / (d["ms"] * 1e-3) / 1e12 / pk["tensor"]}
+        else:
+            kernels[name] = {"bound": "hbm", "achieved": rate / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": rate / 1e9 / pk["hbm"], "launches_per_step": d["n"] / steps,
+                             "ms_per_step": d["ms"] / steps, "share_of_step": d["ms"] / ms_total}
+    return kernels
+
+
+def run_sharded_inference(args, cfg, dev, rank, world):
+    """BASELINE configs[3]: render ALL receivers of a scene once (MeshRIR S1-M3969: 3969 positions), sharded over the ranks
+    in DistributedSampler order (tools/README.md:3-5, eval_rotate_doa_avr.py:104-110), no collective on the data path; the
+    ``[n_local, F, 2]`` spectra are all-gathered at the end."""
     import torch.distributed as dist
 
     import avr_b200
-    from avr_b200 import _lib, ops
+    from avr_b200 import _lib
+    from avr_b200.ddp import shard_receivers
+    w = Workload(args.config, args.bs, "infer", args.grid_grad, dev, rank, world)
+    n = args.receivers
+    rx_all, tx_all = meshrir_grid(n)
+    mine = shard_receivers(n, rank, world)
+    rx_h, tx_h = rx_all[mine].pin_memory(), tx_all[mine].pin_memory()
+    free, _ = torch.cuda.mem_get_info(dev)
+    w.ren.max_receivers_per_pass = args.bs
+    out_h = torch.empty(len(mine), w.F, 2).pin_memory()
+
+    def render_all():
+        with torch.no_grad():
+            out = w.ren(rx_h.to(dev, non_blocking=True), tx_h.to(dev, non_blocking=True))
+            if world > 1:
+                gathered = torch.empty(world * out.shape[0], *out.shape[1:], device=dev)
+                dist.all_gather_into_tensor(gathered, out.contiguous())
+            out_h.copy_(out, non_blocking=True)
+        return out
+
+    with torch.no_grad():                                        # warm-up: one pass of --bs receivers
+        w.ren(rx_h[:args.bs].to(dev), tx_h[:args.bs].to(dev))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    _lib.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = render_all()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        ns = argparse.Namespace(**vars(args))
+        config = workload_config(cfg, ns, world)
+        config.update({"workload": f"avr_{args.config}.yml: inference render of all {n} receivers of a scene, sharded over "
+                                   f"{world} GPU(s) in DistributedSampler order, {args.bs} receivers per pass",
+                       "global_receivers": n, "receivers_per_gpu": len(mine), "free_hbm_gb_before": free / 1e9})
+        line = {"metric": "rendered IRs/sec (inference, all receivers of a scene)", "value": n / (ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(rx_h.numel() * 8),
+                        "d2h_bytes_per_step": int(out_h.numel() * 4),
+                        "note": "host positions in, spectra out to pinned host memory: this mode IS the end-to-end call"},
+                "gpu_launches": int(launches), "finite": bool(torch.isfinite(out).all())}
+        print(json.dumps(line), flush=True)
+
+
+def run_native(args, cfg):
+    import torch.distributed as dist
+
+    from avr_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,102 +417,79 @@ def run_native(args, cfg):
             os.dup2(saved, 1)
             os.close(saved)
     _lib.load()
-
-    cls = avr_b200.AVRModel if cfg["model_class"] == "AVRModel" else avr_b200.AVRModel_complex
-    field = cls(cfg["model"], seed=1337)                       # same init on every rank (DDP broadcast semantics)
-    with torch.no_grad():
-        g = torch.Generator().manual_seed(7)
-        for m in field.modules():
-            if isinstance(m, avr_b200.Encoding):
-                m.params.copy_(torch.randn(m.params.shape, generator=g) * 0.1)
-    field = field.to(dev)
-    ren = avr_b200.AVRRender(field, **cfg["render"], max_receivers_per_pass=args.bs)
-    arena = avr_b200.GradArena(ren.parameters())
-    overlap = world > 1 and args.overlap
-    if overlap:
-        arena.attach(ren)
-    complex_field = cfg["model_class"] != "AVRModel"
-
-    rx_h, tx_h, dtx_h = synthetic_inputs(cfg["render"], args.bs, 100 + rank)
-    rx_h, tx_h, dtx_h = rx_h.pin_memory(), tx_h.pin_memory(), dtx_h.pin_memory()
-    rx_d, tx_d, dtx_d = rx_h.to(dev), tx_h.to(dev), dtx_h.to(dev)
-    F = cfg["model"]["signal_output_dim"] // 2 + 1
-    out_h = torch.empty(args.bs, F, 2).pin_memory()
-
-    def step(host_io: bool):
-        arena.zero_()
-        if host_io:
-            rx, tx = rx_h.to(dev, non_blocking=True), tx_h.to(dev, non_blocking=True)
-            dtx = dtx_h.to(dev, non_blocking=True) if complex_field else None
-        else:
-            rx, tx, dtx = rx_d, tx_d, (dtx_d if complex_field else None)
-        if args.mode == "infer":
-            with torch.no_grad():
-                out = ren(rx, tx, dtx)
-        else:
-            out = ren(rx, tx, dtx)
-            out.square().sum().backward()
-            if not overlap:
-                arena.all_reduce_mean()
-        if host_io:
-            out_h.copy_(out.detach(), non_blocking=True)
-
-    def timed(host_io, steps, profile):
+    if args.mode == "infer" and args.receivers > 0:
+        run_sharded_inference(args, cfg, dev, rank, world)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ops.PROFILE = [] if profile else None
-        _lib.launch_count(reset=True)
-        e0.record()
-        for _ in range(steps):
-            step(host_io)
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        launches = _lib.launch_count()
-        prof, ops.PROFILE = ops.PROFILE, None
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, launches, prof
+            dist.destroy_process_group()
+        return
 
-    for _ in range(max(3, args.warmup)):
-        step(False)
+    pk = peaks()
+    warm = max(3, args.warmup)
+    w = Workload(args.config, args.bs, args.mode, args.grid_grad, dev, rank, world, args.flat_allreduce)
+    for _ in range(warm):
+        w.step(False)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches, prof = timed(False, args.steps, profile=True)
-    clocks = sampler.stop() if sampler else None
-    step(True)
-    ms_e2e, _, _ = timed(True, args.steps, profile=False)
+    ms, launches, _ = w.timed(False, args.steps)                         # headline: no per-kernel events
+    w.step(True)
+    ms_e2e, _, _ = w.timed(True, args.steps)
+    prof_steps = min(args.steps, 5)
+    ms_prof, _, prof = w.timed(False, prof_steps, profile=True)          # third pass: CUDA events around every library call
+    checksums = None
+    if world > 1 and args.mode == "train":
+        cs = torch.tensor([w.arena.checksum()], dtype=torch.float64, device=dev)
+        allc = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allc, cs)
+        checksums = [float(c) for c in allc]
+        if len(set(checksums)) != 1:
+            raise SystemExit(f"gradient arenas differ across ranks after the exchange: {checksums}")
+    grad_bytes = int(w.arena.reduce_numel * 4) if world > 1 and args.mode == "train" else 0
+    arena_bytes = int(w.arena.numel() * 4)
+    h2d, d2h = w.h2d_bytes(), int(w.out_h.numel() * 4)
+    w.close()
 
     total_ir = args.bs * world * args.steps
     value = total_ir / (ms * 1e-3)
     e2e = total_ir / (ms_e2e * 1e-3)
 
+    # the same workload with the other accumulation mode of the hash-table gradients
+    other_mode = "atomic" if args.grid_grad == "deterministic" else "deterministic"
+    alt = None
+    if args.mode == "train":
+        w2 = Workload(args.config, args.bs, args.mode, other_mode, dev, rank, world, args.flat_allreduce)
+        for _ in range(warm):
+            w2.step(False)
+        ms2, _, _ = w2.timed(False, args.steps)
+        alt = {"grid_grad": other_mode, "value": total_ir / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps}
+        w2.close()
+
+    others = {}
+    if not args.no_other_configs and args.config == "simu" and args.mode == "train":
+        plan = [("raf_furnished", 4, "train"), ("real_exp_ch_emb_1", 8, "train"), ("meshrir", 4, "train"), ("meshrir", 8, "infer")]
+        for name, bs, mode in plan:
+            wo = Workload(name, bs, mode, args.grid_grad, dev, rank, world, args.flat_allreduce)
+            for _ in range(3):
+                wo.step(False)
+            mso, lo, _ = wo.timed(False, 5)
+            mse, _, _ = wo.timed(True, 5)
+            msp, _, profo = wo.timed(False, 2, profile=True)
+            if rank == 0:
+                ko = kernel_table(profo, 2, msp, pk)
+                dom = max(ko, key=lambda k: ko[k]["ms_per_step"]) if ko else None
+                ns = argparse.Namespace(**vars(args)); ns.config, ns.bs, ns.mode = name, bs, mode
+                others[f"{name}:{mode}"] = {
+                    "metric": METRIC if mode == "train" else "rendered IRs/sec (inference)",
+                    "value": bs * world * 5 / (mso * 1e-3), "unit": UNIT, "ms_per_step": mso / 5, "steps": 5, "warmup": 3,
+                    "e2e": {"value": bs * world * 5 / (mse * 1e-3), "unit": UNIT}, "gpu_launches": int(lo),
+                    "config": workload_config(wo.cfg, ns, world),
+                    "roofline": dict(ko[dom], kernel=dom) if dom else None,
+                    "grad_exchange_bytes": int(wo.arena.reduce_numel * 4) if world > 1 and mode == "train" else 0}
+            wo.close()
+    clocks = sampler.stop() if sampler else None
+
     if rank == 0:
-        pk = peaks()
-        per = {}
-        for name, work, unit, s, e, executed in prof:
-            d = per.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0, "unit": unit, "executed": 0.0})
-            d["ms"] += s.elapsed_time(e); d["work"] += work; d["n"] += 1; d["executed"] += executed
-        kernels = {}
-        for name, d in per.items():
-            rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
-            if d["unit"] == "flop":
-                kernels[name] = {"bound": "tensor", "achieved": rate / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
-                                 "frac": rate / 1e12 / pk["tensor"], "launches_per_step": d["n"] / args.steps,
-                                 "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / ms,
-                                 "tensor_pipe_tflops": d["executed"] / (d["ms"] * 1e-3) / 1e12,
-                                 "tensor_pipe_frac": d["executed"] / (d["ms"] * 1e-3) / 1e12 / pk["tensor"]}
-            else:
-                kernels[name] = {"bound": "hbm", "achieved": rate / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                 "frac": rate / 1e9 / pk["hbm"], "launches_per_step": d["n"] / args.steps,
-                                 "ms_per_step": d["ms"] / args.steps, "share_of_step": d["ms"] / ms}
+        kernels = kernel_table(prof, prof_steps, ms_prof, pk)
         if os.environ.get("AVR_BENCH_DETAIL"):
-            per_step = len(prof) // args.steps
+            per_step = len(prof) // prof_steps
             for name, work, unit, s0, e0, _ex in prof[-per_step:]:
                 t = s0.elapsed_time(e0)
                 rate = work / (t * 1e-3) / (1e12 if unit == "flop" else 1e9)
@@ -328,7 +497,7 @@ def run_native(args, cfg):
         dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
         roof = dict(kernels[dominant]) if dominant else {}
         traffic, traffic_src = None, None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "umma_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "umma_traffic.json")
         if dominant == "umma_gemm" and args.config == "simu" and args.bs == 4 and os.path.exists(tpath):
             # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture of this very
             # command (profilers are never run inside a timed bench); null for any other workload
@@ -337,23 +506,28 @@ def run_native(args, cfg):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         roof.update({"kernel": dominant, "traffic": traffic, "traffic_unit": "DRAM bytes per launch", "traffic_source": traffic_src,
                      "peak_source": pk["src"],
-                     "note": "achieved = algorithmic flops (2MNK of the fp32-grade product) or bytes (SURVEY 8d) of the timed "
-                             "launches / their CUDA-event time inside the timed region; each algorithmic product costs 3 "
-                             "(backward bf16 pairs, forward fp16 pairs) or 6 (forward bf16 triples) tcgen05 products, see tensor_pipe_*"})
+                     "note": "achieved = algorithmic flops (2MNK of the fp32-grade product) or bytes (SURVEY 8d) of the launches "
+                             "of the profiling pass / their CUDA-event time; each algorithmic product costs 3 (backward bf16 "
+                             "pairs, forward fp16 pairs) or 6 (forward bf16 triples) tcgen05 products, see tensor_pipe_*"})
         cpu = None
         if not args.no_cpu_baseline:
-            v, dt, desc = time_cpu_oracle(cfg, steps=1, warmup=1, ray_div=(4, 2))
+            v, dt, done, desc = time_cpu_oracle(cfg, steps=1, warmup=0, budget_s=30.0)
             cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
         line = {
-            "metric": METRIC if args.mode == "train" else "rendered IRs/sec (inference)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC if args.mode == "train" else "rendered IRs/sec (inference)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, args, world), "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(rx_h.numel() * 4 * (3 if complex_field else 2) +
-                                              (cfg["render"]["n_azi"] * cfg["render"]["n_ele"] + 2) * 12),
-                    "d2h_bytes_per_step": int(out_h.numel() * 4)},
-            "gpu_launches": int(launches), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "grad_allreduce_bytes": int(arena.numel() * 4) if world > 1 and args.mode == "train" else 0,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pinned host positions -> device and an asynchronous D2H of the spectra every step; steps are not "
+                            "synchronised one by one (throughput), the timed region ends with a device synchronise"},
+            "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
+            "profile_pass": {"steps": prof_steps, "ms_per_step": ms_prof / prof_steps,
+                             "note": "kernels / roofline come from this separate pass with CUDA events around every library call"},
+            "grid_grad_alt": alt, "other_configs": others, "cpu_baseline": cpu,
+            "grad_exchange": {"allreduce_bytes": grad_bytes, "arena_bytes": arena_bytes,
+                              "row_exchange": bool(world > 1 and args.mode == "train" and not args.flat_allreduce)},
+            "grad_checksums": checksums,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

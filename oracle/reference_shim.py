@@ -96,3 +96,37 @@ def load_reference_criterion():
             else:
                 sys.modules[k] = v
     return mod
+
+
+def load_reference_datasets():
+    """-> the reference ``datasets_loader`` module executed from where it lies, with a stand-in ``librosa`` whose ``load``
+    reads WAV files through scipy (librosa is absent here).  Pins the on-disk formats of ``avr_b200/datasets.py``."""
+    import sys
+    import types
+
+    path = os.path.join(REFERENCE_ROOT, "datasets_loader.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"no reference tree at {REFERENCE_ROOT}")
+
+    def load(p, sr=None, mono=True):
+        from scipy.io import wavfile
+        import numpy as np
+        rate, x = wavfile.read(p)
+        assert sr is None and mono
+        y = x.astype(np.float32) / 32768.0 if x.dtype == np.int16 else x.astype(np.float32)
+        return (y.mean(axis=1) if y.ndim == 2 else y), rate
+
+    fake = types.ModuleType("librosa")
+    fake.load = load
+    saved = sys.modules.get("librosa")
+    sys.modules["librosa"] = fake
+    try:
+        spec = importlib.util.spec_from_file_location("avr_reference_datasets_loader", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop("librosa", None)
+        else:
+            sys.modules["librosa"] = saved
+    return mod

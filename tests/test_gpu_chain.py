@@ -1,0 +1,107 @@
+"""The fused chain of 128-wide dense layers (``avr_mlp_chain_fwd``, csrc/mlp_chain.cu) against the layer-by-layer
+tensor-core kernel (``avr_umma_gemm_nt``): same six-product / two-accumulator arithmetic, so EVERY output -- saved planes,
+raw planes, ReLU bitmasks, the fp32 head -- must be bit-identical; and against float64 for good measure."""
+import pytest
+import torch
+
+from avr_b200 import ops
+from avr_b200.ops import PlanePair
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+K3 = ops.PLANES_BF16x3
+
+
+def _planes(x, kind=K3):
+    return ops.planes_split(x.to(DEV), PlanePair.empty(x.shape[0], x.shape[1], DEV, kind=kind))
+
+
+def _reference_chain(x0p, mats, spec, M):
+    """Layer by layer through umma_nt, mirroring what fused_tc.py did before the chain kernel existed."""
+    outs, h = [], x0p
+    for w, s in zip(mats, spec):
+        wp = _planes(w)
+        o = {}
+        if s.get("out_f32"):
+            o["out_f32"] = torch.zeros(M, w.shape[0], device=DEV)
+            ops.umma_nt(h, wp, ops.UMMA_OUT_F32, c_f32=o["out_f32"])
+        elif s.get("raw"):
+            o["save_raw"] = PlanePair.zeros(M, w.shape[0], DEV, kind=K3)
+            o["save"] = PlanePair.zeros(M, w.shape[0], DEV, kind=K3)
+            o["bits"] = torch.zeros_like(ops.relu_bits_empty(M, w.shape[0], DEV))
+            ops.umma_nt(h, wp, ops.UMMA_DUAL_RELU, o["save_raw"], o["save"], bits_out=o["bits"])
+            h = o["save"]
+        else:
+            y = PlanePair.zeros(M, w.shape[0], DEV, kind=K3)
+            o["bits"] = torch.zeros_like(ops.relu_bits_empty(M, w.shape[0], DEV))
+            ops.umma_nt(h, wp, ops.UMMA_RELU if s["relu"] else 0, y, bits_out=o["bits"])
+            o["full"] = y
+            h = y
+        outs.append(o)
+    return outs
+
+
+@pytest.mark.parametrize("M,k0,n_hidden,head", [(300, 48, 4, 16), (128 * 149 + 37, 48, 4, 16), (1000, 128, 3, 16), (517, 80, 2, 64),
+                                                (129, 16, 1, 128)])
+def test_chain_is_bit_identical_to_the_layer_by_layer_kernel(built_library, M, k0, n_hidden, head):
+    g = torch.Generator().manual_seed(M + k0)
+    x0 = torch.randn(M, k0, generator=g)
+    dims = [k0] + [128] * n_hidden + [head]
+    mats = [torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5 for i in range(len(dims) - 1)]
+    # hidden layers: ReLU + saved planes + bitmask; the LAST hidden layer also keeps its raw output (sigma_feat); the head
+    # is fp32 when 16 wide, else a linear plane output
+    spec = [{"relu": True} for _ in range(n_hidden)]
+    spec[-1]["raw"] = True
+    spec.append({"out_f32": True} if head == 16 else {"relu": False})
+    x0p = _planes(x0)
+    ref = _reference_chain(x0p, mats, spec, M)
+    layers, mine = [], []
+    for li, (w, s) in enumerate(zip(mats, spec)):
+        L = {"w": _planes(w), "relu": bool(s.get("relu"))}
+        o = {}
+        if s.get("out_f32"):
+            o["out_f32"] = torch.zeros(M, w.shape[0], device=DEV)
+            L["out_f32"] = o["out_f32"]
+        else:
+            kind = ops.PLANES_BF16x2 if (li % 2 == 1 and not s.get("raw")) else K3       # 2-plane saves: the first two planes
+            o["save"] = PlanePair.zeros(M, w.shape[0], DEV, kind=kind)
+            o["bits"] = torch.zeros_like(ops.relu_bits_empty(M, w.shape[0], DEV))
+            L["save"], L["bits"] = o["save"], o["bits"]
+            if s.get("raw"):
+                o["save_raw"] = PlanePair.zeros(M, w.shape[0], DEV, kind=K3)
+                L["save_raw"] = o["save_raw"]
+        layers.append(L)
+        mine.append(o)
+    ops.mlp_chain_fwd(x0p, layers)
+    torch.cuda.synchronize()
+    # float64 chain on the values the kernels see
+    h = ops.planes_merge(x0p).double().cpu()
+    for li, (w, s, a, b) in enumerate(zip(mats, spec, mine, ref)):
+        wq = ops.planes_merge(_planes(w)).double().cpu()
+        pre = h @ wq.t()
+        if s.get("out_f32"):
+            assert torch.equal(a["out_f32"], b["out_f32"]), li
+            assert rel_l2(a["out_f32"], pre) < 2e-6
+            continue
+        words = (w.shape[0] + 31) // 32
+        assert torch.equal(a["bits"][:, :words], b["bits"][:, :words]), li
+        full = b["full"] if "full" in b else b["save"]
+        n = a["save"].n
+        assert torch.equal(a["save"].buf[:n], full.buf[:n]), li                       # the saved planes, bit for bit
+        if s.get("raw"):
+            assert torch.equal(a["save_raw"].buf, b["save_raw"].buf), li
+            assert rel_l2(ops.planes_merge(a["save_raw"]), pre) < 2e-6
+        h = ops.planes_merge(full).double().cpu()                                      # next layer sees the stored values
+        assert rel_l2(h, pre.clamp_min(0) if s["relu"] else pre) < 2e-6
+
+
+def test_chain_argument_checks(built_library):
+    from avr_b200 import _lib
+    x0 = _planes(torch.randn(64, 48))
+    w_bad = _planes(torch.randn(128, 64))                                              # k_in does not match
+    with pytest.raises(_lib.AVRLibraryError):
+        ops.mlp_chain_fwd(x0, [{"w": w_bad, "relu": True}])
+    w0, w1 = _planes(torch.randn(64, 48)), _planes(torch.randn(16, 64))               # a 64-wide hidden layer
+    with pytest.raises(_lib.AVRLibraryError):
+        ops.mlp_chain_fwd(x0, [{"w": w0, "relu": True}, {"w": w1, "relu": False, "out_f32": torch.zeros(64, 16, device=DEV)}])
