@@ -37,11 +37,12 @@ class GridMeta(C.Structure):
 
 class ChainLayer(C.Structure):
     """``avr_chain_layer`` (include/avr_b200.h, fused chain of 128-wide dense layers)."""
-    _fields_ = [("w", C.c_void_p), ("ldw", C.c_int64), ("w_plane", C.c_int64), ("n_out", C.c_int32), ("k_in", C.c_int32),
-                ("relu", C.c_int32),
+    _fields_ = [("w", C.c_void_p), ("ldw", C.c_int64), ("w_plane", C.c_int64), ("w_kind", C.c_int32), ("n_out", C.c_int32),
+                ("k_in", C.c_int32), ("relu", C.c_int32),
                 ("save", C.c_void_p), ("ld_save", C.c_int64), ("save_plane", C.c_int64), ("save_kind", C.c_int32),
                 ("save_raw", C.c_void_p), ("ld_raw", C.c_int64), ("raw_plane", C.c_int64), ("raw_kind", C.c_int32),
                 ("bits", C.c_void_p), ("ldbits", C.c_int64),
+                ("mask", C.c_void_p), ("ldmask", C.c_int64), ("accumulate", C.c_int32),
                 ("out_f32", C.c_void_p), ("ld_f32", C.c_int64)]
 
 
@@ -72,7 +73,7 @@ SIGNATURES = {
                                    _I64, C.c_int, _P, _I64, _I64, C.c_int, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _I64,
                                    _P, _I64, _P, C.c_float, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt_splitk_slices": (_I64, [_I64]),
-    "avr_mlp_chain_fwd": (C.c_int, [_I64, _P, _I64, _I64, _I32, C.POINTER(ChainLayer), _I32, C.c_int, _P]),
+    "avr_mlp_chain": (C.c_int, [_I64, _P, _I64, _I64, _I32, _I32, C.POINTER(ChainLayer), _I32, C.c_int, _P]),
     "avr_umma_gemm_tn_workspace_bytes": (_I64, [_I64, _I64, _I64]),
     "avr_umma_gemm_tn": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _P, _I64, C.c_int,
                                    _P, _I64, C.c_int, _P]),

@@ -165,7 +165,7 @@ class FusedRenderTC(torch.autograd.Function):
             layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win, save=dec_in, bits=bits_feat))   # raw feat + relu(feat)
             layers += [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_dec[:-1], acts_dec, bits_dec)]
             layers.append(dict(w=w_dec[-1], relu=False, out_f32=dec_out))                                 # the |leaky_relu| kink follows
-            ops.mlp_chain_fwd(x0, layers)
+            ops.mlp_chain(x0, layers)
         else:
             acts_enc, bits_enc, h = [], [], x0
             for li in range(len(w_enc) - 1):
@@ -243,7 +243,7 @@ class FusedRenderTC(torch.autograd.Function):
             ctx.small_in, ctx.roles = small_in, roles
             ctx.bufs = dict(x0=x0, acts_enc=acts_enc, sig_in=sig_in, dec_in=dec_in, acts_dec=acts_dec, dec_out=dec_out,
                             acts_sig=acts_sig, sort=sort, prefix=prefix, bits_enc=bits_enc, bits_dec=bits_dec, bits_sig=bits_sig,
-                            bits_feat=bits_feat)
+                            bits_feat=bits_feat, chain=chain)
             ctx.save_for_backward(rays_o, dirs, *params)
         return out
 
@@ -357,42 +357,63 @@ class FusedRenderTC(torch.autograd.Function):
         d_dec_mats = dec_net.matrices(g_dec)
         g = PlanePair.empty(n_rows, dec_net.out_pad, dev, n=DENSITY_BWD_PLANES)
         ops.planes_split(d_dec_out, g)
-        acts_dec = B["acts_dec"]
+        acts_dec, acts_enc, x0 = B["acts_dec"], B["acts_enc"], B["x0"]
         n_dec = len(d_dec_mats)
-        for li in range(n_dec - 1, 0, -1):
-            x = acts_dec[li - 1]
-            ops.umma_tn(g, x, d_dec_mats[li], ws)
-            gx = PlanePair.empty(n_rows, x.cols, dev, n=DENSITY_BWD_PLANES)
-            ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=B["bits_dec"][li - 1])
-            g = gx
-            bias_grad("dec", li - 1, g)
-        ops.umma_tn(g, dec_in, d_dec_mats[0], ws)
-        ops.umma_nt(g, wt_dec[0].row_window(0, feat_dim), ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=B["bits_feat"])   # d_feat += relu'(feat) * ...
-        d_dec_tail = None
-        if dec_net.in_pad > feat_dim and plan.get("dec_tail"):
-            d_dec_tail = PlanePair.empty(n_rows, dec_net.in_pad - feat_dim, dev)
-            ops.umma_nt(g, wt_dec[0].row_window(feat_dim, dec_net.in_pad - feat_dim), 0, d_dec_tail)
-        grads[id(dec_net)] = g_dec
-        scatter_segments(plan.get("dec_tail", []), d_dec_tail)
-
-        # ---- sigma encoder -----------------------------------------------------------------------------------
         wt_enc = _weight_planes(enc_net, pmap[id(enc_net)], True, BWD_PLANES)
         g_enc = torch.empty_like(pmap[id(enc_net)])
         d_enc_mats = enc_net.matrices(g_enc)
-        acts_enc = B["acts_enc"]
-        g = d_feat
-        for li in range(len(d_enc_mats) - 1, 0, -1):
-            x = acts_enc[li - 1]
-            ops.umma_tn(g, x, d_enc_mats[li], ws)
-            gx = PlanePair.empty(n_rows, x.cols, dev)
-            ops.umma_nt(g, wt_enc[li], ops.UMMA_MASK, gx, mask=B["bits_enc"][li - 1])
-            g = gx
-            bias_grad("enc", li - 1, g)
-        x0 = B["x0"]
-        ops.umma_tn(g, x0, d_enc_mats[0], ws)
+        n_enc = len(d_enc_mats)
         d_x0 = PlanePair.empty(n_rows, enc_net.in_pad, dev)
-        ops.umma_nt(g, wt_enc[0], 0, d_x0)
-        grads[id(enc_net)] = g_enc
+        if B.get("chain"):
+            # ---- backward-data of sigma decoder -> d_feat (+= signal path) -> sigma encoder: ONE launch; the gradient
+            # tile stays in shared memory, every layer's output is stored once for the weight-gradient GEMMs below
+            g_dec_l = [g] + [PlanePair.empty(n_rows, 128, dev, n=DENSITY_BWD_PLANES) for _ in range(n_dec - 1)]     # g at layer n_dec-1 .. 1
+            g_enc_l = [d_feat] + [PlanePair.empty(n_rows, 128, dev) for _ in range(n_enc - 1)]                       # g at layer n_enc-1 .. 1
+            layers = []
+            for k, li in enumerate(range(n_dec - 1, 0, -1)):
+                layers.append(dict(w=wt_dec[li], mask=B["bits_dec"][li - 1], save=g_dec_l[k + 1]))
+            layers.append(dict(w=wt_dec[0], mask=B["bits_feat"], save=d_feat, accumulate=True))                    # d_feat += relu'(feat) * ...
+            for k, li in enumerate(range(n_enc - 1, 0, -1)):
+                layers.append(dict(w=wt_enc[li], mask=B["bits_enc"][li - 1], save=g_enc_l[k + 1]))
+            layers.append(dict(w=wt_enc[0], save=d_x0))
+            ops.mlp_chain(g, layers)
+            for k, li in enumerate(range(n_dec - 1, 0, -1)):
+                ops.umma_tn(g_dec_l[k], acts_dec[li - 1], d_dec_mats[li], ws)
+            ops.umma_tn(g_dec_l[-1], dec_in, d_dec_mats[0], ws)
+            for k, li in enumerate(range(n_enc - 1, 0, -1)):
+                ops.umma_tn(g_enc_l[k], acts_enc[li - 1], d_enc_mats[li], ws)
+            ops.umma_tn(g_enc_l[-1], x0, d_enc_mats[0], ws)
+            grads[id(dec_net)] = g_dec
+            grads[id(enc_net)] = g_enc
+        else:
+            for li in range(n_dec - 1, 0, -1):
+                x = acts_dec[li - 1]
+                ops.umma_tn(g, x, d_dec_mats[li], ws)
+                gx = PlanePair.empty(n_rows, x.cols, dev, n=DENSITY_BWD_PLANES)
+                ops.umma_nt(g, wt_dec[li], ops.UMMA_MASK, gx, mask=B["bits_dec"][li - 1])
+                g = gx
+                bias_grad("dec", li - 1, g)
+            ops.umma_tn(g, dec_in, d_dec_mats[0], ws)
+            ops.umma_nt(g, wt_dec[0].row_window(0, feat_dim), ops.UMMA_MASK | ops.UMMA_ACCUM, d_feat, mask=B["bits_feat"])   # d_feat += relu'(feat) * ...
+            d_dec_tail = None
+            if dec_net.in_pad > feat_dim and plan.get("dec_tail"):
+                d_dec_tail = PlanePair.empty(n_rows, dec_net.in_pad - feat_dim, dev)
+                ops.umma_nt(g, wt_dec[0].row_window(feat_dim, dec_net.in_pad - feat_dim), 0, d_dec_tail)
+            grads[id(dec_net)] = g_dec
+            scatter_segments(plan.get("dec_tail", []), d_dec_tail)
+
+            # ---- sigma encoder -----------------------------------------------------------------------------------
+            g = d_feat
+            for li in range(n_enc - 1, 0, -1):
+                x = acts_enc[li - 1]
+                ops.umma_tn(g, x, d_enc_mats[li], ws)
+                gx = PlanePair.empty(n_rows, x.cols, dev)
+                ops.umma_nt(g, wt_enc[li], ops.UMMA_MASK, gx, mask=B["bits_enc"][li - 1])
+                g = gx
+                bias_grad("enc", li - 1, g)
+            ops.umma_tn(g, x0, d_enc_mats[0], ws)
+            ops.umma_nt(g, wt_enc[0], 0, d_x0)
+            grads[id(enc_net)] = g_enc
         scatter_segments(plan["x0"], d_x0)
         for mod, handle in deferred:
             # rows of ALL ranks (already scaled to the mean), scattered in rank order with the int64 accumulator: every

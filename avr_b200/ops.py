@@ -421,24 +421,25 @@ def umma_nt(a: PlanePair, b: PlanePair, flags=0, c: PlanePair = None, c2: PlaneP
             _p(ws), ws.numel() * 4 if ws is not None else 0, dev, st), "avr_umma_gemm_nt")
 
 
-def mlp_chain_fwd(x0: PlanePair, layers):
-    """Fused chain of 128-wide dense layers on one launch (``avr_mlp_chain_fwd``): ``y_{l+1} = act_l(y_l W_l^T)``.
+def mlp_chain(x0: PlanePair, layers):
+    """Fused chain of 128-wide dense layers on one launch (``avr_mlp_chain``): ``y_{l+1} = act_l(y_l W_l^T)``.
 
-    ``x0``: BF16x3 plane set ``[M, k0]``.  ``layers``: dicts with ``w`` (BF16x3 planes of ``W[n_out, k_in]``), ``relu``
-    (bool) and the optional outputs ``save`` (PlanePair, rectified output), ``save_raw`` (PlanePair, raw output), ``bits``
-    (int32 ReLU bitmask), ``out_f32`` (fp32 ``[M, >= n_out]`` tensor; last layer only).  Bit-identical to running the
+    ``x0``: bf16 plane set ``[M, k0]`` (pair or triple).  ``layers``: dicts with ``w`` (bf16 planes of ``W[n_out, k_in]``)
+    and the optional ``relu`` (bool), ``mask`` (int32 bitmask multiplied into the output: ReLU backward), ``accumulate``
+    (add what ``save`` already holds), outputs ``save`` (PlanePair), ``save_raw`` (PlanePair, un-rectified output), ``bits``
+    (int32 ReLU bitmask out), ``out_f32`` (fp32 ``[M, >= n_out]`` tensor; last layer only).  Bit-identical to running the
     layers through ``umma_nt`` one by one."""
     dev, st = _ctx(x0)
-    assert x0.kind == PLANES_BF16x3, "the chain input must be a bf16 triple"
+    assert not x0.f16, "the chain input must be a bf16 plane set"
     n = len(layers)
     arr = (_lib.ChainLayer * n)()
-    flops = 0.0
+    flops, executed, planes_in = 0.0, 0.0, x0.n
     for a, L in zip(arr, layers):
         w = L["w"]
-        assert w.kind == PLANES_BF16x3
-        a.w, a.ldw, a.w_plane, a.n_out, a.k_in = w.ptr.value, w.ld, w.plane, w.rows, w.cols
+        assert not w.f16
+        a.w, a.ldw, a.w_plane, a.w_kind, a.n_out, a.k_in = w.ptr.value, w.ld, w.plane, w.kind, w.rows, w.cols
         a.relu = 1 if L.get("relu") else 0
-        sv, raw, bits, o32 = L.get("save"), L.get("save_raw"), L.get("bits"), L.get("out_f32")
+        sv, raw, bits, o32, mask = L.get("save"), L.get("save_raw"), L.get("bits"), L.get("out_f32"), L.get("mask")
         if sv is not None:
             assert sv.rows == x0.rows and sv.cols == w.rows
             a.save, a.ld_save, a.save_plane, a.save_kind = sv.ptr.value, sv.ld, sv.plane, sv.kind
@@ -447,11 +448,20 @@ def mlp_chain_fwd(x0: PlanePair, layers):
             a.save_raw, a.ld_raw, a.raw_plane, a.raw_kind = raw.ptr.value, raw.ld, raw.plane, raw.kind
         if bits is not None:
             a.bits, a.ldbits = _p(bits, torch.int32).value, bits.stride(0)
+        if mask is not None:
+            a.mask, a.ldmask = _p(mask, torch.int32).value, mask.stride(0)
+        a.accumulate = 1 if L.get("accumulate") else 0
         if o32 is not None:
             a.out_f32, a.ld_f32 = _p(o32).value, o32.stride(0)
-        flops += 2.0 * x0.rows * w.rows * w.cols
-    with _timed("mlp_chain", flops, "flop", 6.0 * flops):
-        _lib.check(_lib.load().avr_mlp_chain_fwd(x0.rows, x0.ptr, x0.ld, x0.plane, x0.cols, arr, n, dev, st), "avr_mlp_chain_fwd")
+        f = 2.0 * x0.rows * w.rows * w.cols
+        flops += f
+        executed += f * (6 if (planes_in == 3 and w.n == 3) else 3)
+        planes_in = 3                                      # (upper bound for the executed-product count of later layers)
+    with _timed("mlp_chain", flops, "flop", executed):
+        _lib.check(_lib.load().avr_mlp_chain(x0.rows, x0.ptr, x0.ld, x0.plane, x0.kind, x0.cols, arr, n, dev, st), "avr_mlp_chain")
+
+
+mlp_chain_fwd = mlp_chain
 
 
 def umma_tn_workspace_bytes(M, N, K) -> int:

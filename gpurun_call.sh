@@ -1,6 +1,10 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python profiles/diag_realexp_r2.py > gpurun_out/diag_realexp.txt 2>&1
-( time timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_kernels.py tests/test_gpu_chain.py -m gpu -q 2>&1 | tail -30 ) > gpurun_out/pytest_render.log 2>&1
+( time timeout 600 python -m pytest tests/test_gpu_chain.py -m gpu -q -x 2>&1 | tail -4 ) > gpurun_out/pytest_chain.log 2>&1
+timeout 120 python profiles/run_chain_once.py > gpurun_out/chain_timing.txt 2>&1
 timeout 300 python bench.py --steps 20 --no-other-configs --no-cpu-baseline > gpurun_out/bench_chain.json 2> gpurun_out/bench_chain.err
-tail -3 gpurun_out/pytest_render.log
+cp avr_b200/libavr_b200.so /tmp/lib_backup.so
+python -m avr_b200.build --experiments > gpurun_out/build_exp.log 2>&1
+python profiles/trace_chain.py > gpurun_out/chain_trace.txt 2>&1
+cp /tmp/lib_backup.so avr_b200/libavr_b200.so
+cat gpurun_out/chain_timing.txt; cat gpurun_out/pytest_chain.log

@@ -214,31 +214,37 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
 AVR_API int64_t avr_umma_gemm_nt_splitk_slices(int64_t K);
 /* ---- fused chain of 128-wide dense layers ------------------------------------------------------------------
  * model.py:206-216 -- the sigma encoder and sigma decoder, which the reference evaluates as tiny-cuda-nn FullyFusedMLP
- * kernels (model.py:117,146): y_0 = x0, y_{l+1} = act_l(y_l . W_l^T), all layers of a 128-row tile of sample points in ONE
- * launch.  The activation tile stays in shared memory as bf16 (hi, mid, lo) planes -- it is the next layer's tcgen05
- * operand and the source of the bulk stores below -- accumulators live in tensor memory, weights stream from L2.  Same
- * six-product / two-accumulator arithmetic as avr_umma_gemm_nt on BF16x3 operands: results are bit-identical to running
- * the layers one by one.
- *   w          BF16x3 planes of W[n_out, k_in] (K-major), leading dimension ldw, plane stride w_plane (elements)
- *   relu       rectify the output before the next layer (and before `save`)
- *   save       optional: the (rectified) output as a BF16x2 / BF16x3 plane set [*][M][ld_save]  (what the weight-gradient
- *              GEMM of the next layer reads); save_raw: optional, the un-rectified output likewise (sigma_feat feeds the
+ * kernels (model.py:117,146) -- and their backward-data pass: y_0 = x0, y_{l+1} = act_l(y_l . W_l^T), all layers of a
+ * 128-row tile of sample points in ONE launch.  The activation tile stays in shared memory as bf16 planes -- it is the
+ * next layer's tcgen05 operand and the source of the bulk stores below -- accumulators live in tensor memory (two sets,
+ * so the next layer's MMAs overlap this layer's epilogue), weights stream from L2.  Same arithmetic as avr_umma_gemm_nt
+ * (six products / two accumulators when both operands are BF16x3, else three products on the (hi, mid) planes): results
+ * are bit-identical to running the layers one by one.
+ *   w          BF16x2 / BF16x3 planes (w_kind) of W[n_out, k_in] (K-major), leading dimension ldw, plane stride w_plane
+ *   relu       forward: rectify the output before the next layer (and before `save`)
+ *   mask       backward: bitmask [M][ldmask] multiplied into the output (the ReLU decisions of the forward pass)
+ *   accumulate backward: add the planes already in `save` to the output before it is stored back (two consumers of one
+ *              activation: d_feat = signal path + density path)
+ *   save       optional: the (rectified / masked) output as a BF16x2 / BF16x3 plane set [*][M][ld_save]  (what the
+ *              weight-gradient GEMMs read); save_raw: optional, the un-rectified output likewise (sigma_feat feeds the
  *              signal network raw, model.py:219, and the decoder rectified, model.py:209)
- *   bits       optional ReLU bitmask: bit (col % 32) of word [row][col / 32] = (raw output > 0)
+ *   bits       optional ReLU bitmask out: bit (col % 32) of word [row][col / 32] = (raw output > 0)
  *   out_f32    last layer only: fp32 output [M][ld_f32] instead of planes (the 16-wide density head); no activation
  * Hidden layers are 128 wide; k_in of layer 0 (= k0, the width of x0) is a multiple of 16 up to 128; the last layer may
- * be any multiple of 16 up to 128 (64 / 128 for plane outputs).  x0: BF16x3 planes [3][M][ldx]. */
+ * be any multiple of 16 up to 128 (up to 64 for fp32).  x0: BF16x2 / BF16x3 planes [*][M][ldx]. */
 #define AVR_CHAIN_MAX_LAYERS 8
 typedef struct avr_chain_layer {
-    const void* w; int64_t ldw, w_plane; int32_t n_out, k_in;
+    const void* w; int64_t ldw, w_plane; int32_t w_kind; int32_t n_out, k_in;
     int32_t relu;
     void* save; int64_t ld_save, save_plane; int32_t save_kind;
     void* save_raw; int64_t ld_raw, raw_plane; int32_t raw_kind;
     uint32_t* bits; int64_t ldbits;
+    const uint32_t* mask; int64_t ldmask;
+    int32_t accumulate;
     float* out_f32; int64_t ld_f32;
 } avr_chain_layer;
-AVR_API int avr_mlp_chain_fwd(int64_t M, const void* x0, int64_t ldx, int64_t x_plane, int32_t k0,
-                              const avr_chain_layer* layers, int32_t n_layers, int device, void* stream);
+AVR_API int avr_mlp_chain(int64_t M, const void* x0, int64_t ldx, int64_t x_plane, int32_t x_kind, int32_t k0,
+                          const avr_chain_layer* layers, int32_t n_layers, int device, void* stream);
 
 /* C[M,N] (+)= sum_k A[k,M] * B[k,N]   (A = dY[points,out], B = X[points,in] plane sets; weight gradients).
  * fp32 output; deterministic split-K over the points through `workspace`.  A (the gradient) is a bf16 plane set, B

@@ -42,22 +42,40 @@ def rel_l2(a, b):
     return render_ref.rel_l2(torch.as_tensor(a).cpu(), torch.as_tensor(b).cpu())
 
 
-def oracle_fp32_noise(ref_net, render_kwargs, rx, tx, G, dtx=None, **fwd_kwargs):
-    """How far the fp32 oracle is from itself with the dense layers evaluated in float64: ``(rel_l2 of the IR,
-    {param name: rel_l2 of its gradient})``.  Geometry, renderer and the hash-grid cell positions stay fp32 (the
-    network inputs are NOT widened: at the fine levels of the real grids, resolution ~2^21, a float64 position lands
-    elsewhere in the cell and would measure a different function, not rounding noise).  A single ReLU /
-    |leaky_relu| decision that differs between the two evaluations moves a gradient by ~1e-4, so on some weight
-    draws this noise of the checker reaches the 1e-4 parity bar; tests take the first seed where it does not."""
+def oracle_fp32_noise(ref_net, render_kwargs, rx, tx, G, dtx=None, orders=(None, 1, 2), **fwd_kwargs):
+    """How well the fp32 oracle determines the answer on this weight draw: ``(rel_l2 of the IR, {param name: rel_l2 of its
+    gradient})``, the LARGEST distance of several fp32 evaluations of the oracle from its evaluation with float64 dense
+    layers.  The fp32 evaluations differ only in the summation order of the dense layers (``field_ref.K_ORDER_SEED``:
+    ``None`` = the plain oracle, then permuted reduction orders).  Geometry, renderer and the hash-grid cell positions
+    stay fp32 in all of them (the network inputs are NOT widened: at the fine levels of the real grids, resolution ~2^21,
+    a float64 position lands elsewhere in the cell and would measure a different function, not rounding noise).
+
+    A single ReLU / |leaky_relu| decision that differs between two evaluations gates that unit's back-propagated gradient
+    on or off; when the unit sits at a sample point that carries a visible share of the gradient (compositing weights and
+    path loss concentrate it on few points) one such flip moves a hash-table gradient by 1e-4 .. 3e-3 (measured,
+    profiles/r2/parity_flips.md).  The plain oracle alone under-reports this: it may happen to decide like float64 while
+    any other rounding -- another GEMM blocking, the GPU's -- does not.  Hence several summation orders."""
     import copy
 
     net64 = copy.deepcopy(ref_net).double()
-    net32 = copy.deepcopy(ref_net)
-    for p in list(net64.parameters()) + list(net32.parameters()):
+    for p in net64.parameters():
         p.grad = None
-    out32 = render_ref.RenderRef(net32, **render_kwargs)(rx, tx, dtx, **fwd_kwargs)
-    (out32 * G).sum().backward()
     out64 = render_ref.RenderRef(net64, **render_kwargs)(rx, tx, dtx, **fwd_kwargs)
     (out64 * G.double()).sum().backward()
-    g32 = dict(net32.named_parameters())
-    return rel_l2(out32, out64), {n: rel_l2(g32[n].grad, p.grad) for n, p in net64.named_parameters()}
+    g64 = {n: p.grad for n, p in net64.named_parameters()}
+    worst_out, worst = 0.0, {n: 0.0 for n in g64}
+    saved = field_ref.K_ORDER_SEED
+    try:
+        for order in orders:
+            field_ref.K_ORDER_SEED = order
+            net32 = copy.deepcopy(ref_net)
+            for p in net32.parameters():
+                p.grad = None
+            out32 = render_ref.RenderRef(net32, **render_kwargs)(rx, tx, dtx, **fwd_kwargs)
+            (out32 * G).sum().backward()
+            worst_out = max(worst_out, rel_l2(out32, out64))
+            for n, p in net32.named_parameters():
+                worst[n] = max(worst[n], rel_l2(p.grad, g64[n]))
+    finally:
+        field_ref.K_ORDER_SEED = saved
+    return worst_out, worst

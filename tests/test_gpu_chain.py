@@ -73,7 +73,7 @@ def test_chain_is_bit_identical_to_the_layer_by_layer_kernel(built_library, M, k
                 L["save_raw"] = o["save_raw"]
         layers.append(L)
         mine.append(o)
-    ops.mlp_chain_fwd(x0p, layers)
+    ops.mlp_chain(x0p, layers)
     torch.cuda.synchronize()
     # float64 chain on the values the kernels see
     h = ops.planes_merge(x0p).double().cpu()
@@ -96,12 +96,52 @@ def test_chain_is_bit_identical_to_the_layer_by_layer_kernel(built_library, M, k
         assert rel_l2(h, pre.clamp_min(0) if s["relu"] else pre) < 2e-6
 
 
+@pytest.mark.parametrize("M", [300, 128 * 150 + 5])
+def test_backward_data_chain_is_bit_identical(built_library, M):
+    """The backward-data pass of sigma decoder -> sigma encoder as one chain: ReLU bitmasks multiplied into every output,
+    24-bit (six-product) layers along the decoder, the accumulate into d_feat (two consumers of sigma_feat), then 16-bit
+    (three-product) layers along the encoder, a 48-wide last layer -- against umma_nt with UMMA_MASK / UMMA_ACCUM."""
+    g = torch.Generator().manual_seed(M)
+    K2 = ops.PLANES_BF16x2
+    g0 = _planes(torch.randn(M, 16, generator=g))                                     # d(density head), 3 planes
+    dims = [16, 128, 128, 128, 128, 48]
+    kinds = [K3, K3, K3, K2, K2]                                                       # transposed weights: decoder 24 bits, encoder 16
+    wts = [_planes(torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5, kinds[i]) for i in range(5)]
+    masks = [torch.randint(-2 ** 31, 2 ** 31 - 1, (M, 4), generator=g, dtype=torch.int64).to(torch.int32).to(DEV) for _ in range(4)]
+    feat_prev = _planes(torch.randn(M, 128, generator=g), K2)                          # d_feat from the signal path
+    out_kinds = [K3, K3, K2, K2, K2]
+
+    def run_reference():
+        acc = PlanePair(feat_prev.buf.clone())
+        outs, h = [], g0
+        for li in range(5):
+            if li == 2:
+                ops.umma_nt(h, wts[li], ops.UMMA_MASK | ops.UMMA_ACCUM, acc, mask=masks[li])
+                y = acc
+            else:
+                y = PlanePair.zeros(M, dims[li + 1], DEV, kind=out_kinds[li])
+                ops.umma_nt(h, wts[li], ops.UMMA_MASK if li < 4 else 0, y, mask=masks[li] if li < 4 else None)
+            outs.append(y)
+            h = y
+        return outs
+
+    ref = run_reference()
+    acc = PlanePair(feat_prev.buf.clone())
+    mine = [PlanePair.zeros(M, dims[li + 1], DEV, kind=out_kinds[li]) if li != 2 else acc for li in range(5)]
+    layers = [dict(w=wts[li], save=mine[li], mask=masks[li] if li < 4 else None, accumulate=(li == 2)) for li in range(5)]
+    ops.mlp_chain(g0, layers)
+    torch.cuda.synchronize()
+    for li, (a, b) in enumerate(zip(mine, ref)):
+        assert torch.equal(a.buf[:, :, :dims[li + 1]], b.buf[:, :, :dims[li + 1]]), li
+    assert float(ops.planes_merge(mine[-1]).abs().max()) > 0
+
+
 def test_chain_argument_checks(built_library):
     from avr_b200 import _lib
     x0 = _planes(torch.randn(64, 48))
     w_bad = _planes(torch.randn(128, 64))                                              # k_in does not match
     with pytest.raises(_lib.AVRLibraryError):
-        ops.mlp_chain_fwd(x0, [{"w": w_bad, "relu": True}])
+        ops.mlp_chain(x0, [{"w": w_bad, "relu": True}])
     w0, w1 = _planes(torch.randn(64, 48)), _planes(torch.randn(16, 64))               # a 64-wide hidden layer
     with pytest.raises(_lib.AVRLibraryError):
-        ops.mlp_chain_fwd(x0, [{"w": w0, "relu": True}, {"w": w1, "relu": False, "out_f32": torch.zeros(64, 16, device=DEV)}])
+        ops.mlp_chain(x0, [{"w": w0, "relu": True}, {"w": w1, "relu": False, "out_f32": torch.zeros(64, 16, device=DEV)}])

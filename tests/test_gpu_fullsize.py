@@ -111,9 +111,9 @@ def test_full_size_vs_cpu_oracle(built_library, name, bs):
           f"{max(tc_vs_simt[1].values()):.2e}")
     bar, noise = TOL, None
     if res["tc"][0] >= TOL or worst["tc"] >= TOL or worst["tc_atomic"] >= TOL:
-        # an ill-conditioned draw: measure the oracle against itself with float64 dense layers -- only then, it triples
-        # the host time -- and hold the product to max(1e-4, 2 x that noise)
-        n_out, n_g = oracle_fp32_noise(ref_net, cfg["render"], rx, tx, G, dtx=dtx, azi_rand=azi)
+        # an ill-conditioned draw: measure the oracle's own spread over summation orders against its float64-dense
+        # evaluation -- only then, it multiplies the host time -- and hold the product to max(1e-4, 2 x that spread)
+        n_out, n_g = oracle_fp32_noise(ref_net, cfg["render"], rx, tx, G, dtx=dtx, azi_rand=azi, orders=(None, 1, 2))
         noise = max([n_out] + list(n_g.values()))
         bar = max(TOL, 2 * noise)
     _record(test="full_size_vs_cpu_oracle", config=name, bs=bs, cpu_oracle_seconds=cpu_s, oracle_fp32_noise=noise,
@@ -132,9 +132,11 @@ def test_full_size_vs_cpu_oracle(built_library, name, bs):
 @pytest.mark.parametrize("name,n_azi,n_ele", [("simu", 16, 8), ("meshrir", 10, 6), ("raf_furnished", 12, 6),
                                               ("real_exp_ch_emb_1", 16, 8)])
 def test_real_fields_all_seeds_reported(built_library, name, n_azi, n_ele):
-    """The real fields on a reduced ray grid, EVERY candidate seed: on seeds where the fp32 oracle agrees with its own
-    float64 evaluation to 1e-5 the bar is 1e-4; on the others (a ReLU decision inside the oracle's own rounding noise)
-    the bar is max(1e-4, 2 x oracle noise).  Per seed: oracle noise, tc and simt distances -- printed and recorded."""
+    """The real fields on a reduced ray grid, EVERY candidate seed.  The oracle's own spread -- six fp32 evaluations that
+    differ only in the summation order of the dense layers, each against the float64-dense evaluation -- says how well
+    fp32 arithmetic determines the answer on that draw: where it is <= 2e-5 the bar is 1e-4; elsewhere (a ReLU decision
+    inside fp32 rounding noise at a point that carries a visible share of the gradient) the bar is max(1e-4, 2 x spread).
+    Per seed: spread, tc and simt distances -- printed and recorded; no seed is skipped."""
     cfg = get_config(name)
     cfg["render"]["n_azi"], cfg["render"]["n_ele"] = n_azi, n_ele
     mc = cfg["model_class"]
@@ -143,9 +145,9 @@ def test_real_fields_all_seeds_reported(built_library, name, n_azi, n_ele):
     rows, rejected = [], 0
     for seed in range(41, 51, 2):
         ref_net = field_ref.trained_like_(cls(cfg["model"], seed=seed), seed=seed + 1)
-        n_out, n_g = oracle_fp32_noise(ref_net, cfg["render"], rx, tx, G, dtx=dtx, azi_rand=azi)
+        n_out, n_g = oracle_fp32_noise(ref_net, cfg["render"], rx, tx, G, dtx=dtx, azi_rand=azi, orders=(None, 1, 2, 3, 4, 5))
         noise = max([n_out] + list(n_g.values()))
-        well = n_out <= 1e-5 and max(n_g.values()) <= 1e-5
+        well = noise <= 2e-5
         rejected += 0 if well else 1
         ref_out = render_ref.RenderRef(ref_net, **cfg["render"])(rx, tx, dtx, azi_rand=azi)
         (ref_out * G).sum().backward()
@@ -162,6 +164,6 @@ def test_real_fields_all_seeds_reported(built_library, name, n_azi, n_ele):
               f"{e['tc'][1]:.1e} ({e['tc'][2]})  simt IR {e['simt'][0]:.1e} grad {e['simt'][1]:.1e}")
         bar = TOL if well else max(TOL, 2 * noise)
         assert e["tc"][0] < bar and e["tc"][1] < bar, (seed, e["tc"], bar)
-    print(f"{name}: {rejected} of {len(rows)} seeds ill-conditioned for the fp32 oracle")
+    print(f"{name}: {rejected} of {len(rows)} seeds ill-conditioned for fp32 arithmetic")
     _record(test="real_fields_all_seeds", config=name, rays=n_azi * n_ele + 2, ill_conditioned=rejected, seeds=rows)
     assert rejected < len(rows), "no seed on which the oracle can check at 1e-4"

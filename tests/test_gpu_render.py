@@ -129,25 +129,22 @@ def test_channel_embedding_vs_oracle(built_library, conn, enc, dec, sig):
     ch = torch.tensor([5, 0, 5])                                   # a repeated channel: its row gradient is a sum
     azi = torch.rand(r["n_azi"], generator=gen)
     G = torch.randn(bs, 201, 2, generator=gen)
-    # Random embedding rows can put a tiny problem on a kink (|leaky_relu(.)| at 0, a ReLU at 0) or make its gradient
-    # sums cancel; then the fp32 oracle disagrees with ITSELF (field in float64) by up to 5e-4 and is no checker at
-    # 1e-4.  Take the first weight seed the oracle alone judges well-conditioned (self-noise <= 2e-5).
-    for seed in range(21, 41):
-        ref_net = field_ref.trained_like_(field_ref.AVRModelRef(cfg["model"], seed=seed), seed=seed + 1)
-        n_out, noise = oracle_fp32_noise(ref_net, r, rx, tx, G, ch_idx=ch, azi_rand=azi)
-        if n_out <= 1e-5 and max(noise.values()) <= 2e-5:
-            break
-    else:
-        pytest.fail("no well-conditioned seed")
+    # Random embedding rows can put a tiny problem on a kink (|leaky_relu(.)| at 0, a ReLU at 0): then fp32 evaluations that
+    # differ only in summation order disagree with each other.  No seed is rejected: the bar is 1e-4, widened to twice the
+    # oracle's own spread over summation orders when that is larger (tests/helpers.py::oracle_fp32_noise).
+    ref_net = field_ref.trained_like_(field_ref.AVRModelRef(cfg["model"], seed=21), seed=22)
+    n_out, noise = oracle_fp32_noise(ref_net, r, rx, tx, G, ch_idx=ch, azi_rand=azi, orders=(None, 1, 2, 3, 4, 5))
+    tol = max(TOL, 2 * max([n_out] + list(noise.values())))
+    print(f"\nchannel embedding {conn} enc={enc} dec={dec} sig={sig}: oracle spread {max(noise.values()):.1e} -> bar {tol:.1e}")
     native = _native_from(ref_net, "AVRModel", cfg["model"])
     assert [k for k, _ in native.named_parameters()] == [k for k, _ in ref_net.named_parameters()]
     ref_out = render_ref.RenderRef(ref_net, **r)(rx, tx, None, ch_idx=ch, azi_rand=azi)
     (ref_out * G).sum().backward()
     ren = avr_b200.AVRRender(native, **r)
     out = ren(rx.to(DEV), tx.to(DEV), ch_idx=ch.to(DEV), azi_rand=azi)
-    assert float(ref_out.abs().max()) > 0 and rel_l2(out, ref_out) < TOL
+    assert float(ref_out.abs().max()) > 0 and rel_l2(out, ref_out) < tol
     (out * G.to(DEV)).sum().backward()
-    _check_grads(native, ref_net)
+    _check_grads(native, ref_net, tol)
     emb = [p for n, p in native.named_parameters() if "embedding" in n]
     assert emb and all(float(p.grad[[1, 2, 3, 4, 6, 7]].abs().max()) == 0 and float(p.grad[5].abs().max()) > 0 for p in emb)
     # the standalone field (explicit points, torch-composed layers) agrees as well
@@ -258,42 +255,8 @@ def test_full_size_simu_properties(built_library):
         assert torch.equal(a, b) and bool(torch.isfinite(a).all())
 
 
-@pytest.mark.parametrize("name,n_azi,n_ele", [("simu", 16, 8), ("meshrir", 10, 6), ("raf_furnished", 12, 6),
-                                              ("real_exp_ch_emb_1", 16, 8)])
-def test_baseline_networks_reduced_rays_vs_oracle(built_library, name, n_azi, n_ele):
-    """The four BASELINE configs with their real fields (20-level 2^18..2^20 hash grids, 128/512-wide MLPs), real S and T,
-    and a reduced ray grid so that the CPU oracle finishes in seconds: IR and every parameter gradient within 1e-4."""
-    cfg = get_config(name)
-    cfg["render"]["n_azi"], cfg["render"]["n_ele"] = n_azi, n_ele
-    mc = cfg["model_class"]
-    cls = field_ref.AVRModelRef if mc == "AVRModel" else field_ref.AVRModelComplexRef
-    r = cfg["render"]
-    bs = 2
-    gen = torch.Generator().manual_seed(11)
-    c = (r["xyz_min"] + r["xyz_max"]) / 2
-    rx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 1.5).float()
-    tx = (c + (torch.rand(bs, 3, generator=gen) * 2 - 1) * 1.5).float()
-    dtx = torch.nn.functional.normalize(torch.randn(bs, 3, generator=gen), dim=-1) if mc != "AVRModel" else None
-    azi = torch.rand(n_azi, generator=gen)
-    T = cfg["model"]["signal_output_dim"]
-    G = torch.randn(bs, T // 2 + 1, 2, generator=gen)
-    # One ReLU decision that differs from the oracle's moves a hash-grid gradient by ~1e-4 at this size: take the first
-    # weight seed on which the fp32 oracle agrees with its own float64 evaluation (tests/helpers.py::oracle_fp32_noise).
-    for seed in range(41, 61, 2):
-        ref_net = field_ref.trained_like_(cls(cfg["model"], seed=seed), seed=seed + 1)
-        n_out, noise = oracle_fp32_noise(ref_net, r, rx, tx, G, dtx=dtx, azi_rand=azi)
-        if n_out <= 1e-5 and max(noise.values()) <= 1e-5:
-            break
-    else:
-        pytest.fail("no well-conditioned seed")
-    native = _native_from(ref_net, mc, cfg["model"])
-    ref_out = render_ref.RenderRef(ref_net, **r)(rx, tx, dtx, azi_rand=azi)
-    (ref_out * G).sum().backward()
-    ren = avr_b200.AVRRender(native, **r)
-    out = ren(rx.to(DEV), tx.to(DEV), dtx.to(DEV) if dtx is not None else None, azi_rand=azi)
-    assert float(ref_out.abs().max()) > 0 and rel_l2(out, ref_out) < TOL
-    (out * G.to(DEV)).sum().backward()
-    _check_grads(native, ref_net)
+# (the real fields of the four BASELINE configs against the oracle, on reduced ray grids over ALL candidate seeds and at
+# full size: tests/test_gpu_fullsize.py)
 
 
 @pytest.mark.parametrize("name,bs", [("meshrir", 1), ("raf_furnished", 2), ("real_exp_ch_emb_1", 1)])
