@@ -67,6 +67,7 @@ def parse_args():
                          "per-receiver table gradients as rows (GradArena.attach)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the pass with the other hash-table-gradient mode (profiling runs)")
     return ap.parse_args()
 
 
@@ -454,7 +455,7 @@ def run_native(args, cfg):
     # the same workload with the other accumulation mode of the hash-table gradients
     other_mode = "atomic" if args.grid_grad == "deterministic" else "deterministic"
     alt = None
-    if args.mode == "train":
+    if args.mode == "train" and not args.no_alt:
         w2 = Workload(args.config, args.bs, args.mode, other_mode, dev, rank, world, args.flat_allreduce)
         for _ in range(warm):
             w2.step(False)

@@ -1,10 +1,12 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 600 python -m pytest tests/test_gpu_chain.py -m gpu -q -x 2>&1 | tail -4 ) > gpurun_out/pytest_chain.log 2>&1
-timeout 120 python profiles/run_chain_once.py > gpurun_out/chain_timing.txt 2>&1
-timeout 300 python bench.py --steps 20 --no-other-configs --no-cpu-baseline > gpurun_out/bench_chain.json 2> gpurun_out/bench_chain.err
-cp avr_b200/libavr_b200.so /tmp/lib_backup.so
-python -m avr_b200.build --experiments > gpurun_out/build_exp.log 2>&1
-python profiles/trace_chain.py > gpurun_out/chain_trace.txt 2>&1
-cp /tmp/lib_backup.so avr_b200/libavr_b200.so
-cat gpurun_out/chain_timing.txt; cat gpurun_out/pytest_chain.log
+( time python -m pytest tests -m gpu -q -s --durations=15 ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+python bench.py --config meshrir --mode infer --receivers 3969 --bs 8 > gpurun_out/bench_meshrir_all_1gpu.json 2> gpurun_out/bench_meshrir_all_1gpu.err
+python bench.py --config simu --bs 1 --steps 20 --no-other-configs --no-cpu-baseline > gpurun_out/bench_simu_bs1.json 2> gpurun_out/bench_simu_bs1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2a_launches.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:umma_gemm_kernel -s 60 -c 20 --csv --log-file gpurun_out/r2a_umma_dram_traffic.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_traffic.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:mlp_chain -c 1 -o gpurun_out/chain_r2d python profiles/run_chain_once.py > gpurun_out/ncu_chain.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log

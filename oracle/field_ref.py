@@ -131,6 +131,50 @@ class HashGridRef(nn.Module):
 #: reference's included -- is determined to 1e-4, and the tests widen the bar to twice the measured spread.
 K_ORDER_SEED = None
 
+#: Second conditioning probe: when set to a float g, every ReLU (and the |leaky_relu| kink of the density head) keeps
+#: its forward value but takes its backward decision at ``v > g * mean|v|`` of its layer instead of ``v > 0``.
+#: Evaluating the gradients at g = +tau and g = -tau (tau ~ the relative error of an fp32 GEMM row, 1e-6) flips EVERY
+#: decision that lies within fp32 rounding noise of zero; the distance between the two gradients is how much of the
+#: answer those decisions control on this weight draw.
+GATE_SHIFT = None
+
+
+class _GatedRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, thr):
+        ctx.save_for_backward(x > thr)
+        return x.clamp_min(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (gate,) = ctx.saved_tensors
+        return g * gate, None
+
+
+class _GatedAbsLeaky(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope, thr):
+        ctx.save_for_backward(x > thr)
+        ctx.slope = slope
+        return torch.abs(F.leaky_relu(x, slope))
+
+    @staticmethod
+    def backward(ctx, g):
+        (gate,) = ctx.saved_tensors
+        return torch.where(gate, g, -ctx.slope * g), None, None
+
+
+def _relu(x):
+    if GATE_SHIFT is None:
+        return F.relu(x)
+    return _GatedRelu.apply(x, float(GATE_SHIFT) * float(x.detach().abs().mean()))
+
+
+def _abs_leaky(x, slope):
+    if GATE_SHIFT is None:
+        return torch.abs(F.leaky_relu(x, slope))
+    return _GatedAbsLeaky.apply(x, slope, float(GATE_SHIFT) * float(x.detach().abs().mean()))
+
 
 class MLPRef(nn.Module):
     """Bias-free ReLU MLP with tcnn padding rules.
@@ -175,7 +219,7 @@ class MLPRef(nn.Module):
             else:
                 x = x @ w.t()
             if k + 1 < len(mats):
-                x = F.relu(x)
+                x = _relu(x)
         return x[:, : self.n_out]
 
 
@@ -206,7 +250,7 @@ class LayeredInjectionRef(nn.Module):
             h = layer(x)
             if ch_id is not None:
                 h = h + self.layer_embeddings[idx][ch_id]
-            x = F.relu(h)
+            x = _relu(h)
         return self.output_layer(x)
 
 
@@ -273,10 +317,10 @@ class AVRModelRef(nn.Module):
         if ch_idx is not None:
             ch = ch_idx.unsqueeze(1).expand(-1, n_pts).reshape(-1)                  # :193-195
         sigma_feat = self._run("enc", "_model_encoder_sigma", "encoder_channel_embedding", self._pos_encoding(pts), ch)   # :191-206
-        attn = self._run("dec", "_model_decoder_sigma", "decoder_channel_embedding", F.relu(sigma_feat), ch)              # :209-216
+        attn = self._run("dec", "_model_decoder_sigma", "decoder_channel_embedding", _relu(sigma_feat), ch)              # :209-216
         sig_in = torch.cat([sigma_feat, self._dir_encoding(view), self._tx_encoding(tx)], dim=-1)   # :219-221
         signal = self._run("sig", "_model_signal", "signal_channel_embedding", sig_in, ch)          # :223-231
-        attn = torch.abs(F.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)   # :233
+        attn = _abs_leaky(attn, self.leaky_slope).view(bs, n_pts, 1)                # :233
         return attn, signal.view(bs, n_pts, self.signal_output_dim)
 
 
@@ -306,11 +350,11 @@ class AVRModelComplexRef(nn.Module):
         tx_view = (tx_view.reshape(-1, 3) + 1) / 2
         sigma_feat = self._model_encoder_sigma(
             torch.cat([self._pos_encoding(pts), self._tx_pos_encoding(tx)], -1))    # :313-318
-        attn = self._model_decoder_sigma(F.relu(sigma_feat))                        # :319
-        feat = torch.cat([F.relu(sigma_feat), self._dir_encoding(view), self._tx_dir_encoding(tx_view),
+        attn = self._model_decoder_sigma(_relu(sigma_feat))                         # :319
+        feat = torch.cat([_relu(sigma_feat), self._dir_encoding(view), self._tx_dir_encoding(tx_view),
                           self._pos_signal_encoding(pts), self._tx_pos_signal_encoding(tx)], -1)     # :321-326
         signal = self._model_signal(feat)                                           # :327
-        attn = torch.abs(F.leaky_relu(attn, self.leaky_slope)).view(bs, n_pts, 1)   # :329
+        attn = _abs_leaky(attn, self.leaky_slope).view(bs, n_pts, 1)                # :329
         return attn, signal.reshape(bs, n_pts, self.signal_output_dim)
 
 

@@ -79,3 +79,35 @@ def oracle_fp32_noise(ref_net, render_kwargs, rx, tx, G, dtx=None, orders=(None,
     finally:
         field_ref.K_ORDER_SEED = saved
     return worst_out, worst
+
+
+def oracle_gate_spread(ref_net, render_kwargs, rx, tx, G, dtx=None, tau=1e-6, **fwd_kwargs):
+    """{param name: rel_l2} between the oracle's gradients with every ReLU / |leaky_relu| backward decision taken at
+    ``v > +tau * mean|v|`` and at ``v > -tau * mean|v|`` (``field_ref.GATE_SHIFT``): ALL decisions that lie within fp32
+    rounding noise of zero (an fp32 GEMM row is good to ~1e-6 of its scale) flipped at once.  Deterministic, unlike the
+    summation-order probe, which only samples which of those decisions a particular rounding happens to flip."""
+    import copy
+
+    grads = []
+    saved = field_ref.GATE_SHIFT
+    try:
+        for shift in (tau, -tau):
+            field_ref.GATE_SHIFT = shift
+            net = copy.deepcopy(ref_net)
+            for p in net.parameters():
+                p.grad = None
+            out = render_ref.RenderRef(net, **render_kwargs)(rx, tx, dtx, **fwd_kwargs)
+            (out * G).sum().backward()
+            grads.append({n: p.grad for n, p in net.named_parameters()})
+    finally:
+        field_ref.GATE_SHIFT = saved
+    return {n: rel_l2(grads[0][n], grads[1][n]) for n in grads[0]}
+
+
+def oracle_conditioning(ref_net, render_kwargs, rx, tx, G, dtx=None, orders=(None, 1, 2), tau=1e-6, **fwd_kwargs):
+    """-> (spread of the IR, {param: spread}): the larger of the summation-order probe and the gate-shift probe.  The
+    parity bar of a test is ``max(1e-4, 2 * spread)``: where fp32 arithmetic itself leaves the answer open by more than
+    the bar, no implementation -- the reference's included -- can be held to it."""
+    n_out, a = oracle_fp32_noise(ref_net, render_kwargs, rx, tx, G, dtx=dtx, orders=orders, **fwd_kwargs)
+    b = oracle_gate_spread(ref_net, render_kwargs, rx, tx, G, dtx=dtx, tau=tau, **fwd_kwargs)
+    return n_out, {n: max(a[n], b[n]) for n in a}

@@ -9,7 +9,7 @@ import torch
 import avr_b200
 from avr_b200.configs import get_config, tiny_config
 from oracle import field_ref, render_ref
-from tests.helpers import GOLDEN_CASES, case_config, load_golden, oracle_field, oracle_fp32_noise, rel_l2
+from tests.helpers import GOLDEN_CASES, case_config, load_golden, oracle_conditioning, oracle_field, rel_l2
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -131,9 +131,9 @@ def test_channel_embedding_vs_oracle(built_library, conn, enc, dec, sig):
     G = torch.randn(bs, 201, 2, generator=gen)
     # Random embedding rows can put a tiny problem on a kink (|leaky_relu(.)| at 0, a ReLU at 0): then fp32 evaluations that
     # differ only in summation order disagree with each other.  No seed is rejected: the bar is 1e-4, widened to twice the
-    # oracle's own spread over summation orders when that is larger (tests/helpers.py::oracle_fp32_noise).
+    # oracle's own spread when that is larger (tests/helpers.py::oracle_conditioning).
     ref_net = field_ref.trained_like_(field_ref.AVRModelRef(cfg["model"], seed=21), seed=22)
-    n_out, noise = oracle_fp32_noise(ref_net, r, rx, tx, G, ch_idx=ch, azi_rand=azi, orders=(None, 1, 2, 3, 4, 5))
+    n_out, noise = oracle_conditioning(ref_net, r, rx, tx, G, ch_idx=ch, azi_rand=azi)
     tol = max(TOL, 2 * max([n_out] + list(noise.values())))
     print(f"\nchannel embedding {conn} enc={enc} dec={dec} sig={sig}: oracle spread {max(noise.values()):.1e} -> bar {tol:.1e}")
     native = _native_from(ref_net, "AVRModel", cfg["model"])
