@@ -11,7 +11,7 @@ holds a full replica, and the only exchange is the mean of the parameter gradien
 tables (``_dir_encoding``, ``_tx_encoding``: 76 of the 120 MB at simu, 183 of 229 MB at MeshRIR, 152 of 236 MB at RAF)
 are touched by R = 650..3202 resp. bs points per step, so > 93 % of what the flat all-reduce ships for them is zeros.
 With ``attach`` the backward pass all-gathers the pre-scatter rows instead (``[R, 3 + 40]`` floats per rank and table,
-~350 KB; started inside the backward pass, finished at its end) and every rank scatters the rows of ALL ranks into its
+~350 KB; one collective at the end of the pass) and every rank scatters the rows of ALL ranks into its
 own table gradient with the int64 fixed-point accumulator -- integer sums, so every replica holds the bit-identical
 mean, exactly what an all-reduce guarantees.  Those tables then sit behind ``reduce_numel`` in the arena and the
 all-reduce covers the dense prefix only (the per-point tables, the MLPs, channel embeddings).
@@ -30,35 +30,43 @@ def _active(group=None) -> bool:
 
 
 class RowExchange:
-    """All-gather of the ``(unit-cube input, gradient row)`` pairs of a per-ray / per-receiver encoding."""
+    """All-gather of the ``(unit-cube input, gradient row)`` pairs of the per-ray / per-receiver encodings: ONE collective
+    for all such tables of a backward pass, issued at its end.  (Starting it in the middle of the pass was measured
+    slower: a collective that becomes resident next to the persistent one-CTA-per-SM GEMM kernels takes an SM away from
+    the next of them, whose 148th CTA then runs after the other 147.)"""
 
     def __init__(self, group=None):
         self.group = group
 
-    def start(self, u: torch.Tensor, rows: torch.Tensor):
-        """``u[n,3]``, ``rows[n,w]`` of this rank -> handle; every rank must call with the same ``n`` and ``w``."""
-        packed = torch.cat([u, rows], dim=1).contiguous()
-        if not _active(self.group):
-            return None, packed, 1, packed.device
-        world = dist.get_world_size(self.group)
-        staged = packed
-        if packed.is_cuda and dist.get_backend(self.group) != "nccl":      # gloo (tests): gather through host copies
-            staged = packed.cpu()
-        out = torch.empty(world * staged.shape[0], staged.shape[1], dtype=staged.dtype, device=staged.device)
-        work = dist.all_gather_into_tensor(out, staged, group=self.group, async_op=True)
-        return work, out, world, packed.device
-
-    def finish(self, handle):
-        """-> ``(u_all[W*n,3], rows_all[W*n,w] / W)`` in rank order (stream-level wait on NCCL: the host does not block)."""
-        work, out, world, dev = handle
-        if work is not None:
-            work.wait()
-        out = out.to(dev)
-        u_all = out[:, :3].contiguous()
-        rows_all = out[:, 3:].contiguous()
-        if world > 1:
-            rows_all = rows_all * (1.0 / world)                             # gradients are averaged over ranks (DDP)
-        return u_all, rows_all
+    def gather(self, blocks):
+        """``blocks``: list of ``(u[n_i,3], rows[n_i,w])`` of this rank (same shapes on every rank) ->
+        list of ``(u_all[W*n_i,3], rows_all[W*n_i,w] / W)`` in rank order."""
+        if not blocks:
+            return []
+        w = blocks[0][1].shape[1]
+        if any(r.shape[1] != w for _, r in blocks):
+            raise ValueError("row blocks of one exchange must share their width")
+        packed = torch.cat([torch.cat([u, r], dim=1) for u, r in blocks], dim=0).contiguous()        # [sum n_i, 3 + w]
+        world, dev = 1, packed.device
+        if _active(self.group):
+            world = dist.get_world_size(self.group)
+            staged = packed
+            if packed.is_cuda and dist.get_backend(self.group) != "nccl":     # gloo (tests): gather through host copies
+                staged = packed.cpu()
+            out = torch.empty(world * staged.shape[0], staged.shape[1], dtype=staged.dtype, device=staged.device)
+            dist.all_gather_into_tensor(out, staged, group=self.group)
+            packed = out.to(dev)
+        packed = packed.view(world, -1, 3 + w)
+        res, off = [], 0
+        for u, r in blocks:
+            n = u.shape[0]
+            blk = packed[:, off:off + n, :].reshape(world * n, 3 + w)
+            rows_all = blk[:, 3:].contiguous()
+            if world > 1:
+                rows_all = rows_all * (1.0 / world)                             # gradients are averaged over ranks (DDP)
+            res.append((blk[:, :3].contiguous(), rows_all))
+            off += n
+        return res
 
 
 class GradArena:

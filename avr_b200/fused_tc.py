@@ -269,8 +269,8 @@ class FusedRenderTC(torch.autograd.Function):
         grads = {}
         # Data-parallel runs (ddp.GradArena.attach): the per-ray / per-receiver tables receive gradient from only R / bs
         # points, so instead of all-reducing their (almost all-zero) 38-145 MB gradients the ranks all-gather the few
-        # pre-scatter rows and every rank scatters all of them locally.  The gather starts as soon as the rows exist and
-        # the scatter is deferred to the end of the pass, behind the remaining backward kernels.
+        # pre-scatter rows and every rank scatters all of them locally -- ONE collective for all such tables, at the end of
+        # the pass (a collective started mid-pass takes an SM from the persistent GEMM kernels: measured slower).
         exchange = plan.get("row_exchange")
         deferred = []
 
@@ -293,7 +293,7 @@ class FusedRenderTC(torch.autograd.Function):
                 else:
                     small = ops.rows_reduce(geom, d_buf, col, wdt, kind != "ray")
                     if exchange is not None:
-                        deferred.append((mod, exchange.start(ctx.small_in[kind], small)))
+                        deferred.append((mod, ctx.small_in[kind], small))
                         col += wdt
                         continue
                     acc = ops.GridGradAccumulator(mod.meta, dev, small.shape[0], scratch, mod.grid_grad)
@@ -415,11 +415,11 @@ class FusedRenderTC(torch.autograd.Function):
             ops.umma_nt(g, wt_enc[0], 0, d_x0)
             grads[id(enc_net)] = g_enc
         scatter_segments(plan["x0"], d_x0)
-        for mod, handle in deferred:
+        gathered = exchange.gather([(u, small) for _, u, small in deferred]) if deferred else []
+        for (mod, _, _), (u_all, rows_all) in zip(deferred, gathered):
             # rows of ALL ranks (already scaled to the mean), scattered in rank order with the int64 accumulator: every
             # replica gets the bit-identical gradient, like after an all-reduce
-            u_all, rows_all = exchange.finish(handle)
-            acc = ops.GridGradAccumulator(mod.meta, dev, rows_all.shape[0], None, "deterministic")
+            acc = ops.GridGradAccumulator(mod.meta, dev, rows_all.shape[0], scratch, "deterministic")
             acc.observe(rows_all, 0, rows_all.shape[1])
             acc.add_points(u_all, rows_all)
             grads[id(mod)] = acc.finalize()

@@ -1,12 +1,11 @@
 set -x
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -q -s --durations=15 ) > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-python bench.py --config meshrir --mode infer --receivers 3969 --bs 8 > gpurun_out/bench_meshrir_all_1gpu.json 2> gpurun_out/bench_meshrir_all_1gpu.err
-python bench.py --config simu --bs 1 --steps 20 --no-other-configs --no-cpu-baseline > gpurun_out/bench_simu_bs1.json 2> gpurun_out/bench_simu_bs1.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2a_launches.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_launches.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:umma_gemm_kernel -s 60 -c 20 --csv --log-file gpurun_out/r2a_umma_dram_traffic.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_traffic.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mlp_chain -c 1 -o gpurun_out/chain_r2d python profiles/run_chain_once.py > gpurun_out/ncu_chain.log 2>&1
-tail -5 gpurun_out/pytest_gpu.log
+nvidia-smi -L > gpurun_out/gpus.txt
+timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline --no-other-configs --no-alt > gpurun_out/bench_8box_1gpu.json 2> gpurun_out/bench_8box_1gpu.err
+for n in 2 4; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 3 --no-cpu-baseline --no-other-configs --no-alt > gpurun_out/bench_8box_${n}gpu.json 2> gpurun_out/bench_8box_${n}gpu.err
+done
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_8box_8gpu.json 2> gpurun_out/bench_8box_8gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline --no-other-configs --no-alt --flat-allreduce > gpurun_out/bench_8box_8gpu_flat.json 2> gpurun_out/bench_8box_8gpu_flat.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 --config meshrir --mode infer --receivers 3969 --bs 8 > gpurun_out/bench_meshrir_all_8gpu.json 2> gpurun_out/bench_meshrir_all_8gpu.err
+ls -la gpurun_out

@@ -37,11 +37,14 @@ def _worker(rank, world, port, out_dir):
     ex = RowExchange()
     u = torch.full((3, 3), float(rank))
     rows = torch.arange(3 * 5, dtype=torch.float32).view(3, 5) + 100 * rank
-    u_all, rows_all = ex.finish(ex.start(u, rows))
-    assert u_all.shape == (3 * world, 3) and rows_all.shape == (3 * world, 5)
+    u2, rows2 = torch.full((2, 3), 10.0 + rank), torch.full((2, 5), 7.0 * (rank + 1))       # a second table, other row count
+    (u_all, rows_all), (u2_all, rows2_all) = ex.gather([(u, rows), (u2, rows2)])
+    assert u_all.shape == (3 * world, 3) and rows_all.shape == (3 * world, 5) and u2_all.shape == (2 * world, 3)
     for r in range(world):
         assert torch.equal(u_all[3 * r:3 * r + 3], torch.full((3, 3), float(r)))
         assert torch.equal(rows_all[3 * r:3 * r + 3], (torch.arange(15, dtype=torch.float32).view(3, 5) + 100 * r) / world)
+        assert torch.equal(u2_all[2 * r:2 * r + 2], torch.full((2, 3), 10.0 + r))
+        assert torch.equal(rows2_all[2 * r:2 * r + 2], torch.full((2, 5), 7.0 * (r + 1) / world))
     # an arena whose tail is exchanged as rows: the all-reduce must leave that tail alone
     a, b = torch.nn.Parameter(torch.zeros(10)), torch.nn.Parameter(torch.zeros(7))
     arena2 = avr_b200.GradArena([a, b])
@@ -69,8 +72,8 @@ def test_two_rank_gradient_mean_equals_single_process(tmp_path):
 def test_row_exchange_without_process_group_is_the_identity():
     ex = RowExchange()
     u, rows = torch.rand(4, 3), torch.rand(4, 6)
-    u_all, rows_all = ex.finish(ex.start(u, rows))
-    assert torch.equal(u_all, u) and torch.equal(rows_all, rows)
+    ((u_all, rows_all),) = ex.gather([(u, rows)])
+    assert torch.equal(u_all, u) and torch.equal(rows_all, rows) and ex.gather([]) == []
 
 
 def test_shard_receivers_is_distributed_sampler_order():
