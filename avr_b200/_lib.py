@@ -46,6 +46,14 @@ class ChainLayer(C.Structure):
                 ("out_f32", C.c_void_p), ("ld_f32", C.c_int64)]
 
 
+class SplitDesc(C.Structure):
+    """``avr_split_desc`` (include/avr_b200.h)."""
+    _fields_ = [("x", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("ld", C.c_int64),
+                ("planes", C.c_void_p), ("ldp", C.c_int64), ("plane_stride", C.c_int64),
+                ("kind", C.c_int32), ("transpose", C.c_int32)]
+
+
+SPLIT_BATCH_MAX = 32
 CHAIN_MAX_LAYERS = 8
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
@@ -68,6 +76,7 @@ SIGNATURES = {
     "avr_gemm": (C.c_int, [C.c_int, C.c_int, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, C.c_int, _P, _I64,
                            _P, _I64, C.c_int, _P]),
     "avr_planes_split": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "avr_planes_split_batch": (C.c_int, [C.POINTER(SplitDesc), _I32, C.c_int, _P]),
     "avr_planes_merge": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.c_int, _P, _I64, C.c_int, _P]),
     "avr_umma_gemm_nt": (C.c_int, [_I64, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.c_int, _P, _I64,
                                    _I64, C.c_int, _P, _I64, _I64, C.c_int, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P, _I64,

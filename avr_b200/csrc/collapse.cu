@@ -54,18 +54,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// workspace kept from forward to backward: G snapshots [cells][tspan][width], G_tot [cells][width], range [cells][2]
+// workspace kept from forward to backward.  The sorted ray list of a cell is walked in PW_SEG independent segments:
+//   gp    [cells][tspan][width]   slot t - dmin: the prefix sum WITHIN the segment that owns t (rays of that segment with
+//                                 delay <= t); segment k owns t in [first delay of segment k, first delay of segment k+1)
+//   cum   [cells][PW_SEG][width]  sum of all rays of the segments before k  ->  G(t) = cum[k(t)] + gp[t - dmin]
+//   gtot  [cells][width]          sum of all rays (G(t) for t >= dmax), NaN-poisoned when the cell's delay spread > tspan
+//   segfirst [cells][PW_SEG], range [cells][2] = (dmin, dmax);  segtot [cells][PW_SEG][width] = per-segment totals
+constexpr int PW_SEG = 4;
 struct PrefixWs {
     float* gp;
+    float* cum;
     float* gtot;
+    float* segtot;
+    int* segfirst;
     int* range;
 };
 __host__ __device__ inline PrefixWs carve_prefix(void* ws, long long cells, int tspan, int width) {
     PrefixWs w;
     w.gp = reinterpret_cast<float*>(ws);
-    w.gtot = w.gp + cells * tspan * width;
-    w.range = reinterpret_cast<int*>(w.gtot + cells * width);
+    w.cum = w.gp + cells * tspan * width;
+    w.gtot = w.cum + cells * PW_SEG * width;
+    w.segtot = w.gtot + cells * width;
+    w.segfirst = reinterpret_cast<int*>(w.segtot + cells * PW_SEG * width);
+    w.range = w.segfirst + cells * PW_SEG;
     return w;
+}
+// segment of the cell that owns time step t (segfirst is non-decreasing; empty segments carry dmax)
+__device__ __forceinline__ int owner_segment(const int* __restrict__ sf, int t) {
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < PW_SEG; ++j) k += (__ldg(sf + j) <= t) ? 1 : 0;
+    return k;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -125,39 +144,45 @@ delay_sort_kernel(const Geom geo, const int* __restrict__ delay, const float* __
 // prefix walk: G snapshots of one cell
 // ------------------------------------------------------------------------------------------------
 constexpr int PW_GROUP = 4;        // rays per cp.async group
-constexpr int PW_NGROUPS = 8;      // groups in flight  -> 32 rays deep
+constexpr int PW_NGROUPS = 4;      // groups in flight  -> 16 rays deep (seven CTAs per SM: the segments supply the parallelism)
 constexpr int PW_MAX_THREADS = 256;
 
+// grid (cells, PW_SEG): segment k of the cell's delay-sorted ray list
 __global__ void __launch_bounds__(PW_MAX_THREADS)
 prefix_walk_kernel(const Geom geo, const Planes act, int width, const int* __restrict__ order,
                    const int* __restrict__ sdelay, const float* __restrict__ sw, PrefixWs ws, int tspan) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int cell = blockIdx.x, b = cell / geo.S, s = cell - b * geo.S;
+    const int cell = blockIdx.x, seg = blockIdx.y, b = cell / geo.S, s = cell - b * geo.S;
     const int R = geo.R;
+    const int L = (R + PW_SEG - 1) / PW_SEG;
+    const int k_beg = min(R, seg * L), k_end = min(R, k_beg + L), n_here = k_end - k_beg;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int c = tid * 4;
     const bool col_ok = c < width;
     int* l_ord = reinterpret_cast<int*>(smem);
-    int* l_del = l_ord + R;
-    float* l_w = reinterpret_cast<float*>(l_del + R);
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem + (((size_t)R * 12 + 15) & ~(size_t)15));
+    int* l_del = l_ord + L;
+    float* l_w = reinterpret_cast<float*>(l_del + L);
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem + (((size_t)L * 12 + 15) & ~(size_t)15));
     const long long lbase = (long long)cell * R;
-    for (int k = tid; k < R; k += nthr) {
-        l_ord[k] = __ldg(order + lbase + k);
-        l_del[k] = __ldg(sdelay + lbase + k);
-        l_w[k] = __ldg(sw + lbase + k);
+    for (int k = tid; k < n_here; k += nthr) {
+        l_ord[k] = __ldg(order + lbase + k_beg + k);
+        l_del[k] = __ldg(sdelay + lbase + k_beg + k);
+        l_w[k] = __ldg(sw + lbase + k_beg + k);
     }
     __syncthreads();
-    const int dmin = l_del[0], dmax = l_del[R - 1];
+    const int dmin = __ldg(sdelay + lbase), dmax = __ldg(sdelay + lbase + R - 1);
     const bool overflow = (dmax - dmin) > tspan;
-    const int n_groups = (R + PW_GROUP - 1) / PW_GROUP;
+    // this segment owns the time steps from its first delay up to the next segment's first delay
+    const int t_first = n_here > 0 ? l_del[0] : dmax;
+    const int t_next = k_end < R ? __ldg(sdelay + lbase + k_end) : dmax;
+    const int n_groups = (n_here + PW_GROUP - 1) / PW_GROUP;
 
     auto issue = [&](int g) {
         if (g < n_groups && col_ok) {
 #pragma unroll
             for (int j = 0; j < PW_GROUP; ++j) {
                 const int k = g * PW_GROUP + j;
-                if (k < R) {
+                if (k < n_here) {
                     const long long row = ((long long)b * R + l_ord[k]) * geo.S + s;
                     const __nv_bfloat16* q = act.p + row * act.ld + c;
                     const uint32_t dst = ring + (uint32_t)((((g % PW_NGROUPS) * PW_GROUP + j) * nthr + tid) * 16);
@@ -171,16 +196,16 @@ prefix_walk_kernel(const Geom geo, const Planes act, int width, const int* __res
     for (int g = 0; g < PW_NGROUPS; ++g) issue(g);
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int t = dmin;
+    int t = t_first;
     float* gp_cell = ws.gp + (long long)cell * tspan * width;
     for (int g = 0; g < n_groups; ++g) {
         cp_async_wait<PW_NGROUPS - 1>();
 #pragma unroll
         for (int j = 0; j < PW_GROUP; ++j) {
             const int k = g * PW_GROUP + j;
-            if (k >= R) break;
+            if (k >= n_here) break;
             const int d = l_del[k];
-            while (t < d) {                                    // snapshot G(t) for every t the prefix is constant over
+            while (t < d) {                                    // snapshot for every t the prefix is constant over
                 if (col_ok && !overflow)
                     *reinterpret_cast<float4*>(gp_cell + (long long)(t - dmin) * width + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                 ++t;
@@ -200,12 +225,34 @@ prefix_walk_kernel(const Geom geo, const Planes act, int width, const int* __res
         issue(g + PW_NGROUPS);
     }
     cp_async_wait<0>();
-    if (col_ok) {
-        const float poison = overflow ? __uint_as_float(0x7fc00000u) : 0.f;
-        *reinterpret_cast<float4*>(ws.gtot + (long long)cell * width + c) =
-            make_float4(acc[0] + poison, acc[1] + poison, acc[2] + poison, acc[3] + poison);
+    while (t < t_next) {                                       // ... up to the next segment's first delay: the segment total
+        if (col_ok && !overflow)
+            *reinterpret_cast<float4*>(gp_cell + (long long)(t - dmin) * width + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        ++t;
     }
-    if (tid == 0) { ws.range[2 * cell] = dmin; ws.range[2 * cell + 1] = dmax; }
+    if (col_ok)
+        *reinterpret_cast<float4*>(ws.segtot + ((long long)cell * PW_SEG + seg) * width + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (tid == 0) {
+        ws.segfirst[cell * PW_SEG + seg] = t_first;
+        if (seg == 0) { ws.range[2 * cell] = dmin; ws.range[2 * cell + 1] = dmax; }
+    }
+}
+
+// cum[cell][k] = sum of the totals of the segments before k (fixed order); gtot = the sum of all, NaN when the cell's
+// delay spread exceeds tspan (its snapshots do not exist: consumers read the poisoned total instead)
+__global__ void prefix_offsets_kernel(const Geom geo, int width, PrefixWs ws, int tspan) {
+    const int cell = blockIdx.x;
+    const int c = threadIdx.x * 4;
+    if (c >= width) return;
+    const bool overflow = (ws.range[2 * cell + 1] - ws.range[2 * cell]) > tspan;
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < PW_SEG; ++k) {
+        *reinterpret_cast<float4*>(ws.cum + ((long long)cell * PW_SEG + k) * width + c) = run;
+        const float4 t = *reinterpret_cast<const float4*>(ws.segtot + ((long long)cell * PW_SEG + k) * width + c);
+        run.x += t.x; run.y += t.y; run.z += t.z; run.w += t.w;
+    }
+    const float poison = overflow ? __uint_as_float(0x7fc00000u) : 0.f;
+    *reinterpret_cast<float4*>(ws.gtot + (long long)cell * width + c) = make_float4(run.x + poison, run.y + poison, run.z + poison, run.w + poison);
 }
 
 // y[cell, t] = G(cell, t) . W_out[t, :]      grid (cells, t-chunks), one warp per t
@@ -218,15 +265,19 @@ prefix_dot_kernel(const Geom geo, int width, PrefixWs ws, int tspan, const float
     const int t_beg = blockIdx.y * t_per_block, t_end = min(geo.T, t_beg + t_per_block);
     const float* gp_cell = ws.gp + (long long)cell * tspan * width;
     const float* gt = ws.gtot + (long long)cell * width;
+    const int* sf = ws.segfirst + cell * PW_SEG;
     for (int t = t_beg + warp; t < t_end; t += n_warps) {
         float p = 0.f;
         if (t >= dmin) {
             // a cell whose delay spread exceeds tspan has no snapshots (they would lie outside its slice of the
             // workspace): it reads the poisoned total instead -> NaN, never an out-of-bounds access
-            const float* g = (t < dmax && dmax - dmin <= tspan) ? gp_cell + (long long)(t - dmin) * width : gt;
+            const bool snap = t < dmax && dmax - dmin <= tspan;
+            const float* g = snap ? gp_cell + (long long)(t - dmin) * width : gt;
+            const float* off = snap ? ws.cum + ((long long)cell * PW_SEG + owner_segment(sf, t)) * width : nullptr;
             const float* wr = w_out + (long long)t * ldw;
             for (int c = lane * 4; c < width; c += 128) {
-                const float4 a = *reinterpret_cast<const float4*>(g + c);
+                float4 a = *reinterpret_cast<const float4*>(g + c);
+                if (off) { const float4 o = *reinterpret_cast<const float4*>(off + c); a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
                 const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
                 p = fmaf(a.x, wv.x, p); p = fmaf(a.y, wv.y, p); p = fmaf(a.z, wv.z, p); p = fmaf(a.w, wv.w, p);
             }
@@ -249,9 +300,13 @@ __global__ void dwout_reduce_kernel(const Geom geo, int width, const float* __re
         const int dmin = __ldg(ws.range + 2 * i), dmax = __ldg(ws.range + 2 * i + 1);
         if (t < dmin) continue;
         const float g = __ldg(d_y + (long long)i * geo.T + t);
-        const float* src = (t < dmax && dmax - dmin <= tspan) ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c
-                                                              : ws.gtot + (long long)i * width + c;
-        const float4 a = *reinterpret_cast<const float4*>(src);
+        const bool snap = t < dmax && dmax - dmin <= tspan;
+        const float* src = snap ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c : ws.gtot + (long long)i * width + c;
+        float4 a = *reinterpret_cast<const float4*>(src);
+        if (snap) {
+            const float4 o = *reinterpret_cast<const float4*>(ws.cum + ((long long)i * PW_SEG + owner_segment(ws.segfirst + i * PW_SEG, t)) * width + c);
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+        }
         v.x = fmaf(g, a.x, v.x); v.y = fmaf(g, a.y, v.y); v.z = fmaf(g, a.z, v.z); v.w = fmaf(g, a.w, v.w);
     }
     float* dst = d_wout + (long long)t * ldw + c;
@@ -385,7 +440,7 @@ AVR_API int avr_delay_sort(const avr_render_geom* geom, const int32_t* delay, co
 AVR_API int64_t avr_collapse_prefix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan) {
     if (!geom) return 0;
     const int64_t n = (int64_t)geom->bs * geom->S;
-    return (n * tspan * width + n * width) * (int64_t)sizeof(float) + n * 2 * (int64_t)sizeof(int) + 64;
+    return (n * tspan * width + n * width + 2 * n * PW_SEG * width) * (int64_t)sizeof(float) + n * (2 + PW_SEG) * (int64_t)sizeof(int) + 64;
 }
 
 AVR_API int64_t avr_collapse_suffix_bytes(const avr_render_geom* geom, int32_t width, int32_t tspan) {
@@ -411,10 +466,13 @@ AVR_API int avr_collapse_fwd(const avr_render_geom* geom, const void* act_planes
     cudaStream_t st = (cudaStream_t)stream;
     const PrefixWs ws = carve_prefix(prefix_ws, cells, tspan, width);
     const int threads = ((width / 4 + 31) / 32) * 32;
-    const size_t smem = (((size_t)geo.R * 12 + 15) & ~(size_t)15) + (size_t)PW_GROUP * PW_NGROUPS * threads * 16;
+    const size_t seg_len = (size_t)(geo.R + PW_SEG - 1) / PW_SEG;
+    const size_t smem = ((seg_len * 12 + 15) & ~(size_t)15) + (size_t)PW_GROUP * PW_NGROUPS * threads * 16;
     AVR_CUDA(cudaFuncSetAttribute(prefix_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const Planes act = {(const __nv_bfloat16*)act_planes, ld_act, act_plane, planes_f16(act_kind)};
-    prefix_walk_kernel<<<cells, threads, smem, st>>>(geo, act, width, order, sdelay, sw, ws, tspan);
+    prefix_walk_kernel<<<dim3(cells, PW_SEG), threads, smem, st>>>(geo, act, width, order, sdelay, sw, ws, tspan);
+    AVR_LAUNCH_CHECK();
+    prefix_offsets_kernel<<<cells, threads, 0, st>>>(geo, width, ws, tspan);
     AVR_LAUNCH_CHECK();
     const int t_chunks = 8;
     const int t_per_block = (int)ceil_div(geo.T, t_chunks);

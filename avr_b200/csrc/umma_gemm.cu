@@ -548,6 +548,19 @@ __global__ void planes_split_kernel(const float* __restrict__ x, long long rows,
     planes_store(out, transpose ? c * ldp + r : r * ldp + c, plane, kind, v);
 }
 
+// several matrices in one launch (the weight matrices of a pass: 11 forward, 12 transposed backward at simu)
+struct SplitBatch {
+    avr_split_desc d[AVR_SPLIT_BATCH_MAX];
+};
+__global__ void planes_split_batch_kernel(const __grid_constant__ SplitBatch b) {
+    const avr_split_desc& d = b.d[blockIdx.y];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.rows * d.cols) return;
+    const long long r = i / d.cols, c = i - r * d.cols;
+    const float v = d.x[r * d.ld + c];
+    planes_store(d.planes, d.transpose ? c * d.ldp + r : r * d.ldp + c, d.plane_stride, d.kind, v);
+}
+
 __global__ void planes_merge_kernel(const void* __restrict__ in, long long rows, long long cols, long long ldp,
                                     long long plane, int kind, float* __restrict__ out, long long ld) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -711,6 +724,26 @@ AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t
     if (rows * cols == 0) return AVR_OK;
     planes_split_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(
         x, rows, cols, ld, planes, ldp, plane_stride, nplanes, transpose, relu);
+    AVR_LAUNCH_CHECK();
+    return AVR_OK;
+}
+
+AVR_API int avr_planes_split_batch(const avr_split_desc* descs, int32_t n, int device, void* stream) {
+    AVR_REQUIRE(descs || n == 0, "null pointer");
+    AVR_REQUIRE(n >= 0 && n <= AVR_SPLIT_BATCH_MAX, "too many matrices for one batch");
+    AVR_ENTER(device);
+    if (n == 0) return AVR_OK;
+    SplitBatch b = {};
+    long long most = 0;
+    for (int k = 0; k < n; ++k) {
+        AVR_REQUIRE(descs[k].x && descs[k].planes && planes_kind_ok(descs[k].kind) && descs[k].rows >= 0 && descs[k].cols >= 0,
+                    "bad matrix descriptor");
+        b.d[k] = descs[k];
+        const long long e = (long long)descs[k].rows * descs[k].cols;
+        most = e > most ? e : most;
+    }
+    if (most == 0) return AVR_OK;
+    planes_split_batch_kernel<<<dim3((unsigned)ceil_div(most, 256), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(b);
     AVR_LAUNCH_CHECK();
     return AVR_OK;
 }

@@ -49,15 +49,21 @@ def _lib_chain_max():
     return CHAIN_MAX_LAYERS
 
 
-def _weight_planes(net, params, transpose, n):
-    """Plane sets (kind ``n``: 2 / 3 bf16 planes or ops.PLANES_F16x2) of every matrix of ``net`` (``W[out,in]``) or of
-    its transpose (``W^T[in,out]``)."""
-    out = []
-    for w in net.matrices(params):
+def _weight_planes(net, params, transpose, n, jobs=None, count=None):
+    """Plane sets (kind ``n``: 2 / 3 bf16 planes or ops.PLANES_F16x2; a list gives one kind per matrix) of the first
+    ``count`` matrices of ``net`` (``W[out,in]``) or of their transposes (``W^T[in,out]``).  With ``jobs`` (a list) the
+    conversions are only queued there: the caller runs all matrices of the pass in ONE launch (ops.planes_split_many)."""
+    out, own = [], jobs is None
+    jobs = [] if own else jobs
+    mats = net.matrices(params)
+    for k, w in enumerate(mats[:count] if count is not None else mats):
         o, i = w.shape
-        pp = PlanePair.empty(i, o, w.device, kind=n) if transpose else PlanePair.empty(o, i, w.device, kind=n)
-        ops.planes_split(w, pp, transpose=transpose)
+        kind = n[k] if isinstance(n, (list, tuple)) else n
+        pp = PlanePair.empty(i, o, w.device, kind=kind) if transpose else PlanePair.empty(o, i, w.device, kind=kind)
+        jobs.append((w, pp, transpose))
         out.append(pp)
+    if own:
+        ops.planes_split_many(jobs)
     return out
 
 
@@ -144,26 +150,41 @@ class FusedRenderTC(torch.autograd.Function):
                   rows_of)
         if delay_slot:
             _, _, _, delay = ops.sample_points(geom, rays_o, pos_tx, dirs, d_vals, want_pts=False)
-        w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_KIND)
+        f16 = SIG_HIDDEN_F16 and guard is None
+        sig_mats = sig_net.matrices(params_of(sig_net))
+        n_sig = len(sig_mats) - 1                                            # hidden layers (the output layer is collapsed)
+        jobs = []                                                            # every weight matrix of the pass -> planes, one launch
+        w_enc = _weight_planes(enc_net, params_of(enc_net), False, FWD_KIND, jobs)
+        w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND, jobs)
+        w_sig = _weight_planes(sig_net, params_of(sig_net), False,          # layer li > 0 multiplies an fp16-pair activation
+                               [ops.PLANES_F16x2 if (f16 and li > 0) else FWD_KIND for li in range(n_sig)], jobs, count=n_sig)
+        ops.planes_split_many(jobs)
         sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev, kind=FWD_KIND)
         feat_win = sig_in.window(0, feat_dim)                                # sigma_feat lands directly in the signal network's input buffer (no concat)
         bits_feat = ops.relu_bits_empty(n_rows, feat_dim, dev)               # (sigma_feat > 0)
+        # Inference (torch.no_grad(): nothing requires grad) skips everything only the backward pass reads: saved planes of
+        # the 128-wide layers, ReLU bitmasks, the bf16 copies of the signal network's fp16-pair activations.
+        train = any(ctx.needs_input_grad[8:])
         chain = (FUSE_SIGMA_CHAIN and guard is None and not any(k[0] in ("enc", "dec") for k in bias_of) and not plan["sig_relu_feat"] and feat_dim == 128
                  and dec_net.in_pad == feat_dim and not plan.get("dec_tail") and enc_net.in_pad <= 128
                  and all(o == 128 for (o, _) in enc_net.shapes) and all(o == 128 for (o, _) in dec_net.shapes[:-1])
                  and dec_net.out_pad <= 128 and len(enc_net.shapes) + len(dec_net.shapes) <= _lib_chain_max())
         if chain:
             # ---- sigma encoder -> [relu] -> sigma decoder -> density head: one launch ----------------------------------
-            w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND)
-            acts_enc = [PlanePair.empty(n_rows, 128, dev, kind=ops.PLANES_BF16x2) for _ in w_enc[:-1]]   # weight gradients read 16 bits
-            bits_enc = [ops.relu_bits_empty(n_rows, 128, dev) for _ in w_enc[:-1]]
-            acts_dec = [PlanePair.empty(n_rows, 128, dev, kind=FWD_KIND) for _ in w_dec[:-1]]             # ... 24 along the decoder
-            bits_dec = [ops.relu_bits_empty(n_rows, 128, dev) for _ in w_dec[:-1]]
-            dec_in = PlanePair.empty(n_rows, dec_net.in_pad, dev, kind=FWD_KIND)
+            acts_enc = [PlanePair.empty(n_rows if train else 0, 128, dev, kind=ops.PLANES_BF16x2) for _ in w_enc[:-1]]   # weight gradients read 16 bits
+            bits_enc = [ops.relu_bits_empty(n_rows if train else 0, 128, dev) for _ in w_enc[:-1]]
+            acts_dec = [PlanePair.empty(n_rows if train else 0, 128, dev, kind=FWD_KIND) for _ in w_dec[:-1]]             # ... 24 along the decoder
+            bits_dec = [ops.relu_bits_empty(n_rows if train else 0, 128, dev) for _ in w_dec[:-1]]
+            dec_in = PlanePair.empty(n_rows if train else 0, dec_net.in_pad, dev, kind=FWD_KIND)
             dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
-            layers = [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_enc[:-1], acts_enc, bits_enc)]
-            layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win, save=dec_in, bits=bits_feat))   # raw feat + relu(feat)
-            layers += [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_dec[:-1], acts_dec, bits_dec)]
+            if train:
+                layers = [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_enc[:-1], acts_enc, bits_enc)]
+                layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win, save=dec_in, bits=bits_feat))   # raw feat + relu(feat)
+                layers += [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_dec[:-1], acts_dec, bits_dec)]
+            else:
+                layers = [dict(w=wp, relu=True) for wp in w_enc[:-1]]
+                layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win))
+                layers += [dict(w=wp, relu=True) for wp in w_dec[:-1]]
             layers.append(dict(w=w_dec[-1], relu=False, out_f32=dec_out))                                 # the |leaky_relu| kink follows
             ops.mlp_chain(x0, layers)
         else:
@@ -190,7 +211,6 @@ class FusedRenderTC(torch.autograd.Function):
                 raise NotImplementedError("sigma decoder input width does not match the sigma feature width")
 
             # ---- sigma decoder -> density -> ray weights ---------------------------------------------------
-            w_dec = _weight_planes(dec_net, params_of(dec_net), False, FWD_KIND)
             acts_dec, bits_dec, h = [], [], dec_in
             for li in range(len(w_dec) - 1):
                 y = PlanePair.empty(n_rows, w_dec[li].rows, dev, kind=FWD_KIND)
@@ -207,21 +227,14 @@ class FusedRenderTC(torch.autograd.Function):
         # ---- signal network hidden layers + collapsed output layer ---------------------------------
         _assemble(plan["tail"], sig_in, feat_dim, sig_net.in_pad, geom, small_in, rays_o, pos_tx, dirs, d_vals,
                   params_of, [], rows_of)
-        sig_mats = sig_net.matrices(params_of(sig_net))
-        n_sig = len(sig_mats) - 1                                            # hidden layers (the output layer is collapsed)
-        f16 = SIG_HIDDEN_F16 and guard is None
-        w_sig = []
-        for li, wm in enumerate(sig_mats[:-1]):                              # layer li > 0 multiplies an fp16-pair activation
-            o, i = wm.shape
-            w_sig.append(ops.planes_split(wm, PlanePair.empty(o, i, dev, kind=ops.PLANES_F16x2 if (f16 and li > 0) else FWD_KIND)))
         acts_sig, bits_sig, h = [], [], sig_in                               # acts_sig: what the weight gradients read
         for li in range(n_sig):
             last = li == n_sig - 1
-            bits = ops.relu_bits_empty(n_rows, w_sig[li].rows, dev) if not last else None   # the last one is read by collapse
+            bits = ops.relu_bits_empty(n_rows, w_sig[li].rows, dev) if (train and not last) else None   # the last one is read by collapse
             fl, kw = layer_flags("sig", li)
             if f16:
                 y = PlanePair.empty(n_rows, w_sig[li].rows, dev, kind=ops.PLANES_F16x2)
-                if last:                                                     # H: only the collapsed output layer reads it
+                if last or not train:                                        # H: only the collapsed output layer reads it
                     ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, **kw)
                     acts_sig.append(y)
                 else:
@@ -238,7 +251,7 @@ class FusedRenderTC(torch.autograd.Function):
         y_t, prefix = ops.collapse_fwd(geom, h, sort, sig_mats[-1], tspan)
         out = ops.spectrum_fwd_tc(geom, y_t, tables)
 
-        if any(ctx.needs_input_grad[8:]):
+        if train:
             ctx.plan, ctx.geom, ctx.tables, ctx.tspan = plan, geom, tables, tspan
             ctx.small_in, ctx.roles = small_in, roles
             ctx.bufs = dict(x0=x0, acts_enc=acts_enc, sig_in=sig_in, dec_in=dec_in, acts_dec=acts_dec, dec_out=dec_out,
@@ -305,10 +318,15 @@ class FusedRenderTC(torch.autograd.Function):
         ws_bytes = max(ops.umma_tn_workspace_bytes(o, i, n_rows) for n in (enc_net, dec_net, sig_net) for (o, i) in n.shapes)
         ws = torch.empty(max(4, ws_bytes // 4), device=dev)
 
-        def hidden_backward(net, net_key, g, acts, bits, first_input, g_flat):
+        jobs = []                                                            # all transposed weight planes of the pass: one launch
+        wt_sig_all = _weight_planes(sig_net, pmap[id(sig_net)], True, BWD_PLANES, jobs, count=len(sig_net.shapes) - 1)
+        wt_dec = _weight_planes(dec_net, pmap[id(dec_net)], True, DENSITY_BWD_PLANES, jobs)
+        wt_enc = _weight_planes(enc_net, pmap[id(enc_net)], True, BWD_PLANES, jobs)
+        ops.planes_split_many(jobs)
+
+        def hidden_backward(net, net_key, g, acts, bits, first_input, g_flat, wt):
             """Back-propagate through layers len(acts)..1 of ``net`` given g = d(pre-activation of the last
             hidden layer); fills the weight gradients of layers >= 1 and of layer 0; returns g at layer 0."""
-            wt = _weight_planes(net, pmap[id(net)], True, BWD_PLANES)
             d_mats = net.matrices(g_flat)
             bias_grad(net_key, len(acts) - 1, g)
             for li in range(len(acts) - 1, 0, -1):
@@ -333,7 +351,7 @@ class FusedRenderTC(torch.autograd.Function):
 
         # ---- signal network hidden layers ----------------------------------------------------------------
         sig_in, dec_in = B["sig_in"], B["dec_in"]
-        g, wt_sig, _ = hidden_backward(sig_net, "sig", g, B["acts_sig"], B["bits_sig"], sig_in, g_sig)
+        g, wt_sig, _ = hidden_backward(sig_net, "sig", g, B["acts_sig"], B["bits_sig"], sig_in, g_sig, wt_sig_all)
         grads[id(sig_net)] = g_sig
         d_feat = PlanePair.empty(n_rows, feat_dim, dev)
         wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
@@ -352,14 +370,12 @@ class FusedRenderTC(torch.autograd.Function):
         d_dec_out = torch.zeros_like(B["dec_out"])
         ops.ray_weights_bwd(geom, B["dec_out"], B["dec_out"].stride(0), tables["delta"], plan["slope"], d_w, d_dec_out,
                             d_dec_out.stride(0))
-        wt_dec = _weight_planes(dec_net, pmap[id(dec_net)], True, DENSITY_BWD_PLANES)
         g_dec = torch.empty_like(pmap[id(dec_net)])
         d_dec_mats = dec_net.matrices(g_dec)
         g = PlanePair.empty(n_rows, dec_net.out_pad, dev, n=DENSITY_BWD_PLANES)
         ops.planes_split(d_dec_out, g)
         acts_dec, acts_enc, x0 = B["acts_dec"], B["acts_enc"], B["x0"]
         n_dec = len(d_dec_mats)
-        wt_enc = _weight_planes(enc_net, pmap[id(enc_net)], True, BWD_PLANES)
         g_enc = torch.empty_like(pmap[id(enc_net)])
         d_enc_mats = enc_net.matrices(g_enc)
         n_enc = len(d_enc_mats)

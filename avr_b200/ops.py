@@ -340,6 +340,21 @@ def planes_split(x, out: PlanePair, transpose=False, relu=False):
     return out
 
 
+def planes_split_many(items):
+    """``items``: list of ``(x fp32 [rows, cols], out PlanePair, transpose)`` -- all of them in one launch."""
+    items = list(items)
+    for k0 in range(0, len(items), _lib.SPLIT_BATCH_MAX):
+        chunk = items[k0:k0 + _lib.SPLIT_BATCH_MAX]
+        dev, st = _ctx(chunk[0][0])
+        arr = (_lib.SplitDesc * len(chunk))()
+        for a, (x, out, transpose) in zip(arr, chunk):
+            assert x.stride(1) == 1 and x.dtype == torch.float32 and x.is_cuda
+            a.x, a.rows, a.cols, a.ld = x.data_ptr(), x.shape[0], x.shape[1], x.stride(0)
+            a.planes, a.ldp, a.plane_stride, a.kind, a.transpose = out.ptr.value, out.ld, out.plane, out.kind, 1 if transpose else 0
+        _lib.check(_lib.load().avr_planes_split_batch(arr, len(chunk), dev, st), "avr_planes_split_batch")
+    return [out for _, out, _ in items]
+
+
 def planes_merge(pp: PlanePair):
     dev, st = _ctx(pp)
     out = torch.empty(pp.rows, pp.cols, device=pp.device)

@@ -106,6 +106,15 @@ class AVRRender(nn.Module):
                                           ch_idx[sl] if ch_idx is not None else None, dirs))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
+    def graphed_inference(self, bs: int, device=None, direction_tx: bool = False, ch_idx: bool = False):
+        """The ``torch.no_grad()`` forward for a fixed batch size as ONE CUDA graph: ``f = ren.graphed_inference(1)`` then
+        ``f(rays_o, position_tx[, direction_tx][, ch_idx][, azi_rand=...]) -> [bs, F, 2]`` replays ~50 kernel launches with
+        a single ``cudaGraphLaunch``.  For the reference's evaluation loops, which render one receiver per call
+        (eval_rotate_doa_avr.py:104-110, avr_runner.py:235-247): at bs = 1 the eager step is bound by launch latency.
+        The graph reads the field's CURRENT parameters on every replay.  The returned tensor is the graph's static output
+        buffer: it is overwritten by the next call (clone it to keep it)."""
+        return GraphedInference(self, int(bs), device, direction_tx, ch_idx)
+
     def _render_pass(self, rays_o, position_tx, direction_tx, ch_idx, dirs):
         net = self.network_fn
         bs = rays_o.size(0)
@@ -157,3 +166,57 @@ class AVRRender(nn.Module):
         attn = attn.reshape(bs, geom.R, geom.S)
         signal = signal.reshape(bs, geom.R, geom.S, T)
         return CompositeFunction.apply(attn, signal, delay, geom, tab.dev)
+
+
+class GraphedInference:
+    """See ``AVRRender.graphed_inference``."""
+
+    def __init__(self, ren: AVRRender, bs: int, device=None, with_direction_tx: bool = False, with_ch_idx: bool = False):
+        if device is None:
+            device = next(ren.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.AVRLibraryError("graphed inference needs a CUDA device")
+        _lib.load()
+        self.ren, self.bs, self.device = ren, bs, device
+        n_rays = ren.n_azi * ren.n_ele + 2
+        self.rx = torch.zeros(bs, 3, device=device)
+        self.tx = torch.zeros(bs, 3, device=device)
+        self.dtx = torch.zeros(bs, 3, device=device) if with_direction_tx else None
+        if self.dtx is not None:
+            self.dtx[:, 0] = 1.0
+        self.ch = torch.zeros(bs, dtype=torch.long, device=device) if with_ch_idx else None
+        self.dirs = tables.direction_table(ren.n_azi, ren.n_ele, torch.zeros(ren.n_azi)).to(device)
+        self.dirs_host = torch.empty(n_rays, 3).pin_memory()
+        self.copied = torch.cuda.Event()
+        side = torch.cuda.Stream(device)                                   # warm-up off the capture: caches, allocator pools
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                ren._render_pass(self.rx, self.tx, self.dtx, self.ch, self.dirs)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = ren._render_pass(self.rx, self.tx, self.dtx, self.ch, self.dirs)
+
+    @torch.no_grad()
+    def __call__(self, rays_o, position_tx, direction_tx=None, ch_idx=None, azi_rand=None):
+        if rays_o.shape[0] != self.bs:
+            raise ValueError(f"this graph was captured for {self.bs} receivers per call")
+        self.rx.copy_(rays_o, non_blocking=True)
+        self.tx.copy_(position_tx, non_blocking=True)
+        if self.dtx is not None:
+            if direction_tx is None:
+                raise ValueError("this graph was captured with direction_tx")
+            self.dtx.copy_(direction_tx, non_blocking=True)
+        if self.ch is not None:
+            if ch_idx is None:
+                raise ValueError("this graph was captured with ch_idx")
+            self.ch.copy_(ch_idx, non_blocking=True)
+        self.copied.synchronize()                                          # the previous call's upload has left the pinned buffer
+        self.dirs_host.copy_(tables.direction_table(self.ren.n_azi, self.ren.n_ele, azi_rand))
+        self.dirs.copy_(self.dirs_host, non_blocking=True)
+        self.copied.record()
+        self.graph.replay()
+        return self.out

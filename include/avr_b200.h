@@ -187,6 +187,14 @@ enum {
 /* fp32 [rows, cols] (ld) <-> plane pair; transpose != 0 writes planes[c, r] = x[r, c]; relu != 0 clamps */
 AVR_API int avr_planes_split(const float* x, int64_t rows, int64_t cols, int64_t ld, void* planes, int64_t ldp,
                              int64_t plane_stride, int nplanes, int transpose, int relu, int device, void* stream);
+/* Several avr_planes_split calls in ONE launch (all weight matrices of a pass). */
+#define AVR_SPLIT_BATCH_MAX 32
+typedef struct avr_split_desc {
+    const float* x; int64_t rows, cols, ld;      /* fp32 source [rows, cols]                              */
+    void* planes; int64_t ldp, plane_stride;     /* destination plane set; out[c, r] when transpose != 0 */
+    int32_t kind, transpose;
+} avr_split_desc;
+AVR_API int avr_planes_split_batch(const avr_split_desc* descs, int32_t n, int device, void* stream);
 AVR_API int avr_planes_merge(const void* planes, int64_t rows, int64_t cols, int64_t ldp, int64_t plane_stride,
                              int nplanes, float* out, int64_t ld, int device, void* stream);
 /* C[M,N] = A[M,K] . B[N,K]^T   (A, B plane pairs with the reduction index contiguous; N % 8 == 0).

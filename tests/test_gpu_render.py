@@ -223,6 +223,43 @@ def test_no_grad_inference_and_optimizer_step(built_library):
     assert set(ren.state_dict()) == {"network_fn." + k for k in native.state_dict()}
 
 
+@pytest.mark.parametrize("name", ["simu", "raf_furnished"])
+def test_inference_paths_agree(built_library, name):
+    """torch.no_grad() skips every buffer only the backward pass reads (saved planes, ReLU bitmasks, bf16 copies) and
+    ``graphed_inference`` replays that forward as one CUDA graph: all three give the same spectrum, bit for bit."""
+    cfg = get_config(name)
+    cfg["render"]["n_azi"], cfg["render"]["n_ele"] = 8, 4
+    r = cfg["render"]
+    cx = avr_b200.AVRModel_complex if cfg["model_class"] != "AVRModel" else avr_b200.AVRModel
+    native = cx(cfg["model"]).to(DEV)
+    with torch.no_grad():
+        for m in native.modules():
+            if isinstance(m, avr_b200.Encoding):
+                m.params.normal_(0, 0.1)
+    ren = avr_b200.AVRRender(native, **r)
+    gen = torch.Generator().manual_seed(2)
+    complex_field = cfg["model_class"] != "AVRModel"
+    graphed = ren.graphed_inference(2, direction_tx=complex_field)
+    for trial in range(3):
+        rx = (torch.rand(2, 3, generator=gen) * 2 - 1).to(DEV)
+        tx = (torch.rand(2, 3, generator=gen) * 2 - 1).to(DEV)
+        dtx = torch.nn.functional.normalize(torch.randn(2, 3, generator=gen), dim=-1).to(DEV) if complex_field else None
+        azi = torch.rand(8, generator=gen)
+        o_train = ren(rx, tx, dtx, azi_rand=azi)
+        with torch.no_grad():
+            o_eval = ren(rx, tx, dtx, azi_rand=azi)
+        o_graph = graphed(rx, tx, dtx, azi_rand=azi).clone()
+        assert o_train.requires_grad and not o_eval.requires_grad
+        assert float(o_train.abs().max()) > 0 and bool(torch.isfinite(o_train).all())
+        assert torch.equal(o_train.detach(), o_eval) and torch.equal(o_graph, o_eval), trial
+    with torch.no_grad():                                               # the graph reads the CURRENT parameters
+        o, i = native._model_signal.shapes[-1]
+        native._model_signal.params[-o * i:] *= 0.5                     # the (linear) output layer
+        assert rel_l2(graphed(rx, tx, dtx, azi_rand=azi), 0.5 * o_eval) < 1e-5
+    with pytest.raises(ValueError):
+        graphed(rx[:1], tx[:1], dtx[:1] if dtx is not None else None)
+
+
 def test_full_size_simu_properties(built_library):
     """BASELINE config[1] shape (R=2050, S=64, T=1600): size-independent properties instead of the oracle."""
     cfg = get_config("simu")
