@@ -288,26 +288,43 @@ prefix_dot_kernel(const Geom geo, int width, PrefixWs ws, int tspan, const float
 }
 
 // d_W_out[t, c] (+)= sum_cells d_y[cell, t] * G(cell, t)[c]      (fixed order over the cells)
-__global__ void dwout_reduce_kernel(const Geom geo, int width, const float* __restrict__ d_y, PrefixWs ws, int tspan,
-                                    float* __restrict__ d_wout, long long ldw, int accumulate) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// block = (32 float4 columns of one t) x DW_GROUPS cell groups: every group sums its share of the cells (four times the
+// loads in flight of one thread walking all cells), the groups are combined through shared memory in a fixed order
+constexpr int DW_GROUPS = 4;
+__global__ void __launch_bounds__(32 * DW_GROUPS)
+dwout_reduce_kernel(const Geom geo, int width, const float* __restrict__ d_y, PrefixWs ws, int tspan,
+                    float* __restrict__ d_wout, long long ldw, int accumulate) {
+    __shared__ float4 part[DW_GROUPS][32];
     const int wq = width / 4;
-    if (q >= geo.T * wq) return;
-    const int t = q / wq, c = (q - t * wq) * 4;
+    const int q = blockIdx.x * 32 + threadIdx.x;
+    const bool ok = q < geo.T * wq;
+    const int t = ok ? q / wq : 0, c = ok ? (q - t * wq) * 4 : 0;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const int n = geo.bs * geo.S;
-    for (int i = 0; i < n; ++i) {
-        const int dmin = __ldg(ws.range + 2 * i), dmax = __ldg(ws.range + 2 * i + 1);
-        if (t < dmin) continue;
-        const float g = __ldg(d_y + (long long)i * geo.T + t);
-        const bool snap = t < dmax && dmax - dmin <= tspan;
-        const float* src = snap ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c : ws.gtot + (long long)i * width + c;
-        float4 a = *reinterpret_cast<const float4*>(src);
-        if (snap) {
-            const float4 o = *reinterpret_cast<const float4*>(ws.cum + ((long long)i * PW_SEG + owner_segment(ws.segfirst + i * PW_SEG, t)) * width + c);
-            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    const int per = (n + DW_GROUPS - 1) / DW_GROUPS;
+    const int i_beg = threadIdx.y * per, i_end = min(n, i_beg + per);
+    if (ok) {
+        for (int i = i_beg; i < i_end; ++i) {
+            const int dmin = __ldg(ws.range + 2 * i), dmax = __ldg(ws.range + 2 * i + 1);
+            if (t < dmin) continue;
+            const float g = __ldg(d_y + (long long)i * geo.T + t);
+            const bool snap = t < dmax && dmax - dmin <= tspan;
+            const float* src = snap ? ws.gp + ((long long)i * tspan + (t - dmin)) * width + c : ws.gtot + (long long)i * width + c;
+            float4 a = *reinterpret_cast<const float4*>(src);
+            if (snap) {
+                const float4 o = *reinterpret_cast<const float4*>(ws.cum + ((long long)i * PW_SEG + owner_segment(ws.segfirst + i * PW_SEG, t)) * width + c);
+                a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            }
+            v.x = fmaf(g, a.x, v.x); v.y = fmaf(g, a.y, v.y); v.z = fmaf(g, a.z, v.z); v.w = fmaf(g, a.w, v.w);
         }
-        v.x = fmaf(g, a.x, v.x); v.y = fmaf(g, a.y, v.y); v.z = fmaf(g, a.z, v.z); v.w = fmaf(g, a.w, v.w);
+    }
+    part[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.y != 0 || !ok) return;
+#pragma unroll
+    for (int k = 1; k < DW_GROUPS; ++k) {
+        const float4 o = part[k][threadIdx.x];
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
     float* dst = d_wout + (long long)t * ldw + c;
     if (accumulate) {
@@ -502,7 +519,7 @@ AVR_API int avr_collapse_bwd(const avr_render_geom* geom, const void* act_planes
     const PrefixWs ws = carve_prefix(const_cast<void*>(prefix_ws), cells, tspan, width);
     float* gs = (float*)suffix_ws;
     const int total = geo.T * (width / 4);
-    dwout_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(geo, width, d_y, ws, tspan, d_wout, ld_dw, accumulate);
+    dwout_reduce_kernel<<<(total + 31) / 32, dim3(32, DW_GROUPS), 0, st>>>(geo, width, d_y, ws, tspan, d_wout, ld_dw, accumulate);
     AVR_LAUNCH_CHECK();
     const size_t smem = (size_t)geo.T * sizeof(float);
     AVR_CUDA(cudaFuncSetAttribute(suffix_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

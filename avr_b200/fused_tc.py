@@ -166,9 +166,9 @@ class FusedRenderTC(torch.autograd.Function):
         # the 128-wide layers, ReLU bitmasks, the bf16 copies of the signal network's fp16-pair activations.
         train = any(ctx.needs_input_grad[8:])
         chain = (FUSE_SIGMA_CHAIN and guard is None and not any(k[0] in ("enc", "dec") for k in bias_of) and not plan["sig_relu_feat"] and feat_dim == 128
-                 and dec_net.in_pad == feat_dim and not plan.get("dec_tail") and enc_net.in_pad <= 128
+                 and dec_net.in_pad == feat_dim and not plan.get("dec_tail") and enc_net.in_pad <= 128 and enc_net.in_pad % 16 == 0
                  and all(o == 128 for (o, _) in enc_net.shapes) and all(o == 128 for (o, _) in dec_net.shapes[:-1])
-                 and dec_net.out_pad <= 128 and len(enc_net.shapes) + len(dec_net.shapes) <= _lib_chain_max())
+                 and dec_net.out_pad <= 64 and dec_net.out_pad % 16 == 0 and len(enc_net.shapes) + len(dec_net.shapes) <= _lib_chain_max())
         if chain:
             # ---- sigma encoder -> [relu] -> sigma decoder -> density head: one launch ----------------------------------
             acts_enc = [PlanePair.empty(n_rows if train else 0, 128, dev, kind=ops.PLANES_BF16x2) for _ in w_enc[:-1]]   # weight gradients read 16 bits
@@ -353,15 +353,18 @@ class FusedRenderTC(torch.autograd.Function):
         sig_in, dec_in = B["sig_in"], B["dec_in"]
         g, wt_sig, _ = hidden_backward(sig_net, "sig", g, B["acts_sig"], B["bits_sig"], sig_in, g_sig, wt_sig_all)
         grads[id(sig_net)] = g_sig
-        d_feat = PlanePair.empty(n_rows, feat_dim, dev)
         wt0 = wt_sig[0]                                                      # W0^T planes [in_pad, width]
-        if plan["sig_relu_feat"]:
-            ops.umma_nt(g, wt0.row_window(0, feat_dim), ops.UMMA_MASK, d_feat, mask=B["bits_feat"])
-        else:
-            ops.umma_nt(g, wt0.row_window(0, feat_dim), 0, d_feat)
         tail_w = sig_net.in_pad - feat_dim
-        d_tail = PlanePair.empty(n_rows, tail_w, dev)
-        ops.umma_nt(g, wt0.row_window(feat_dim, tail_w), 0, d_tail)
+        if plan["sig_relu_feat"]:
+            d_feat = PlanePair.empty(n_rows, feat_dim, dev)
+            ops.umma_nt(g, wt0.row_window(0, feat_dim), ops.UMMA_MASK, d_feat, mask=B["bits_feat"])
+            d_tail = PlanePair.empty(n_rows, tail_w, dev)
+            ops.umma_nt(g, wt0.row_window(feat_dim, tail_w), 0, d_tail)
+        else:
+            # d(signal-network input) in ONE product -- g is read once instead of twice; d_feat and d_tail are its column windows
+            d_sig_in = PlanePair.empty(n_rows, sig_net.in_pad, dev)
+            ops.umma_nt(g, wt0, 0, d_sig_in)
+            d_feat, d_tail = d_sig_in.window(0, feat_dim), d_sig_in.window(feat_dim, tail_w)
         B["acts_sig"] = None
         scatter_segments(plan["tail"], d_tail)
         d_tail = None

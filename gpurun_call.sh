@@ -1,27 +1,11 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_gpu_umma.py tests/test_gpu_render.py tests/test_gpu_kernels.py tests/test_gpu_chain.py -m gpu -q 2>&1 | tail -30 ) > gpurun_out/pytest_subset.log 2>&1
-timeout 300 python bench.py --steps 20 --no-other-configs --no-cpu-baseline > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err
-timeout 300 python bench.py --config meshrir --mode infer --bs 8 --steps 10 --no-other-configs --no-cpu-baseline > gpurun_out/bench_meshrir_infer.json 2> gpurun_out/bench_meshrir_infer.err
-timeout 300 python -c "
-import torch, time, avr_b200
-from avr_b200.configs import get_config
-cfg=get_config('simu'); dev='cuda:0'
-f=avr_b200.AVRModel(cfg['model']).to(dev); ren=avr_b200.AVRRender(f, **cfg['render'])
-rx=torch.rand(1,3,device=dev); tx=torch.rand(1,3,device=dev)
-def t(fn,n=50):
-    for _ in range(5): fn()
-    torch.cuda.synchronize(); t0=time.perf_counter()
-    for _ in range(n): fn()
-    torch.cuda.synchronize(); return (time.perf_counter()-t0)/n*1e3
-def eager():
-    with torch.no_grad(): return ren(rx,tx)
-g=ren.graphed_inference(1)
-print('simu bs=1 inference: eager %.3f ms, CUDA graph %.3f ms per receiver'%(t(eager), t(lambda: g(rx,tx))))
-g8=ren.graphed_inference(8); rx8=torch.rand(8,3,device=dev); tx8=torch.rand(8,3,device=dev)
-def eager8():
-    with torch.no_grad(): return ren(rx8,tx8)
-print('simu bs=8 inference: eager %.3f ms, CUDA graph %.3f ms per call'%(t(eager8,20), t(lambda: g8(rx8,tx8),20)))
-" > gpurun_out/graph_latency.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1
-cat gpurun_out/graph_latency.txt gpurun_out/smoke.txt; tail -5 gpurun_out/pytest_subset.log
+( time python -m pytest tests -m gpu -q -s --durations=10 ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+AVR_BENCH_DETAIL=1 python bench.py --steps 5 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/bench_detail.json 2> gpurun_out/bench_detail.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2b_launches.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:umma_gemm_kernel -s 57 -c 19 --csv --log-file gpurun_out/r2b_umma_dram_traffic.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_traffic.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:prefix_walk -c 1 -s 3 -o gpurun_out/prefix_r2b python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_prefix.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log

@@ -135,7 +135,7 @@ def test_real_fields_all_seeds_reported(built_library, name, n_azi, n_ele):
     """The real fields on a reduced ray grid, EVERY candidate seed.  The oracle's own spread (tests/helpers.py::
     oracle_conditioning: fp32 evaluations in other summation orders against the float64-dense evaluation, and the
     gradients with every ReLU decision inside fp32 rounding noise of zero flipped) says how well fp32 arithmetic
-    determines the answer on that draw: where it is <= 2e-5 the bar is 1e-4; elsewhere (a decision within 1e-6 of zero at
+    determines the answer on that draw: where it is <= 5e-5 the bar is 1e-4; elsewhere (a decision within 1e-6 of zero at
     a point that carries a visible share of the gradient) the bar is max(1e-4, 2 x spread).  Per seed: spread, tc and
     simt distances -- printed and recorded; no seed is skipped."""
     cfg = get_config(name)
@@ -148,7 +148,7 @@ def test_real_fields_all_seeds_reported(built_library, name, n_azi, n_ele):
         ref_net = field_ref.trained_like_(cls(cfg["model"], seed=seed), seed=seed + 1)
         n_out, n_g = oracle_conditioning(ref_net, cfg["render"], rx, tx, G, dtx=dtx, azi_rand=azi)
         noise = max([n_out] + list(n_g.values()))
-        well = noise <= 2e-5
+        well = 2 * noise <= TOL                                   # <=> this seed is held to the plain 1e-4 bar below
         rejected += 0 if well else 1
         ref_out = render_ref.RenderRef(ref_net, **cfg["render"])(rx, tx, dtx, azi_rand=azi)
         (ref_out * G).sum().backward()
