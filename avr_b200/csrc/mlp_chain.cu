@@ -71,7 +71,6 @@ struct ChainMaps {
     CUtensorMap save[CH_MAX_LAYERS];
 };
 
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // Schedule of one 128-row tile (steady state).  Accumulators alternate between two TMEM sets from layer to layer and
 // the epilogue hands the activation tile over one 64-column k-block at a time, so the next layer's first k-block runs on
@@ -145,7 +144,12 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer (also issues the bulk stores of the saved planes)
-        if (lane == 0) {
+        // The whole warp walks the schedule in lock step; ONE elected lane executes the tcgen05 / bulk-store instructions.
+        // Descriptors and addresses are then warp-uniform (uniform registers, UTCHMMAs back to back); inside an
+        // `if (lane == 0)` branch every MMA was wrapped in an ELECT / R2UR.BROADCAST loop of ~15 dependent instructions --
+        // 89-120 clk per 128 x 128 x 16 MMA against the 64 clk it occupies the tensor pipe.
+        {
+            const bool elected = elect_one() != 0u;
             int stage = 0;
             uint32_t wphase = 0, x0phase = 0, ar_phase[2] = {0u, 0u}, gl = 0;
             int tn = 0; (void)tn;
@@ -158,7 +162,8 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
 #ifdef AVR_EXPERIMENTS
                 if (p.debug & 2) planes = 0;
 #endif
-                if (planes) { tma_store_3d(&maps.save[l], a_base + h * CH_A_KB, h * UBK, m0, 0); tma_store_commit(); }
+                if (planes && elected) { tma_store_3d(&maps.save[l], a_base + h * CH_A_KB, h * UBK, m0, 0); tma_store_commit(); }
+                __syncwarp();
             };
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int m0 = tile * UM;
@@ -187,6 +192,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                         const uint64_t b0 = smem_desc(sb, 16, 1024), b1 = smem_desc(sb + b_plane, 16, 1024),
                                        b2 = smem_desc(sb + 2 * b_plane, 16, 1024);
                         uint32_t acc = kb == 0 ? 0u : 1u;
+                        if (elected) {
 #pragma unroll
                         for (int j = 0; j < UBK / 16; ++j) {
                             if (j >= k_steps) break;
@@ -208,8 +214,9 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                             }
                             acc = 1u;
                         }
+                        }
                         CH_TRACE(0, tn);
-                        if (last_kb) {
+                        if (last_kb && elected) {
                             // The accumulator is final -> the epilogue may rewrite the tile.  Before that is announced the
                             // bulk stores that read it (issued when this layer started on each k-block) must be through.
                             // (Issuing the last k-block as two 64-column halves with a commit each was measured slower: a
@@ -218,7 +225,8 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                             umma_commit(bar_dfull);
                             umma_commit(bar_dfull + 8);
                         }
-                        umma_commit(bar_wempty + 8 * stage);
+                        if (elected) umma_commit(bar_wempty + 8 * stage);
+                        __syncwarp();
                         if (++stage == 2) { stage = 0; wphase ^= 1; }
                     }
                 }
@@ -226,10 +234,13 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                 // saves, and release the tile for the next load once the MMAs have retired and the stores have read it
                 take_half(p.n_layers - 1, 0, m0);
                 take_half(p.n_layers - 1, 1, m0);
-                tma_store_wait_read();
-                umma_commit(bar_afree);
+                if (elected) {
+                    tma_store_wait_read();
+                    umma_commit(bar_afree);
+                }
+                __syncwarp();
             }
-            tma_store_wait_all();                                              // shared memory must outlive the bulk stores
+            if (elected) tma_store_wait_all();                                 // shared memory must outlive the bulk stores
         }
     } else {
         // ===================================== epilogue: warps 2..9 -> TMEM lane groups 2,3,0,1; two warps per group,

@@ -26,6 +26,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -56,6 +57,8 @@ struct UmmaParams {
     int mode;               // product schedule, see the MMA issuer
     float small_scale;      // factor of the small-products accumulator in the epilogue (2^-11 with an fp16 operand)
     int b_resident, nkb;    // K-major, single column tile, short K: the whole B operand stays in shared memory
+    int cluster;            // 2: CTA pairs (thread-block cluster 2x1x1, tcgen05 cta_group::2) multiply two adjacent row tiles
+                            // by one column tile as ONE 256-row MMA; each CTA stages only half of the B tile
     int flags;
     __nv_bfloat16* c; long long ldc, c_plane;          // plane-pair output
     __nv_bfloat16* c2; long long ldc2, c2_plane;       // second (ReLU'd) plane-pair output
@@ -66,7 +69,9 @@ struct UmmaParams {
     int geo_R, geo_S;                                  // row = (b*R + r)*S + s
     float* c32; long long ldc32;                       // fp32 output / split-K partials
     int epi_split;                                     // 1: warps 2..5 drain every chunk; 2: warps 6..9 take the odd chunks
-    uint32_t epi_warp_bytes;                           // staging bytes per epilogue warp (nc planes x 2 KB)
+    uint32_t epi_warp_bytes;                           // staging bytes per epilogue warp and buffer (nc planes x 2 KB)
+    int epi_bufs;                                      // staging buffers per epilogue warp: 2 = a chunk is converted and staged
+                                                       // while the bulk store of the previous one still reads its buffer
     // near-zero guard (forward layers): elements with |out| < near_tau * (mean |out| of their row chunk) are listed
     // and re-evaluated by umma_fixup_kernel with fp32 FMAs, so that sign decisions (ReLU, |leaky_relu|) taken on the
     // output are as good as an fp32 GEMM's.  The tensor core truncates once per MMA: ~6e-9*K of the row scale.
@@ -117,14 +122,22 @@ __device__ __forceinline__ void near_zero_guard(const UmmaParams& p, const float
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <bool MN_MAJOR>
+template <bool MN_MAJOR, bool PAIR>
 __global__ void __launch_bounds__(UTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                 const __grid_constant__ CUtensorMap tmBh, const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bn_rows = MN_MAJOR ? ((p.BN + 63) / 64) * 64 : p.BN;     // B rows (K-major) / MN extent (MN-major) in smem
+    // (a separate instantiation: a kernel that contains cta_group::2 instructions cannot be launched without a cluster)
+    constexpr bool pair = PAIR;
+    static_assert(!(PAIR && MN_MAJOR), "pair mode is K-major only");
+    uint32_t crank = 0u;
+    if constexpr (PAIR) crank = cluster_ctarank();
+    const bool leader = crank == 0u;
+    // B rows (K-major; pair mode: this CTA's half of the column tile) / MN extent (MN-major) in smem
+    const int bn_rows = MN_MAJOR ? ((p.BN + 63) / 64) * 64 : (pair ? p.BN >> 1 : p.BN);
     const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
     const uint32_t a_tile_bytes = (uint32_t)p.na * A_PLANE_BYTES;
     const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)p.nb * (uint32_t)bn_rows * 128u : (uint32_t)p.nb * b_plane_bytes;
@@ -143,44 +156,63 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t epi_base = (smem_base + (uint32_t)p.stages * stage_bytes + 256u + 1023u) & ~1023u;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128 * p.epi_split); }
+        // pair mode: the leader's "full" barrier counts both producers (its own arrive + expect_tx of both CTAs' bytes, the
+        // peer's remote arrive) and its "accumulator drained" barrier both CTAs' epilogue threads; "stage free" and
+        // "accumulator final" are announced to each CTA's own barrier by the leader's multicast commits
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, pair ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (pair ? 256 : 128) * p.epi_split); }
         mbar_init(bar_bres, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (pair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (pair) cluster_sync_all(); else __syncthreads();      // the peer's barriers must exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+    // work list: tiles (row tile, column tile, K slice) strided over the CTAs, or -- pair mode -- units of two adjacent
+    // row tiles x one column tile strided over the clusters, rank r of the pair taking row tile 2 u + r
+    const int n_tiles = pair ? ((p.tiles_m + 1) / 2) * p.tiles_n : p.tiles_m * p.tiles_n * p.k_splits;
+    const int t_begin = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_stride = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto row_tile = [&](int mn) { const int mt = mn / p.tiles_n; return pair ? 2 * mt + (int)crank : mt; };
     if (warp == 0) {
         // ===================================== TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            if (bres && (int)blockIdx.x < n_tiles) {                          // B is the same for every tile of this CTA
+            if (bres && t_begin < n_tiles) {                                  // B is the same for every tile of this CTA
                 mbar_expect_tx(bar_bres, bres_bytes);
                 for (int kb = 0; kb < p.nkb; ++kb) tma_load_3d(bres_base + kb * b_tile_bytes, &tmB, bar_bres, kb * UBK, 0, 0);
             }
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = t_begin; tile < n_tiles; tile += t_stride) {
                 const int split = tile % p.k_splits;
                 const int mn = tile / p.k_splits;
-                const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
+                const int m0 = row_tile(mn) * UM, n0 = (mn % p.tiles_n) * p.BN;
                 // split-K slices are interleaved (k-block j of slice s is block j*k_splits + s) so that the CTAs
                 // sharing operand columns walk the same rows at the same time and the re-reads hit L2
                 for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_tile_bytes;
-                    mbar_expect_tx(full, stage_bytes);
-                    if (!MN_MAJOR) {
+                    if constexpr (!pair) mbar_expect_tx(full, stage_bytes);
+                    else if (leader) mbar_expect_tx(full, 2u * stage_bytes);
+                    else mbar_arrive_cluster(full, 0u);
+                    if constexpr (pair) {
+                        // my row tile and my half of the rows of the column tile; the bytes count on the leader's barrier
+                        tma_load_3d_2sm(sa, &tmA, full, k0, m0, 0);
+                        tma_load_3d_2sm(sb, &tmBh, full, k0, n0 + (int)crank * bn_rows, 0);
+                    } else if (!MN_MAJOR) {
                         tma_load_3d(sa, &tmA, full, k0, m0, 0);
                         if (!bres) tma_load_3d(sb, &tmB, full, k0, n0, 0);
                     } else {
@@ -194,15 +226,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer
-        if (lane == 0) {
+        // (pair mode: the leader's thread issues for both CTAs -- M = 256, each CTA's tensor core takes its 128 rows of A and
+        // its half of B from its own shared memory at the same offsets, and accumulates into its own tensor memory)
+        // The whole warp runs this loop in lock step and ONE elected lane executes the tcgen05 instructions: everything an
+        // MMA needs (descriptors, accumulator addresses, flags) is then warp-uniform and lives in uniform registers.  Inside
+        // an `if (lane == 0)` branch the compiler cannot prove that and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST /
+        // BRA.U.ANY loop (~15 dependent instructions per MMA, 90-140 clk): longer than the 64 clk a 128-column MMA occupies
+        // the tensor pipe, so 128-column tiles were bound by the issuing thread.
+        auto issue_tiles = [&](auto cta2_tag) {
+            constexpr bool CTA2 = decltype(cta2_tag)::value;
+            const bool elected = elect_one() != 0u;
             // instruction descriptor: fp32 accumulate, A / B element formats (0 = f16, 1 = bf16), N, M
             uint32_t idesc = (1u << 4) | ((p.fa ? 0u : 1u) << 7) | ((p.fb ? 0u : 1u) << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                             ((uint32_t)(UM >> 4) << 24);
+                             ((uint32_t)((CTA2 ? 2 * UM : UM) >> 4) << 24);
             if (MN_MAJOR) idesc |= (1u << 15) | (1u << 16);
             int stage = 0, iter = 0;
             uint32_t phase = 0;
-            if (bres && (int)blockIdx.x < n_tiles) mbar_wait(bar_bres, 0);
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+            if (bres && t_begin < n_tiles) mbar_wait(bar_bres, 0);
+            for (int tile = t_begin; tile < n_tiles; tile += t_stride, ++iter) {
                 const int split = tile % p.k_splits;
                 const int acc = p.acc_bufs == 2 ? (iter & 1) : 0;
                 const uint32_t acc_phase = (uint32_t)(p.acc_bufs == 2 ? (iter >> 1) : iter) & 1u;
@@ -239,17 +280,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // Product schedules, smallest terms first.  With fp16 pairs the products that involve a lo' plane carry
                     // a factor 2^11 and MUST go to the small accumulator (scaled back in the epilogue).  A and B share one
                     // element format: tcgen05.mma raises an illegal-instruction fault on a bf16 x f16 mix.
-                    if (p.mode == 1) {          // bf16x3 . bf16x3: six products (fp32-grade pre-activations / ill-conditioned sums)
+                    if (!elected) {
+                    } else if (p.mode == 1) {   // bf16x3 . bf16x3: six products (fp32-grade pre-activations / ill-conditioned sums)
 #pragma unroll
                         for (int j = 0; j < UBK / 16; ++j) {
                             if (j >= k_steps) break;
                             const uint64_t o = step * j;
-                            umma_bf16(d_small, a2 + o, b0 + o, idesc, acc_small | (acc_main & shared_acc));
-                            umma_bf16(d_small, a0 + o, b2 + o, idesc, 1u);
-                            umma_bf16(d_small, a1 + o, b1 + o, idesc, 1u);
-                            umma_bf16(d_small, a1 + o, b0 + o, idesc, 1u);
-                            umma_bf16(d_small, a0 + o, b1 + o, idesc, 1u);
-                            umma_bf16(d_main, a0 + o, b0 + o, idesc, p.dual_acc ? acc_main : 1u);
+                            umma_issue<CTA2>(d_small, a2 + o, b0 + o, idesc, acc_small | (acc_main & shared_acc));
+                            umma_issue<CTA2>(d_small, a0 + o, b2 + o, idesc, 1u);
+                            umma_issue<CTA2>(d_small, a1 + o, b1 + o, idesc, 1u);
+                            umma_issue<CTA2>(d_small, a1 + o, b0 + o, idesc, 1u);
+                            umma_issue<CTA2>(d_small, a0 + o, b1 + o, idesc, 1u);
+                            umma_issue<CTA2>(d_main, a0 + o, b0 + o, idesc, p.dual_acc ? acc_main : 1u);
                             acc_small = acc_main = 1u;
                         }
                     } else {                    // bf16x2 . bf16x2 (16 bits; gradients) and f16x2 . f16x2 (24 bits): three products
@@ -257,18 +299,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < UBK / 16; ++j) {
                             if (j >= k_steps) break;
                             const uint64_t o = step * j;
-                            umma_bf16(d_small, a1 + o, b0 + o, idesc, acc_small | (acc_main & shared_acc));
-                            umma_bf16(d_small, a0 + o, b1 + o, idesc, 1u);
-                            umma_bf16(d_main, a0 + o, b0 + o, idesc, p.dual_acc ? acc_main : 1u);
+                            umma_issue<CTA2>(d_small, a1 + o, b0 + o, idesc, acc_small | (acc_main & shared_acc));
+                            umma_issue<CTA2>(d_small, a0 + o, b1 + o, idesc, 1u);
+                            umma_issue<CTA2>(d_main, a0 + o, b0 + o, idesc, p.dual_acc ? acc_main : 1u);
                             acc_small = acc_main = 1u;
                         }
                     }
-                    umma_commit(bar_empty + 8 * stage);                          // frees the stage when the MMAs retire
+                    acc_small = acc_main = 1u;                                   // (all lanes: the flags stay warp-uniform)
+                    if (elected) {
+                        if constexpr (CTA2) umma_commit_2sm(bar_empty + 8 * stage);      // frees the stage (in both CTAs) when the MMAs retire
+                        else umma_commit(bar_empty + 8 * stage);
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * acc);                                // accumulator complete
+                if (elected) {
+                    if constexpr (CTA2) umma_commit_2sm(bar_tfull + 8 * acc);            // accumulator complete (both CTAs' epilogues)
+                    else umma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
             }
-        }
+        };
+        if constexpr (!pair) issue_tiles(std::false_type{});
+        else if (leader) issue_tiles(std::true_type{});
     } else if (((warp - 2) >> 2) < p.epi_split) {
         // ===================================== epilogue: warps 2..5 (and 6..9) -> TMEM lane groups 2,3,0,1.
         // One chunk of a tile is a latency chain (tcgen05.ld -> convert -> st.shared -> proxy fence -> bulk store ->
@@ -277,10 +330,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int lane_grp = warp & 3;
         const int half = (warp - 2) >> 2;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = t_begin; tile < n_tiles; tile += t_stride, ++iter) {
             const int split = tile % p.k_splits;
             const int mn = tile / p.k_splits;
-            const int m0 = (mn / p.tiles_n) * UM, n0 = (mn % p.tiles_n) * p.BN;
+            const int m0 = row_tile(mn) * UM, n0 = (mn % p.tiles_n) * p.BN;
             const int acc = p.acc_bufs == 2 ? (iter & 1) : 0;
             const uint32_t acc_phase = (uint32_t)(p.acc_bufs == 2 ? (iter >> 1) : iter) & 1u;
             const long long row = m0 + lane_grp * 32 + lane;
@@ -291,7 +344,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             //   bt*[j]  value of column 32j + lane of the warp's shared bias row           (UF_BIAS, uniform case)
             uint32_t mw[8];
             int ray_row = 0, rcv_row = 0, ray_uniform = 0, rcv_uniform = 0;
-            const uint32_t bias_s = epi_base + 4u * (uint32_t)p.epi_split * p.epi_warp_bytes + (uint32_t)lane_grp * 1024u;   // 256 floats (UF_BIAS implies epi_split = 1)
+            const uint32_t bias_s = epi_base + 4u * (uint32_t)(p.epi_split * p.epi_bufs) * p.epi_warp_bytes + (uint32_t)lane_grp * 1024u;   // 256 floats (UF_BIAS implies epi_split = 1)
             if (!MN_MAJOR && !(p.flags & UF_OUT_F32)) {
                 if (p.flags & UF_BIAS) {
                     const long long rrow = row_ok ? row : (long long)p.M - 1;
@@ -355,7 +408,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
                 // plane outputs: registers -> swizzled smem staging -> TMA bulk tensor store (full lines, rows and
                 // columns outside the output window are clipped by the tensor map)
-                const uint32_t stage = epi_base + (uint32_t)(4 * half + lane_grp) * p.epi_warp_bytes;
+                const uint32_t stage0 = epi_base + (uint32_t)((4 * half + lane_grp) * p.epi_bufs) * p.epi_warp_bytes;
+                uint32_t sbuf = 0;
                 for (int c0 = EPI_COLS * half; c0 < p.BN && n0 + c0 < p.N; c0 += EPI_COLS * p.epi_split) {
                     float v[32];
                     {
@@ -453,8 +507,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int kind_o = o == 0 ? p.kc : p.kc2;
                         const int n_o = planes_count(kind_o);
                         pack_planes32(v, (o == 1 && (p.flags & UF_DUAL_RELU)) || (p.flags & UF_RELU), kind_o, ph, pm, pl);
-                        if (lane == 0 && !UF_DBG(p.flags, UF_DEBUG_NOWAIT)) tma_store_wait_read();   // staging tiles free again?
+                        // staging buffer free again?  Bulk-store groups complete in order: with two buffers, at most ONE
+                        // group still in flight means that it is the store of the other buffer
+                        if (lane == 0 && !UF_DBG(p.flags, UF_DEBUG_NOWAIT)) { if (p.epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
                         __syncwarp();
+                        const uint32_t stage = stage0 + sbuf * p.epi_warp_bytes;
+                        sbuf ^= (uint32_t)(p.epi_bufs - 1);
                         if (!UF_DBG(p.flags, UF_DEBUG_NOSTAGE)) stage_packed32(stage, lane, n_o, ph, pm, pl);
                         if (!UF_DBG(p.flags, UF_DEBUG_NOFENCE)) fence_async_smem();
                         __syncwarp();
@@ -468,15 +526,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
+            if constexpr (pair) mbar_arrive_cluster(bar_tempty + 8 * acc, 0u);             // the leader's MMA thread waits for both CTAs
+            else mbar_arrive(bar_tempty + 8 * acc);
         }
         if (lane == 0) tma_store_wait_all();                                   // smem must outlive the bulk stores
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (pair) cluster_sync_all(); else __syncthreads();      // neither CTA of a pair leaves while the other may still signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -616,14 +676,14 @@ static EncodeTiledFn encode_fn() {
 
 // plane-pair tensor [2][rows][ld] of bf16, logical width `cols`; box = (64 cols, box_rows, 2 planes), 128B swizzle
 static int encode_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
-                      int box_rows, int nplanes, bool store_map) {
+                      int box_rows, int nplanes, bool store_map, int box_planes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(AVR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld * 2) % 16 || (plane * 2) % 16)
         return fail(AVR_ERR_INVALID, "plane tensors need 16-byte aligned base, row pitch and plane pitch");
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nplanes};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)nplanes};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     if (store_map) { box[0] = EPI_COLS; box[1] = 32; box[2] = 1; }          // epilogue staging tile: 32 rows x 64 B
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -639,10 +699,10 @@ static int encode_map(CUtensorMap* map, const void* base, long long rows, long l
 // distinct operand.  Guarded by a mutex (concurrent callers: nn.DataParallel threads, autograd's device threads);
 // bounded: the cache is dropped when it reaches 4096 entries.
 struct MapKey {
-    const void* base; long long rows, cols, ld, plane; int box_rows, nplanes, store;
+    const void* base; long long rows, cols, ld, plane; int box_rows, nplanes, store, box_planes;
     bool operator==(const MapKey& o) const {
         return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && plane == o.plane && box_rows == o.box_rows &&
-               nplanes == o.nplanes && store == o.store;
+               nplanes == o.nplanes && store == o.store && box_planes == o.box_planes;
     }
 };
 struct MapKeyHash {
@@ -650,21 +710,22 @@ struct MapKeyHash {
         uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
         auto mix = [&h](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
         mix((uint64_t)k.rows); mix((uint64_t)k.cols); mix((uint64_t)k.ld); mix((uint64_t)k.plane);
-        mix(((uint64_t)k.box_rows << 8) | ((uint64_t)k.nplanes << 1) | (uint64_t)k.store);
+        mix(((uint64_t)k.box_rows << 12) | ((uint64_t)k.box_planes << 8) | ((uint64_t)k.nplanes << 1) | (uint64_t)k.store);
         return (size_t)h;
     }
 };
 int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long plane,
-             int box_rows, int nplanes, bool store_map) {
+             int box_rows, int nplanes, bool store_map, int box_planes) {
+    if (box_planes <= 0) box_planes = nplanes;
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{base, rows, cols, ld, plane, box_rows, nplanes, store_map ? 1 : 0};
+    const MapKey key{base, rows, cols, ld, plane, box_rows, nplanes, store_map ? 1 : 0, box_planes};
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
         if (it != cache.end()) { *map = it->second; return AVR_OK; }
     }
-    if (int rc = encode_map(map, base, rows, cols, ld, plane, box_rows, nplanes, store_map)) return rc;
+    if (int rc = encode_map(map, base, rows, cols, ld, plane, box_rows, nplanes, store_map, box_planes)) return rc;
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() >= 4096) cache.clear();
     cache.emplace(key, *map);
@@ -672,10 +733,10 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device) state: raised to the 227 KB opt-in limit once
-template <bool MN_MAJOR>
+template <bool MN_MAJOR, bool PAIR>
 static int allow_max_smem(int device) {
     static std::atomic<uint64_t> done{0};                        // one flag word per kernel instantiation
-    auto kernel = umma_gemm_kernel<MN_MAJOR>;
+    auto kernel = umma_gemm_kernel<MN_MAJOR, PAIR>;
     const uint64_t bit = 1ull << (device & 63);
     if (done.load(std::memory_order_acquire) & bit) return AVR_OK;
     AVR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -701,6 +762,43 @@ static int tmem_cols_for(int bn, int dual = 0, int bufs = 2) {
     int need = (dual ? 2 : 1) * bufs * bn, c = 32;
     while (c < need) c <<= 1;
     return c;
+}
+
+// How many 2-CTA clusters of the K-major kernel can be resident at once (one CTA per SM; a GPC with an odd number of
+// free SMs leaves one idle).  Asked once per (device, dynamic shared memory size).
+static int max_resident_pairs(int device) {
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> cache;
+    const size_t smem = 232448;
+    const uint64_t key = (uint64_t)device;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * 148u);
+    cfg.blockDim = dim3(UTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (allow_max_smem<false, true>(device) != AVR_OK) return 0;
+    if (cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<false, true>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    std::lock_guard<std::mutex> lock(mu);
+    cache[key] = n;
+    return n;
+}
+
+// which launches run as CTA pairs: every wide K-major product over many row tiles.  Measured on the 524800 x 512 x 512
+// layers of the simu signal network (profiles/r2/pair_probe.jsonl): fp16 pairs 0.82 -> 0.66 ms, with the second bf16 copy
+// of the output 1.16 -> 0.80 ms, bf16 triples at K = 208 0.93 -> 0.83 ms, masked bf16-pair backward products 0.66 -> 0.60 ms.
+static bool pair_mode_wanted(int a_f16, int a_nplanes) {
+    (void)a_f16; (void)a_nplanes;
+    if (const char* e = AVR_EXP_ENV("AVR_UMMA_CLUSTER")) return atoi(e) != 0;
+    return true;
 }
 
 int num_sms(int device) {
@@ -806,10 +904,25 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.small_scale = a_f16 ? F16_LO_INV : 1.0f;
     p.BN = pick_bn(N, (a_nplanes == 3 || a_f16) ? 128 : 256);                // two accumulators per tile: 4 * BN <= 512
     p.acc_bufs = 2;
-    // fp16 pairs, wide layers: three products make a 128 x 128 tile L2-feed-bound (512 KB of operands per 10 k clk of
-    // MMAs); a 128 x 256 tile moves 25 % fewer bytes per flop.  Its two accumulators fill TMEM, so tiles are not
-    // double-buffered there.
-    if (a_f16 && N % 256 == 0 && K >= 256 && !(flags & UF_BIAS) && !AVR_EXP_ENV("AVR_UMMA_F16_BN128")) { p.BN = 256; p.acc_bufs = 1; }
+    // The 24-bit forward modes keep two accumulators per tile, so a double-buffered tile is at most 128 columns wide --
+    // and a 128 x 128 x 16 MMA reads 8 KB of operands from shared memory in the ~64 clk it occupies the tensor pipe: the
+    // main loop is bound by the shared-memory operand bandwidth (128 B/clk), not by the pipe or by L2 (measured: the
+    // 524800 x 512 x 512 fp16-pair layer WITHOUT epilogue takes 0.80-0.92 ms in 128-column tiles against 0.57 ms for the same
+    // number of 256-column MMAs; sharing the B tile between two CTAs by TMA multicast, which cuts the L2 traffic by a
+    // quarter, changes nothing).  CTA pairs (cta_group::2) multiply two adjacent row tiles by one column tile as ONE
+    // 256-row MMA: each SM reads its 128 rows of A and only HALF of the B tile (6 KB per MMA), the pipe is the bound
+    // again, and tiles stay double-buffered in tensor memory.
+    if (int rc = allow_max_smem<false, false>(device)) return rc;
+    p.cluster = 1;
+    int pairs = 0;
+    if (!splitk_workspace && !(flags & UF_OUT_F32) && N > p.BN && p.BN % 32 == 0 && M >= 2ll * UM * num_sms(device) &&
+        pair_mode_wanted(a_f16, a_nplanes)) {
+        pairs = max_resident_pairs(device);
+        if (pairs > 0) p.cluster = 2;
+    }
+    // Without pairs (no cluster launch possible): fp16 pairs in 128 x 256 tiles, whose two accumulators fill tensor memory
+    // (no overlap of a tile's epilogue with the next tile's MMAs), but whose MMAs are not operand-bound.
+    if (p.cluster == 1 && a_f16 && N % 256 == 0 && K >= 256 && !(flags & UF_BIAS) && !AVR_EXP_ENV("AVR_UMMA_F16_BN128")) { p.BN = 256; p.acc_bufs = 1; }
     p.tiles_m = (int)ceil_div(M, UM); p.tiles_n = (int)ceil_div(N, p.BN);
     p.k_splits = 1; p.k_per_split = (int)(ceil_div(K, UBK) * UBK);
     // long reductions into an fp32 output (the DFT and its adjoint, K = T or 2F): the accumulator is truncated once per
@@ -844,7 +957,8 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.near_list = (uint2*)near_list; p.near_cap = (uint32_t)near_cap; p.near_count = near_count; p.near_tau = near_tau;
     p.a_raw = (const __nv_bfloat16*)a_planes; p.lda = lda; p.a_plane = a_plane;
     p.b_raw = (const __nv_bfloat16*)b_planes; p.ldb = ldb; p.b_plane = b_plane;
-    const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES, b_tile = (uint32_t)p.nb * (uint32_t)p.BN * 128u;
+    const uint32_t a_tile = (uint32_t)p.na * A_PLANE_BYTES;
+    const uint32_t b_tile = (uint32_t)p.nb * (uint32_t)(p.cluster == 2 ? p.BN / 2 : p.BN) * 128u;    // pair mode: this CTA's half
     p.nkb = (int)ceil_div(K, UBK);
     const int nc2 = planes_count(c2_nplanes);
     p.epi_warp_bytes = (flags & UF_OUT_F32) ? 0u : (uint32_t)(p.nc > nc2 ? p.nc : nc2) * EPI_PLANE_BYTES;
@@ -852,18 +966,23 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     uint32_t epi_bytes = 0, bres_total = 0, stage_bytes = 0;
     // two epilogue warps per lane group when their staging tiles fit next to a two-stage pipeline (two-plane outputs,
     // fp32 outputs); the per-receiver bias rows are staged per lane group, so that mode keeps one warp per group
-    for (p.epi_split = (flags & UF_BIAS) ? 1 : 2; p.epi_split >= 1; --p.epi_split) {
+    // ... and two staging buffers per warp when three pipeline stages still fit next to them
+    const int cand[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+    const bool one_buf = AVR_EXP_ENV("AVR_UMMA_EPI_BUFS") && atoi(AVR_EXP_ENV("AVR_UMMA_EPI_BUFS")) == 1;
+    for (int ci = (flags & UF_BIAS) ? 2 : 0; ci < 4; ++ci) {
+        p.epi_split = cand[ci][0]; p.epi_bufs = cand[ci][1];
+        if (one_buf && p.epi_bufs == 2) continue;
         // 227 KB per CTA = alignment slack (1 KB) + operands + barrier block padded to 1 KB + staging (+ bias rows)
-        epi_bytes = 4u * (uint32_t)p.epi_split * p.epi_warp_bytes + bias_bytes;
+        epi_bytes = 4u * (uint32_t)(p.epi_split * p.epi_bufs) * p.epi_warp_bytes + bias_bytes;
         const uint32_t budget = 232448u - 2048u - epi_bytes;
-        p.b_resident = (p.tiles_n == 1 && p.tiles_m > 1 && (uint64_t)p.nkb * b_tile + 2ull * a_tile <= budget) ? 1 : 0;
+        p.b_resident = (p.cluster == 1 && p.tiles_n == 1 && p.tiles_m > 1 && (uint64_t)p.nkb * b_tile + 2ull * a_tile <= budget) ? 1 : 0;
         bres_total = p.b_resident ? (uint32_t)p.nkb * b_tile : 0u;
         stage_bytes = p.b_resident ? a_tile : a_tile + b_tile;
         p.stages = (int)((budget - bres_total) / stage_bytes);
         if (p.stages > 6) p.stages = 6;
-        if (p.stages >= 2) break;
+        if (p.stages >= (p.epi_bufs == 2 ? 3 : 2)) break;
     }
-    if (p.epi_split < 1 || p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
+    if (p.stages < 2) return fail(AVR_ERR_UNSUPPORTED, "tile does not fit two pipeline stages");
     if (const char* e = AVR_EXP_ENV("AVR_UMMA_EPI_SPLIT")) {                   // A/B experiments: force one warp per lane group
         if (atoi(e) == 1 && p.epi_split == 2) p.epi_split = 1;
     }
@@ -878,10 +997,26 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
         if (dual)
             if (int rc = make_map(&tc2, c2_planes, M, N, ldc2, c2_plane, 32, nc2, true)) return rc;
     }
-    if (int rc = allow_max_smem<false>(device)) return rc;
-    const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
-    const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
-    umma_gemm_kernel<false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, tc, tc2, p);
+    CUtensorMap tbh = tb;
+    if (p.cluster == 2) {
+        if (int rc = make_map(&tbh, b_planes, N, K, ldb, b_plane, p.BN / 2, p.nb)) return rc;    // this CTA's half of a column tile
+
+        const int units = ((p.tiles_m + 1) / 2) * p.tiles_n;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2u * (unsigned)(units < pairs ? units : pairs));
+        cfg.blockDim = dim3(UTHREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        AVR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<false, true>, ta, tb, tc, tc2, tbh, p));
+    } else {
+        const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
+        const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
+        umma_gemm_kernel<false, false><<<grid, UTHREADS, smem, (cudaStream_t)stream>>>(ta, tb, tc, tc2, tbh, p);
+    }
     AVR_LAUNCH_CHECK();
     if (p.k_splits > 1) {
         umma_splitk_reduce_kernel<<<(unsigned)ceil_div(M * (N / 4) * 32, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -946,7 +1081,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.dual_acc = (b_f16 || (nplanes == 3 && 4 * p.BN <= 512 && !AVR_EXP_ENV("AVR_UMMA_SINGLE_ACC"))) ? 1 : 0;
     p.tmem_cols = tmem_cols_for(p.BN, p.dual_acc);
     p.c32 = (float*)workspace; p.ldc32 = ldp;
-    p.epi_split = 2; p.epi_warp_bytes = 0;
+    p.epi_split = 2; p.epi_warp_bytes = 0; p.epi_bufs = 1;
     if (const char* e = AVR_EXP_ENV("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
     const int bn_rows = (p.BN + 63) / 64 * 64;
     const uint32_t stage_bytes = (uint32_t)na * A_PLANE_BYTES + (uint32_t)nb * (uint32_t)bn_rows * 128u;
@@ -959,10 +1094,10 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
         CUtensorMap ta, tb;
         if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, na)) return rc;
         if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nb)) return rc;
-        if (int rc = allow_max_smem<true>(device)) return rc;
+        if (int rc = allow_max_smem<true, false>(device)) return rc;
         const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
         const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
-        umma_gemm_kernel<true><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, p);
+        umma_gemm_kernel<true, false><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, ta, p);
         AVR_LAUNCH_CHECK();
     } else {
         p.k_splits = 0;
