@@ -1,9 +1,11 @@
 set -x
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_launches.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:umma_gemm_kernel -s 57 -c 19 --csv --log-file gpurun_out/r2f_umma_dram_traffic.csv python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_traffic.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mlp_chain -c 1 -s 3 -o gpurun_out/chain_r2f -f python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_chain.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; tail -2 gpurun_out/smoke.txt
-head -c 600 gpurun_out/bench_1gpu.json
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu_g.json 2> gpurun_out/bench_1gpu_g.err
+tail -3 gpurun_out/bench_1gpu_g.err
+python bench.py --config meshrir --mode infer --receivers 512 --bs 8 > gpurun_out/bench_meshrir_512.json 2> gpurun_out/bench_meshrir_512.err; tail -2 gpurun_out/bench_meshrir_512.err
+python -c "
+import json
+d=json.load(open('gpurun_out/bench_1gpu_g.json')); print(round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), round(d['e2e']['ms_per_step'],3))
+for k,v in d['other_configs'].items(): print(k, round(v['value'],1), 'e2e', round(v['e2e']['value'],1))
+d=json.load(open('gpurun_out/bench_meshrir_512.json')); print(d['value'], d['e2e'])
+"
