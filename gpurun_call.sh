@@ -1,11 +1,12 @@
-set -x
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu_g.json 2> gpurun_out/bench_1gpu_g.err
-tail -3 gpurun_out/bench_1gpu_g.err
-python bench.py --config meshrir --mode infer --receivers 512 --bs 8 > gpurun_out/bench_meshrir_512.json 2> gpurun_out/bench_meshrir_512.err; tail -2 gpurun_out/bench_meshrir_512.err
+python bench.py --steps 40 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/solo.json 2>/dev/null
+CUDA_VISIBLE_DEVICES=0 python bench.py --steps 40 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/conc0.json 2>/dev/null &
+CUDA_VISIBLE_DEVICES=1 python bench.py --steps 40 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/conc1.json 2>/dev/null
+wait
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 40 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ddp2.json 2>/dev/null
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 40 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt --flat-allreduce > gpurun_out/ddp2_flat.json 2>/dev/null
 python -c "
 import json
-d=json.load(open('gpurun_out/bench_1gpu_g.json')); print(round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), round(d['e2e']['ms_per_step'],3))
-for k,v in d['other_configs'].items(): print(k, round(v['value'],1), 'e2e', round(v['e2e']['value'],1))
-d=json.load(open('gpurun_out/bench_meshrir_512.json')); print(d['value'], d['e2e'])
+for f in ('solo','conc0','conc1','ddp2','ddp2_flat'):
+    d=json.load(open('gpurun_out/%s.json'%f)); print(f, round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), d['clocks']['sm_mhz'])
 "
