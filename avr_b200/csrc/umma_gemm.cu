@@ -915,7 +915,10 @@ AVR_API int avr_umma_gemm_nt(int64_t M, int64_t N, int64_t K, const void* a_plan
     if (int rc = allow_max_smem<false, false>(device)) return rc;
     p.cluster = 1;
     int pairs = 0;
-    if (!splitk_workspace && !(flags & UF_OUT_F32) && N > p.BN && p.BN % 32 == 0 && M >= 2ll * UM * num_sms(device) &&
+    // (a single column tile whose whole B operand fits in shared memory keeps the B-resident single-CTA schedule)
+    const bool b_fits = N <= p.BN && (uint64_t)ceil_div(K, UBK) * (uint64_t)b_nplanes * (uint64_t)p.BN * 128u +
+                                         2ull * (uint64_t)a_nplanes * A_PLANE_BYTES <= 232448u - 2048u - 65536u;
+    if (!splitk_workspace && !(flags & UF_OUT_F32) && !b_fits && p.BN % 16 == 0 && M >= 2ll * UM * num_sms(device) &&
         pair_mode_wanted(a_f16, a_nplanes)) {
         pairs = max_resident_pairs(device);
         if (pairs > 0) p.cluster = 2;
