@@ -56,7 +56,8 @@ struct ChainLayer {
 struct ChainParams {
     int M, n_layers, tiles, x_planes;
     int debug;                       // -DAVR_EXPERIMENTS builds only (AVR_CHAIN_DEBUG): 1 epilogue without pack / stores to the tile,
-                                     // 2 no bulk stores, 4 one product per k-step -- timing, results are garbage
+                                     // 2 no bulk stores, 4 one product per k-step, 8 no proxy fence, 16 no tensor-memory reads,
+                                     // 32 no st.shared, 64 no ReLU bitmask -- timing, results are garbage
     long long* trace;                // -DAVR_EXPERIMENTS builds only (AVR_CHAIN_TRACE_PTR): clock64() stamps of CTA 0's roles
     ChainLayer L[CH_MAX_LAYERS];
 };
@@ -286,6 +287,12 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                         }
                     } else if (active) {
                         float v[32];
+#ifdef AVR_EXPERIMENTS
+                        if (p.debug & 16) {                                      // timing: no tensor-memory reads
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __int_as_float(0x3f800000 + i + lane + (int)gl);
+                        } else
+#endif
                         if (L.products == 6) tmem_ld32_dual(taddr + c0, taddr + 128u + c0, 1.0f, v);
                         else {
                             float t0[16], t1[16];
@@ -317,7 +324,11 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                                 }
                             }
                         }
-                        if (L.bits) {
+                        if (L.bits
+#ifdef AVR_EXPERIMENTS
+                            && !(p.debug & 64)
+#endif
+                        ) {
                             uint32_t word = 0;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) word |= (v[i] > 0.f ? 1u : 0u) << i;
@@ -346,6 +357,9 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                         // 16-byte chunk c of row r of a k-block plane lives at chunk c ^ (r & 7)  (128-byte swizzle)
                         const uint32_t blk = a_base + (uint32_t)h * CH_A_KB + row_off;
                         const uint32_t c16 = (uint32_t)(c0 & 63) >> 3;
+#ifdef AVR_EXPERIMENTS
+                        if (p.debug & 32) { if (ph[0] == 0x12345678u && pm[3] == 7u && pl[5] == 9u) L.bits[0] = 1u; goto chunk_done; }   // timing: no st.shared
+#endif
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t off = blk + (((c16 + q) ^ sw) << 4);
