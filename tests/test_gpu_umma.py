@@ -336,3 +336,62 @@ def test_umma_bias_epilogue_and_block_sum(built_library):
         assert rel_l2(part, x[:, :64].double().view(bs * R, S_, 64).sum(1)) < 1e-6
         part_p = ops.rows_block_sum(geom, _pp(x[:, :64].contiguous()))
         assert rel_l2(part_p, x[:, :64].double().view(bs * R, S_, 64).sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("kind,okind,N,K,mode", [
+    (ops.PLANES_F16x2, ops.PLANES_F16x2, 512, 512, "relu_bits"),          # fp16-pair hidden layer
+    (ops.PLANES_F16x2, ops.PLANES_F16x2, 256, 208, "dual_copy"),          # ... with the bf16 copy for the weight gradient
+    (ops.PLANES_BF16x3, ops.PLANES_F16x2, 512, 208, "dual_copy"),         # first signal layer (six products)
+    (ops.PLANES_BF16x2, ops.PLANES_BF16x2, 512, 512, "masked"),           # backward-data product
+    (ops.PLANES_BF16x2, ops.PLANES_BF16x2, 208, 512, "plain"),            # a single column tile whose B is not resident
+])
+def test_umma_nt_cta_pairs_equal_single_cta(built_library, kind, okind, N, K, mode):
+    """Products over >= 2 * 128 * (number of SMs) rows run as CTA pairs (tcgen05 cta_group::2, 2x1x1 clusters; umma_gemm.cu,
+    pair mode): an ODD number of row tiles with a ragged last one here.  The same product computed in row slices too short
+    for pair mode takes the single-CTA schedule -- results must agree bit for bit (and with float64 to the kind's accuracy)."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    M = 2 * 128 * sms + 128 * 3 + 37
+    g = torch.Generator(device=DEV).manual_seed(N + K)
+    A = torch.randn(M, K, device=DEV, generator=g).clamp_min(-0.5)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    a = ops.planes_split(A, PlanePair.empty(M, K, DEV, kind=kind))
+    b = ops.planes_split(W, PlanePair.empty(N, K, DEV, kind=kind))
+    words = ops.relu_bits_empty(1, N, DEV).shape[1]
+    mask = torch.randint(-2 ** 31, 2 ** 31 - 1, (M, words), dtype=torch.int32, device=DEV) if mode == "masked" else None
+
+    def run(a_rows, c, c2, bits, mask_rows):
+        if mode == "relu_bits":
+            ops.umma_nt(a_rows, b, ops.UMMA_RELU, c, bits_out=bits)
+        elif mode == "dual_copy":
+            ops.umma_nt(a_rows, b, ops.UMMA_RELU | ops.UMMA_DUAL_COPY, c, c2=c2, bits_out=bits)
+        elif mode == "masked":
+            ops.umma_nt(a_rows, b, ops.UMMA_MASK, c, mask=mask_rows)
+        else:
+            ops.umma_nt(a_rows, b, 0, c)
+
+    c = PlanePair.empty(M, N, DEV, kind=okind)
+    c2 = PlanePair.empty(M, N, DEV, kind=ops.PLANES_BF16x2)
+    bits = ops.relu_bits_empty(M, N, DEV).zero_()
+    c.buf.zero_(); c2.buf.zero_()
+    run(a, c, c2, bits, mask)                                            # pair schedule
+    s = PlanePair.empty(M, N, DEV, kind=okind)
+    s2 = PlanePair.empty(M, N, DEV, kind=ops.PLANES_BF16x2)
+    sbits = ops.relu_bits_empty(M, N, DEV).zero_()
+    s.buf.zero_(); s2.buf.zero_()
+    step = 16384                                                         # < 2 * 128 * SMs rows: single-CTA schedule
+    for r0 in range(0, M, step):
+        n = min(step, M - r0)
+        run(a.row_window(r0, n), s.row_window(r0, n), s2.row_window(r0, n), sbits[r0:r0 + n],
+            mask[r0:r0 + n] if mask is not None else None)
+    assert torch.equal(c.buf, s.buf)
+    if mode == "dual_copy":
+        assert torch.equal(c2.buf, s2.buf)
+    if mode in ("relu_bits", "dual_copy"):
+        assert torch.equal(bits, sbits)
+    ref = ops.planes_merge(a).double() @ ops.planes_merge(b).double().t()
+    if mode in ("relu_bits", "dual_copy"):
+        ref = ref.clamp_min(0)
+    if mode == "masked":
+        ref = ref * _unpack_bits(mask, N).to(ref.dtype)
+    bound = TOL if kind == ops.PLANES_BF16x2 else 2e-6
+    assert rel_l2(ops.planes_merge(c), ref) < bound
