@@ -43,7 +43,8 @@ class ChainLayer(C.Structure):
                 ("save_raw", C.c_void_p), ("ld_raw", C.c_int64), ("raw_plane", C.c_int64), ("raw_kind", C.c_int32),
                 ("bits", C.c_void_p), ("ldbits", C.c_int64),
                 ("mask", C.c_void_p), ("ldmask", C.c_int64), ("accumulate", C.c_int32),
-                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64)]
+                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64),
+                ("bias", C.c_void_p), ("ld_bias", C.c_int64), ("bias_group_rows", C.c_int64)]
 
 
 class SplitDesc(C.Structure):

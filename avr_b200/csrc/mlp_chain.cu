@@ -52,6 +52,7 @@ struct ChainLayer {
     const uint32_t* mask; long long ldmask;  // in: the output is multiplied by this bitmask (ReLU backward), or null
     const __nv_bfloat16* accum; long long ld_acc, acc_plane; int acc_planes;   // in: planes added to the output, or null
     float* out_f32; long long ld_f32;        // fp32 output instead of planes (no activation; the chain's last layer)
+    const float* bias; long long ld_bias, bias_group;   // in: fp32 row (point / bias_group) added before the activation, or null
 };
 struct ChainParams {
     int M, n_layers, tiles, x_planes;
@@ -266,6 +267,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
                     // operands of the epilogue that do not depend on the accumulator: fetched before the wait
                     uint32_t mword = 0xffffffffu;
                     if (L.mask && active && row_ok) mword = __ldg(L.mask + row * L.ldmask + (c0 >> 5));
+                    const float* bias_row = (L.bias && active) ? L.bias + (row_ok ? row / L.bias_group : 0) * L.ld_bias + c0 : nullptr;
                     mbar_wait(bar_dfull + 8 * h, dphase[h]);
                     dphase[h] ^= 1u;
                     tc_fence_after();
@@ -303,6 +305,13 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
 #ifdef AVR_EXPERIMENTS
                         if (p.debug & 1) { if (v[0] == 123.456f) L.bits[0] = 1u; goto chunk_done; }
 #endif
+                        if (bias_row) {                                          // per-receiver embedding row (same order as the
+#pragma unroll                                                                       // per-layer kernel: after the accumulators are summed)
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(bias_row) + q);
+                                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                            }
+                        }
                         if (L.mask) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = (mword >> i) & 1u ? v[i] : 0.f;
@@ -430,6 +439,9 @@ AVR_API int avr_mlp_chain(int64_t M, const void* x0, int64_t ldx, int64_t x_plan
         AVR_REQUIRE(!a.bits || a.ldbits * 32 >= a.n_out, "bitmask rows too short");
         AVR_REQUIRE(!a.mask || a.ldmask * 32 >= a.n_out, "mask rows too short");
         AVR_REQUIRE(!(a.mask && a.relu) && !(a.mask && a.save_raw), "a masked (backward) layer has no activation and no raw output");
+        AVR_REQUIRE(!a.bias || (!a.out_f32 && !a.mask && a.n_out == 128 && a.bias_group_rows > 0 && a.ld_bias % 4 == 0 && aligned16(a.bias)),
+                    "a bias belongs to a 128-wide forward layer: 16-byte aligned fp32 rows, one per bias_group_rows points");
+        L.bias = a.bias; L.ld_bias = a.ld_bias; L.bias_group = a.bias_group_rows;
         L.K = a.k_in; L.N = a.n_out; L.relu = a.relu ? 1 : 0;
         L.products = (in_planes == 3 && planes_count(a.w_kind) == 3) ? 6 : 3;   // six products need 24 bits on both sides
         L.bits = a.bits; L.ldbits = a.ldbits; L.mask = a.mask; L.ldmask = a.ldmask; L.out_f32 = a.out_f32; L.ld_f32 = a.ld_f32;

@@ -165,7 +165,7 @@ class FusedRenderTC(torch.autograd.Function):
         # Inference (torch.no_grad(): nothing requires grad) skips everything only the backward pass reads: saved planes of
         # the 128-wide layers, ReLU bitmasks, the bf16 copies of the signal network's fp16-pair activations.
         train = any(ctx.needs_input_grad[8:])
-        chain = (FUSE_SIGMA_CHAIN and guard is None and not any(k[0] in ("enc", "dec") for k in bias_of) and not plan["sig_relu_feat"] and feat_dim == 128
+        chain = (FUSE_SIGMA_CHAIN and guard is None and not plan["sig_relu_feat"] and feat_dim == 128
                  and dec_net.in_pad == feat_dim and not plan.get("dec_tail") and enc_net.in_pad <= 128 and enc_net.in_pad % 16 == 0
                  and all(o == 128 for (o, _) in enc_net.shapes) and all(o == 128 for (o, _) in dec_net.shapes[:-1])
                  and dec_net.out_pad <= 64 and dec_net.out_pad % 16 == 0 and len(enc_net.shapes) + len(dec_net.shapes) <= _lib_chain_max())
@@ -177,14 +177,21 @@ class FusedRenderTC(torch.autograd.Function):
             bits_dec = [ops.relu_bits_empty(n_rows if train else 0, 128, dev) for _ in w_dec[:-1]]
             dec_in = PlanePair.empty(n_rows if train else 0, dec_net.in_pad, dev, kind=FWD_KIND)
             dec_out = torch.empty(n_rows, dec_net.out_pad, device=dev)
+            def emb(net_key, li):
+                # per-receiver channel-embedding row of a hidden layer (model.py:44-47): a bias before the activation
+                b = bias_of.get((net_key, li))
+                return dict(bias=b, bias_group_rows=geom.R * geom.S) if b is not None else {}
+
             if train:
-                layers = [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_enc[:-1], acts_enc, bits_enc)]
+                layers = [dict(w=wp, relu=True, save=a, bits=b, **emb("enc", li))
+                          for li, (wp, a, b) in enumerate(zip(w_enc[:-1], acts_enc, bits_enc))]
                 layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win, save=dec_in, bits=bits_feat))   # raw feat + relu(feat)
-                layers += [dict(w=wp, relu=True, save=a, bits=b) for wp, a, b in zip(w_dec[:-1], acts_dec, bits_dec)]
+                layers += [dict(w=wp, relu=True, save=a, bits=b, **emb("dec", li))
+                           for li, (wp, a, b) in enumerate(zip(w_dec[:-1], acts_dec, bits_dec))]
             else:
-                layers = [dict(w=wp, relu=True) for wp in w_enc[:-1]]
+                layers = [dict(w=wp, relu=True, **emb("enc", li)) for li, wp in enumerate(w_enc[:-1])]
                 layers.append(dict(w=w_enc[-1], relu=True, save_raw=feat_win))
-                layers += [dict(w=wp, relu=True) for wp in w_dec[:-1]]
+                layers += [dict(w=wp, relu=True, **emb("dec", li)) for li, wp in enumerate(w_dec[:-1])]
             layers.append(dict(w=w_dec[-1], relu=False, out_f32=dec_out))                                 # the |leaky_relu| kink follows
             ops.mlp_chain(x0, layers)
         else:
@@ -398,9 +405,11 @@ class FusedRenderTC(torch.autograd.Function):
             ops.mlp_chain(g, layers)
             for k, li in enumerate(range(n_dec - 1, 0, -1)):
                 ops.umma_tn(g_dec_l[k], acts_dec[li - 1], d_dec_mats[li], ws)
+                bias_grad("dec", li - 1, g_dec_l[k + 1])                         # d(embedding row) of hidden layer li - 1
             ops.umma_tn(g_dec_l[-1], dec_in, d_dec_mats[0], ws)
             for k, li in enumerate(range(n_enc - 1, 0, -1)):
                 ops.umma_tn(g_enc_l[k], acts_enc[li - 1], d_enc_mats[li], ws)
+                bias_grad("enc", li - 1, g_enc_l[k + 1])
             ops.umma_tn(g_enc_l[-1], x0, d_enc_mats[0], ws)
             grads[id(dec_net)] = g_dec
             grads[id(enc_net)] = g_enc

@@ -441,7 +441,8 @@ def mlp_chain(x0: PlanePair, layers):
 
     ``x0``: bf16 plane set ``[M, k0]`` (pair or triple).  ``layers``: dicts with ``w`` (bf16 planes of ``W[n_out, k_in]``)
     and the optional ``relu`` (bool), ``mask`` (int32 bitmask multiplied into the output: ReLU backward), ``accumulate``
-    (add what ``save`` already holds), outputs ``save`` (PlanePair), ``save_raw`` (PlanePair, un-rectified output), ``bits``
+    (add what ``save`` already holds), ``bias`` + ``bias_group_rows`` (fp32 rows added before the activation, one per group of
+    consecutive points: the per-receiver channel-embedding rows), outputs ``save`` (PlanePair), ``save_raw`` (PlanePair, un-rectified output), ``bits``
     (int32 ReLU bitmask out), ``out_f32`` (fp32 ``[M, >= n_out]`` tensor; last layer only).  Bit-identical to running the
     layers through ``umma_nt`` one by one."""
     dev, st = _ctx(x0)
@@ -468,6 +469,10 @@ def mlp_chain(x0: PlanePair, layers):
         a.accumulate = 1 if L.get("accumulate") else 0
         if o32 is not None:
             a.out_f32, a.ld_f32 = _p(o32).value, o32.stride(0)
+        if L.get("bias") is not None:                      # fp32 [groups, n_out]: row (point // bias_group_rows) is added before the activation
+            bias = L["bias"]
+            assert bias.dtype == torch.float32 and bias.stride(1) == 1 and bias.shape[1] == w.rows
+            a.bias, a.ld_bias, a.bias_group_rows = _p(bias).value, bias.stride(0), int(L["bias_group_rows"])
         f = 2.0 * x0.rows * w.rows * w.cols
         flops += f
         executed += f * (6 if (planes_in == 3 and w.n == 3) else 3)

@@ -238,6 +238,9 @@ AVR_API int64_t avr_umma_gemm_nt_splitk_slices(int64_t K);
  *              signal network raw, model.py:219, and the decoder rectified, model.py:209)
  *   bits       optional ReLU bitmask out: bit (col % 32) of word [row][col / 32] = (raw output > 0)
  *   out_f32    last layer only: fp32 output [M][ld_f32] instead of planes (the 16-wide density head); no activation
+ *   bias       optional, forward: fp32 rows [*][ld_bias] added to the output before the activation, row (point /
+ *              bias_group_rows) for every point -- the per-receiver channel-embedding row of model.py:44-47
+ *              (`h + layer_embeddings[l][ch_id]`), bias_group_rows = R * S points per receiver
  * Hidden layers are 128 wide; k_in of layer 0 (= k0, the width of x0) is a multiple of 16 up to 128; the last layer may
  * be any multiple of 16 up to 128 (up to 64 for fp32).  x0: BF16x2 / BF16x3 planes [*][M][ldx]. */
 #define AVR_CHAIN_MAX_LAYERS 8
@@ -250,6 +253,7 @@ typedef struct avr_chain_layer {
     const uint32_t* mask; int64_t ldmask;
     int32_t accumulate;
     float* out_f32; int64_t ld_f32;
+    const float* bias; int64_t ld_bias, bias_group_rows;
 } avr_chain_layer;
 AVR_API int avr_mlp_chain(int64_t M, const void* x0, int64_t ldx, int64_t x_plane, int32_t x_kind, int32_t k0,
                           const avr_chain_layer* layers, int32_t n_layers, int device, void* stream);

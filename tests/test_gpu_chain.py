@@ -96,6 +96,56 @@ def test_chain_is_bit_identical_to_the_layer_by_layer_kernel(built_library, M, k
         assert rel_l2(h, pre.clamp_min(0) if s["relu"] else pre) < 2e-6
 
 
+@pytest.mark.parametrize("bs,R,S", [(3, 37, 6), (2, 50, 64)])
+def test_chain_with_per_receiver_bias_rows(built_library, bs, R, S):
+    """Channel embeddings in 'add' mode (model.py:44-47): a per-receiver fp32 row is added to a hidden layer's output before
+    the ReLU.  The chain (``bias`` / ``bias_group_rows``) against the layer-by-layer kernel (``bias_rcv`` + geometry): bit for
+    bit; receivers change in the middle of 128-row tiles (R * S is not a multiple of 128)."""
+    M = bs * R * S
+    geom = ops.RenderGeom(bs, R, S, 200, -10.0, 20.0, 16000.0, 343.8)
+    g = torch.Generator().manual_seed(M)
+    x0 = torch.randn(M, 48, generator=g)
+    dims = [48, 128, 128, 128, 16]
+    mats = [torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5 for i in range(4)]
+    biases = [torch.randn(bs, 128, generator=g).to(DEV), None, torch.randn(bs, 128, generator=g).to(DEV)]   # layers 0 and 2
+    x0p = _planes(x0)
+    wps = [_planes(w) for w in mats]
+    # layer by layer
+    h, ref = x0p, []
+    for li in range(3):
+        y = PlanePair.zeros(M, 128, DEV, kind=K3)
+        bits = torch.zeros_like(ops.relu_bits_empty(M, 128, DEV))
+        if biases[li] is not None:
+            ops.umma_nt(h, wps[li], ops.UMMA_RELU, y, bits_out=bits, bias_rcv=biases[li], geom=geom)
+        else:
+            ops.umma_nt(h, wps[li], ops.UMMA_RELU, y, bits_out=bits)
+        ref.append((y, bits))
+        h = y
+    head_ref = torch.zeros(M, 16, device=DEV)
+    ops.umma_nt(h, wps[3], ops.UMMA_OUT_F32, c_f32=head_ref)
+    # one launch
+    layers, mine = [], []
+    for li in range(3):
+        y = PlanePair.zeros(M, 128, DEV, kind=K3)
+        bits = torch.zeros_like(ops.relu_bits_empty(M, 128, DEV))
+        L = dict(w=wps[li], relu=True, save=y, bits=bits)
+        if biases[li] is not None:
+            L.update(bias=biases[li], bias_group_rows=R * S)
+        layers.append(L)
+        mine.append((y, bits))
+    head = torch.zeros(M, 16, device=DEV)
+    layers.append(dict(w=wps[3], relu=False, out_f32=head))
+    ops.mlp_chain(x0p, layers)
+    for li, ((y, bits), (yr, br)) in enumerate(zip(mine, ref)):
+        assert torch.equal(y.buf, yr.buf), li
+        assert torch.equal(bits[:, :4], br[:, :4]), li
+    assert torch.equal(head, head_ref)
+    # and the bias really is the receiver's row: float64 of the first layer
+    pre = ops.planes_merge(x0p).double().cpu() @ ops.planes_merge(wps[0]).double().cpu().t()
+    pre = pre + biases[0].double().cpu().repeat_interleave(R * S, dim=0)
+    assert rel_l2(ops.planes_merge(mine[0][0]).cpu(), pre.clamp_min(0)) < 2e-6
+
+
 @pytest.mark.parametrize("M", [300, 128 * 150 + 5])
 def test_backward_data_chain_is_bit_identical(built_library, M):
     """The backward-data pass of sigma decoder -> sigma encoder as one chain: ReLU bitmasks multiplied into every output,
