@@ -57,6 +57,9 @@ struct UmmaParams {
     int mode;               // product schedule, see the MMA issuer
     float small_scale;      // factor of the small-products accumulator in the epilogue (2^-11 with an fp16 operand)
     int b_resident, nkb;    // K-major, single column tile, short K: the whole B operand stays in shared memory
+    int conv_b;             // MN-major only: the B tile arrives as an fp16 (hi, lo') pair and the otherwise idle epilogue warps
+                            // turn it into a bf16 (hi, mid) pair in shared memory before the MMAs read it (one element format
+                            // per MMA; the gradient operand needs bf16's range)
     int cluster;            // 2: CTA pairs (thread-block cluster 2x1x1, tcgen05 cta_group::2) multiply two adjacent row tiles
                             // by one column tile as ONE 256-row MMA; each CTA stages only half of the B tile
     int flags;
@@ -149,7 +152,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bres_bytes + (size_t)p.stages * stage_bytes);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.stages;
     const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16, bar_bres = bar_tempty + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+    const uint32_t bar_conv = bar_bres + 8;                  // [stages]: the B tile of a stage has been converted (conv_b)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 5);
     const uint32_t bres_base = smem_u32(smem);
     const uint32_t smem_base = bres_base + bres_bytes;
     // epilogue staging: (4 or 8) warps x nc planes x 2 KB, 1024-byte aligned, after the barrier block
@@ -162,6 +166,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, pair ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (pair ? 256 : 128) * p.epi_split); }
         mbar_init(bar_bres, 1);
+        for (int s = 0; s < p.stages; ++s) mbar_init(bar_conv + 8 * s, 4 * p.epi_split);     // one arrival per converting warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -259,6 +264,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t shared_acc = p.dual_acc ? 0u : 0xffffffffu;
                 for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
                     mbar_wait(bar_full + 8 * stage, phase);
+                    if (MN_MAJOR && p.conv_b) mbar_wait(bar_conv + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = bres ? bres_base + (uint32_t)(k0 / UBK) * b_tile_bytes : sa + a_tile_bytes;
@@ -329,7 +335,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // alternate chunks through their own staging tiles, so two such chains are in flight per lane group.
         const int lane_grp = warp & 3;
         const int half = (warp - 2) >> 2;
-        int iter = 0;
+        int iter = 0, cstage = 0;
+        uint32_t cphase = 0;
         for (int tile = t_begin; tile < n_tiles; tile += t_stride, ++iter) {
             const int split = tile % p.k_splits;
             const int mn = tile / p.k_splits;
@@ -338,6 +345,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t acc_phase = (uint32_t)(p.acc_bufs == 2 ? (iter >> 1) : iter) & 1u;
             const long long row = m0 + lane_grp * 32 + lane;
             const bool row_ok = row < p.M;
+            if (MN_MAJOR && p.conv_b) {
+                // Weight gradients from an fp16-pair activation: while the MMAs of this work item run, the epilogue warps
+                // (idle until the accumulator is final) rewrite every B tile in place, element by element -- the two
+                // planes share one layout -- from x = hi + lo' * 2^-11 (exact in fp32) to bf16 (hi, mid), exactly what
+                // avr_planes_split would have written; ~700 issue cycles per k-block against ~1 500 clk of MMAs.
+                const int n_conv = 128 * p.epi_split, t_conv = (warp - 2) * 32 + lane;
+                const uint32_t chunks = (uint32_t)(bn_rows / 64) * 512u;          // 16-byte chunks per plane of the B tile
+                for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
+                    mbar_wait(bar_full + 8 * cstage, cphase);
+                    const uint32_t sb = smem_base + cstage * stage_bytes + a_tile_bytes;
+                    for (uint32_t c = t_conv; c < chunks; c += n_conv) {
+                        const uint32_t a0 = sb + (c >> 9) * mn_blk_b + (c & 511u) * 16u, a1 = a0 + 8192u;
+                        uint32_t h[4], l[4];
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(a0));
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(a1));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 x = planes_unpack2(true, h[i], l[i]);
+                            uint32_t unused;
+                            planes_pack2(AVR_PLANES_BF16x2, x.x, x.y, h[i], l[i], unused);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                    }
+                    fence_async_smem();                                          // generic-proxy writes -> visible to the MMAs
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_conv + 8 * cstage);
+                    if (++cstage == p.stages) { cstage = 0; cphase ^= 1u; }
+                }
+            }
             // per-tile operands of the epilogue are fetched BEFORE waiting for the accumulator, so that their
             // (row-strided / L2) load latency overlaps the tile's MMAs:
             //   mw[j]   ReLU gating word of columns [32j, 32j+32) of this row            (UF_MASK)
@@ -1055,8 +1092,10 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
                              int64_t ldc, int accumulate, void* workspace, int64_t workspace_bytes, int device,
                              void* stream) {
     AVR_REQUIRE(a_planes && b_planes && c && workspace, "null pointer");
-    AVR_REQUIRE(planes_kind_ok(a_kind) && planes_kind_ok(b_kind) && !planes_f16(a_kind) && !planes_f16(b_kind),
-                "weight gradients take bf16 plane sets (one element format per MMA; gradients need bf16's range)");
+    AVR_REQUIRE(planes_kind_ok(a_kind) && planes_kind_ok(b_kind) && !planes_f16(a_kind),
+                "the gradient operand is a bf16 plane set (gradients need bf16's range)");
+    // an fp16-pair activation is converted to a bf16 (hi, mid) pair in shared memory (conv_b): the MMAs see bf16 on both sides
+    const int conv_b = planes_f16(b_kind) ? 1 : 0;
     const int b_f16 = 0;
     int na = planes_count(a_kind), nb = planes_count(b_kind);
     if (!b_f16 && !(na == 3 && nb == 3)) na = nb = 2;                       // bf16 . bf16: six products need 24 bits on both sides
@@ -1070,6 +1109,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.BN = pick_bn(N, nplanes == 3 ? 128 : 256);                // two stages and two accumulators must fit
     p.na = na; p.nb = nb; p.nc = 2;
     p.fa = 0; p.fb = b_f16; p.kc = p.kc2 = AVR_PLANES_BF16x2;
+    p.conv_b = conv_b;
     p.acc_bufs = 2;
     p.mode = b_f16 ? (na == 3 ? 4 : 3) : (na == 3 ? 1 : 0);
     p.small_scale = b_f16 ? F16_LO_INV : 1.0f;

@@ -22,13 +22,18 @@ from .ops import PlanePair
 FWD_KIND = ops.PLANES_BF16x3  # forward operands carry 24 mantissa bits (six products): ReLU decisions must match fp32
 SIG_HIDDEN_F16 = True
 # The 512 x 512 hidden layers of the signal network (tensor-bound, half of the forward MMA time) take fp16
-# (hi, lo' * 2^11) pairs: 24 bits in two planes, THREE products instead of six.  The producing layer writes each hidden
-# activation twice (ops.UMMA_DUAL_COPY): as an fp16 pair for the next layer / the collapsed output layer, and as a bf16
-# (hi, mid) pair for the weight-gradient GEMM (gradients need bf16's range, and tcgen05.mma faults on a bf16 x f16 mix).
-# Measured on one box, same run: 14.6 -> 14.1 ms per step; the layers become L2-feed-bound (512 KB of operands per
-# 128 x 128 tile) instead of MMA-bound, hence not the full 2x.  Range: fp16's -- like tiny-cuda-nn's own activations --
-# inf / NaN beyond 65504 (loud), absolute error <= 1.5e-11 below 6e-5.  False keeps bf16 triples everywhere (a module
-# constant, not an environment switch: tests set it explicitly).
+# (hi, lo' * 2^11) pairs: 24 bits in two planes, THREE products instead of six.  Range: fp16's -- like tiny-cuda-nn's own
+# activations -- inf / NaN beyond 65504 (loud), absolute error <= 1.5e-11 below 6e-5.  False keeps bf16 triples everywhere
+# (a module constant, not an environment switch: tests set it explicitly).
+SIG_TN_FROM_F16 = False
+# The weight-gradient GEMM of such a layer needs its activation as a bf16 pair (the gradient operand needs bf16's range,
+# and tcgen05.mma faults on a bf16 x f16 mix).  False (default): the producing layer writes each hidden activation twice
+# (ops.UMMA_DUAL_COPY: fp16 pair + bf16 pair).  True: avr_umma_gemm_tn takes the fp16 pair and its epilogue warps, idle
+# during the main loop, convert every tile to bf16 (hi, mid) in shared memory -- bit-identical gradients, 2.1 GB less HBM
+# traffic and activation memory per simu step, the two forward layers 0.82 -> 0.62 and 0.79 -> 0.65 ms, BUT the two
+# 512 x 512 weight-gradient GEMMs 0.61 -> 0.87 ms each: with two 96 KB pipeline stages per CTA the conversion (~1 000 clk
+# after the tile has landed) sits on the stage's critical path.  Net on one box, interleaved: 11.76 vs 11.65 ms per step
+# (profiles/ab_tn_from_f16.py, profiles/r2/ab_tn_from_f16.txt) -- kept as the memory-saving option, not the default.
 BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough ...
 DENSITY_BWD_PLANES = 3   # ... except along the sigma decoder: the density gradient of a ray sums to ~0 over its samples
                          # (sum_s w_s = 1), so the decoder's weight-gradient sums cancel to ~1/50 of their terms
@@ -241,7 +246,7 @@ class FusedRenderTC(torch.autograd.Function):
             fl, kw = layer_flags("sig", li)
             if f16:
                 y = PlanePair.empty(n_rows, w_sig[li].rows, dev, kind=ops.PLANES_F16x2)
-                if last or not train:                                        # H: only the collapsed output layer reads it
+                if last or not train or SIG_TN_FROM_F16:                     # the weight-gradient GEMM converts the fp16 pair itself
                     ops.umma_nt(h, w_sig[li], fl, y, bits_out=bits, **kw)
                     acts_sig.append(y)
                 else:

@@ -489,11 +489,13 @@ def umma_tn_workspace_bytes(M, N, K) -> int:
 
 
 def umma_tn(a: PlanePair, b: PlanePair, c_f32, workspace, accumulate=False):
-    """C[M,N] (+)= sum_k A[k,M] B[k,N]  (A, B plane pairs over the same rows k); fp32 C (may be a column view)."""
+    """C[M,N] (+)= sum_k A[k,M] B[k,N]  (A, B plane pairs over the same rows k); fp32 C (may be a column view).
+    ``a`` (the gradient) is a bf16 plane set; ``b`` (the activation) a bf16 set or an fp16 pair, which the kernel turns into
+    the bf16 (hi, mid) pair ``planes_split`` would have written, in shared memory."""
     dev, st = _ctx(a)
     K, M, N = a.rows, a.cols, b.cols
     assert b.rows == K
-    assert not a.f16 and not b.f16, "weight gradients take bf16 plane sets"
+    assert not a.f16, "the gradient operand is a bf16 plane set"
     products = 6 if (a.n == 3 and b.n == 3) else 3       # six products only when both operands carry 24 bits
     with _timed("umma_gemm", 2.0 * M * N * K, "flop", 2.0 * M * N * K * products):
         _lib.check(_lib.load().avr_umma_gemm_tn(M, N, K, a.ptr, a.ld, a.plane, a.kind, b.ptr, b.ld, b.plane, b.kind, _p(c_f32),

@@ -264,7 +264,11 @@ AVR_API int avr_mlp_chain(int64_t M, const void* x0, int64_t ldx, int64_t x_plan
  *   BF16x2 . BF16x2 (or mixed counts): three products on the (hi, mid) planes
  *   BF16x3 . BF16x3: six products on 24-bit operands -- for the ill-conditioned sums of the density path, whose
  *                    terms cancel to ~1/50 of their magnitude
- * fp16 pairs are not accepted: gradients need bf16's exponent range, and tcgen05.mma faults on a bf16 x f16 mix. */
+ *   BF16x* . F16x2: the activation tile is converted in shared memory to the bf16 (hi, mid) pair avr_planes_split would
+ *                    write for the same values (the kernel's epilogue warps do it while the MMAs of earlier tiles run),
+ *                    then three products -- bit-identical to passing that bf16 pair
+ * The gradient operand itself is never fp16: gradients need bf16's exponent range, and tcgen05.mma faults on a bf16 x f16
+ * mix. */
 AVR_API int64_t avr_umma_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
 AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_planes, int64_t lda, int64_t a_plane,
                              int a_kind, const void* b_planes, int64_t ldb, int64_t b_plane, int b_kind, float* c,

@@ -258,6 +258,26 @@ def test_umma_tn_weight_grad(built_library, M, N, K):
     assert float(outs[0][:, N:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 40000), (512, 208, 9001), (128, 80, 3000), (512, 512, 128 * 148 * 3 + 77)])
+def test_umma_tn_fp16_pair_activation_converted_in_kernel(built_library, M, N, K):
+    """Weight gradient whose activation operand is an fp16 (hi, lo') pair: the kernel's epilogue warps turn every tile into a
+    bf16 (hi, mid) pair in shared memory (umma_gemm.cu, conv_b).  Bit-identical to handing it the bf16 pair that
+    planes_split writes for the same values."""
+    g = torch.Generator().manual_seed(M + N + K)
+    dY = torch.randn(K, M, generator=g) * torch.rand(K, 1, generator=g) ** 8          # heavy-tailed rows, like real gradients
+    X = torch.randn(K, N, generator=g).clamp_min(0) * 3
+    a = _pp(dY)
+    x16 = ops.planes_split(X.to(DEV), PlanePair.empty(K, N, DEV, kind=ops.PLANES_F16x2))
+    xbf = ops.planes_split(ops.planes_merge(x16), PlanePair.empty(K, N, DEV, kind=ops.PLANES_BF16x2))
+    ws = torch.empty(max(4, ops.umma_tn_workspace_bytes(M, N, K) // 4), device=DEV)
+    c16, cbf = torch.zeros(M, N, device=DEV), torch.zeros(M, N, device=DEV)
+    ops.umma_tn(a, x16, c16, ws)
+    ops.umma_tn(a, xbf, cbf, ws)
+    assert torch.equal(c16, cbf)
+    assert torch.equal(ops.planes_merge(x16), ops.planes_merge(ops.planes_split(X.to(DEV), PlanePair.empty(K, N, DEV, kind=ops.PLANES_F16x2))))   # operand untouched
+    assert rel_l2(c16, ops.planes_merge(a).double().t() @ ops.planes_merge(x16).double()) < TOL
+
+
 @pytest.mark.parametrize("M,N,K", [(16, 128, 5000), (128, 128, 20000), (128, 48, 3001), (512, 208, 2000), (128, 256, 9000)])
 def test_umma_tn_six_products_ill_conditioned(built_library, M, N, K):
     """Weight gradients of the density path: the terms of sum_k dY[k,m] X[k,n] cancel to a few percent of their
