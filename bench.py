@@ -346,6 +346,27 @@ class Workload:
         torch.cuda.empty_cache()
 
 
+def settle_steps(w, seconds, max_steps):
+    """Untimed steps until ``seconds`` of device time have passed (the same count on every rank: decided from the first
+    steps' duration on rank 0's clock would need a broadcast, so it is derived from the step time measured here and a
+    MAX over the ranks)."""
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        w.step(False)
+    e1.record()
+    torch.cuda.synchronize()
+    per = torch.tensor([e0.elapsed_time(e1) / 3e3], device=w.dev)
+    if w.world > 1:
+        dist.all_reduce(per, op=dist.ReduceOp.MAX)
+    n = int(min(max_steps, max(0.0, seconds / max(float(per), 1e-4) - 3)))
+    for _ in range(n):
+        w.step(False)
+    torch.cuda.synchronize()
+    return n + 3
+
+
 def kernel_table(prof, steps, ms_total, pk):
     per = {}
     for name, work, unit, s, e, executed in prof:
@@ -464,6 +485,10 @@ def run_native(args, cfg):
     w = Workload(args.config, args.bs, args.mode, args.grid_grad, dev, rank, world, args.flat_allreduce)
     for _ in range(warm):
         w.step(False)
+    # ... and on until the GPU has been under this load for ~1.5 s: the boxes are power-capped, and the first ~0.3 s after an
+    # idle period run 2-3 % faster than the steady state every later pass sees (profiles/r2/value_vs_e2e_order.txt: 11.60 ms
+    # for the first 20 steps, 11.9 ms for every pass after it, device-resident or end-to-end alike)
+    settle = settle_steps(w, 1.5, 200)
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, _ = w.timed(False, args.steps)                         # headline: no per-kernel events
     w.step(True)
@@ -559,6 +584,8 @@ def run_native(args, cfg):
                             "two device buffers) and its spectra back to pinned host memory (copy stream, right after the forward "
                             "pass); steps are not synchronised one by one (throughput), the timed region ends with a device "
                             "synchronise over all streams"},
+            "warmup_note": f"{warm} warm-up steps as requested + {settle} more untimed steps (~1.5 s under load) so that the timed "
+                           "passes see the power-capped steady state, not the first tenths of a second after idle",
             "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
             "profile_pass": {"steps": prof_steps, "ms_per_step": ms_prof / prof_steps,
                              "note": "kernels / roofline come from this separate pass with CUDA events around every library call"},
