@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python profiles/diag_flips_f16_vs_bf16x3.py 2>&1 | grep -v Warn | tail -8 | tee gpurun_out/diag_flips_f16_vs_bf16x3.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:umma_gemm_kernel -s 57 -c 19 -o gpurun_out/umma_step_r2g -f python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline --no-alt > gpurun_out/ncu_umma_step.log 2>&1
+tail -3 gpurun_out/ncu_umma_step.log
+ls -la gpurun_out/umma_step_r2g.ncu-rep

@@ -39,7 +39,11 @@ def main(path, labels):
             if key not in ci or r[ci[key]] == "":
                 cells.append("-")
                 continue
-            v = float(r[ci[key]].replace(",", "")) * SCALE.get(units[ci[key]], 1.0)
+            try:
+                v = float(r[ci[key]].replace(",", "")) * SCALE.get(units[ci[key]], 1.0)
+            except ValueError:                                  # "no data" for a metric of this launch
+                cells.append("-")
+                continue
             if units[ci[key]] in ("Kbyte", "Kbyte/block"):
                 v = float(r[ci[key]].replace(",", "")) * 1e3
             cells.append(fmt.format(v * mul))
