@@ -20,6 +20,12 @@
 //               output kind (or write fp32), stage in swizzled shared memory, TMA-store
 // Two operand modes: K-major x K-major (forward, backward-data with a pre-transposed weight) and
 // MN-major x MN-major with split-K over the sample points (weight gradients, deterministic second pass).
+// Third template flavour, PAIR (K-major): the CTAs of a 2x1x1 thread-block cluster work as one tcgen05 CTA pair
+// (cta_group::2) on two adjacent row tiles x one column tile -- one 256-row MMA issued by the leader, each CTA stages its
+// own 128 rows of A and HALF of the B tile, the leader's "full" barriers count both CTAs' TMA bytes, its commits are
+// multicast to both CTAs' "stage free" / "accumulator final" barriers, and the peer's epilogue arrives remotely on the
+// leader's "accumulator drained" barrier.  Used for every wide product over many row tiles (see avr_umma_gemm_nt).
+// In the MN-major flavour the epilogue warps can also convert an fp16-pair B tile to bf16 in shared memory (conv_b).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <atomic>
