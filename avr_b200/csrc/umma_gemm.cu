@@ -20,11 +20,12 @@
 //               output kind (or write fp32), stage in swizzled shared memory, TMA-store
 // Two operand modes: K-major x K-major (forward, backward-data with a pre-transposed weight) and
 // MN-major x MN-major with split-K over the sample points (weight gradients, deterministic second pass).
-// Third template flavour, PAIR (K-major): the CTAs of a 2x1x1 thread-block cluster work as one tcgen05 CTA pair
+// Third template flavour, PAIR (both operand modes): the CTAs of a 2x1x1 thread-block cluster work as one tcgen05 CTA pair
 // (cta_group::2) on two adjacent row tiles x one column tile -- one 256-row MMA issued by the leader, each CTA stages its
 // own 128 rows of A and HALF of the B tile, the leader's "full" barriers count both CTAs' TMA bytes, its commits are
 // multicast to both CTAs' "stage free" / "accumulator final" barriers, and the peer's epilogue arrives remotely on the
-// leader's "accumulator drained" barrier.  Used for every wide product over many row tiles (see avr_umma_gemm_nt).
+// leader's "accumulator drained" barrier.  Used for every wide product over many row tiles (see avr_umma_gemm_nt) and for
+// weight gradients of at least two row tiles (avr_umma_gemm_tn; same split over k, bit-identical partial sums).
 // In the MN-major flavour the epilogue warps can also convert an fp16-pair B tile to bf16 in shared memory (conv_b).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -141,12 +142,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // (a separate instantiation: a kernel that contains cta_group::2 instructions cannot be launched without a cluster)
     constexpr bool pair = PAIR;
-    static_assert(!(PAIR && MN_MAJOR), "pair mode is K-major only");
     uint32_t crank = 0u;
     if constexpr (PAIR) crank = cluster_ctarank();
     const bool leader = crank == 0u;
     // B rows (K-major; pair mode: this CTA's half of the column tile) / MN extent (MN-major) in smem
-    const int bn_rows = MN_MAJOR ? ((p.BN + 63) / 64) * 64 : (pair ? p.BN >> 1 : p.BN);
+    const int bn_rows = MN_MAJOR ? (((pair ? p.BN >> 1 : p.BN) + 63) / 64) * 64 : (pair ? p.BN >> 1 : p.BN);
     const uint32_t b_plane_bytes = MN_MAJOR ? 8192u : (uint32_t)bn_rows * 128u;
     const uint32_t a_tile_bytes = (uint32_t)p.na * A_PLANE_BYTES;
     const uint32_t b_tile_bytes = MN_MAJOR ? (uint32_t)p.nb * (uint32_t)bn_rows * 128u : (uint32_t)p.nb * b_plane_bytes;
@@ -193,7 +193,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     // work list: tiles (row tile, column tile, K slice) strided over the CTAs, or -- pair mode -- units of two adjacent
     // row tiles x one column tile strided over the clusters, rank r of the pair taking row tile 2 u + r
-    const int n_tiles = pair ? ((p.tiles_m + 1) / 2) * p.tiles_n : p.tiles_m * p.tiles_n * p.k_splits;
+    const int n_tiles = (pair ? ((p.tiles_m + 1) / 2) * p.tiles_n : p.tiles_m * p.tiles_n) * p.k_splits;
     const int t_begin = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int t_stride = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     auto row_tile = [&](int mn) { const int mt = mn / p.tiles_n; return pair ? 2 * mt + (int)crank : mt; };
@@ -219,7 +219,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if constexpr (!pair) mbar_expect_tx(full, stage_bytes);
                     else if (leader) mbar_expect_tx(full, 2u * stage_bytes);
                     else mbar_arrive_cluster(full, 0u);
-                    if constexpr (pair) {
+                    if constexpr (pair && MN_MAJOR) {
+                        // my 128 columns of A (two 64-wide boxes) and my half of the B columns
+                        tma_load_3d_2sm(sa, &tmA, full, m0, k0, 0);
+                        tma_load_3d_2sm(sa + mn_blk_a, &tmA, full, m0 + 64, k0, 0);
+                        for (int i = 0; i < bn_rows / 64; ++i)
+                            tma_load_3d_2sm(sb + mn_blk_b * i, &tmB, full, n0 + (int)crank * bn_rows + 64 * i, k0, 0);
+                    } else if constexpr (pair) {
                         // my row tile and my half of the rows of the column tile; the bytes count on the leader's barrier
                         tma_load_3d_2sm(sa, &tmA, full, k0, m0, 0);
                         tma_load_3d_2sm(sb, &tmBh, full, k0, n0 + (int)crank * bn_rows, 0);
@@ -809,7 +815,8 @@ static int tmem_cols_for(int bn, int dual = 0, int bufs = 2) {
 
 // How many 2-CTA clusters of the K-major kernel can be resident at once (one CTA per SM; a GPC with an odd number of
 // free SMs leaves one idle).  Asked once per (device, dynamic shared memory size).
-static int max_resident_pairs(int device) {
+template <bool MN_MAJOR>
+static int max_resident_pairs_of(int device) {
     static std::mutex mu;
     static std::unordered_map<uint64_t, int> cache;
     const size_t smem = 232448;
@@ -828,12 +835,14 @@ static int max_resident_pairs(int device) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (allow_max_smem<false, true>(device) != AVR_OK) return 0;
-    if (cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<false, true>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (allow_max_smem<MN_MAJOR, true>(device) != AVR_OK) return 0;
+    if (cudaOccupancyMaxActiveClusters(&n, umma_gemm_kernel<MN_MAJOR, true>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
     std::lock_guard<std::mutex> lock(mu);
     cache[key] = n;
     return n;
 }
+
+static int max_resident_pairs(int device) { return max_resident_pairs_of<false>(device); }
 
 // which launches run as CTA pairs: every wide K-major product over many row tiles.  Measured on the 524800 x 512 x 512
 // layers of the simu signal network (profiles/r2/pair_probe.jsonl): fp16 pairs 0.82 -> 0.66 ms, with the second bf16 copy
@@ -1132,7 +1141,16 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     p.c32 = (float*)workspace; p.ldc32 = ldp;
     p.epi_split = 2; p.epi_warp_bytes = 0; p.epi_bufs = 1;
     if (const char* e = AVR_EXP_ENV("AVR_UMMA_EPI_SPLIT_TN")) p.epi_split = atoi(e) == 1 ? 1 : 2;
-    const int bn_rows = (p.BN + 63) / 64 * 64;
+    // CTA pairs (cta_group::2) for gradients of at least two row tiles: one 256-row MMA per pair, each CTA stages its 128
+    // columns of A and half of the B columns (a third pipeline stage fits).  The split over k is the single-CTA schedule's,
+    // so the partial sums -- and the result -- are bit-identical to it.
+    p.cluster = 1;
+    int pairs = 0;
+    if (!conv_b && K >= 4096 && p.tiles_m >= 2 && p.BN % 32 == 0 && pair_mode_wanted(0, na)) {
+        pairs = max_resident_pairs_of<true>(device);
+        if (pairs > 0) p.cluster = 2;
+    }
+    const int bn_rows = ((p.cluster == 2 ? p.BN / 2 : p.BN) + 63) / 64 * 64;
     const uint32_t stage_bytes = (uint32_t)na * A_PLANE_BYTES + (uint32_t)nb * (uint32_t)bn_rows * 128u;
     p.stages = (int)((220 * 1024) / stage_bytes);
     if (p.stages > 6) p.stages = 6;
@@ -1143,10 +1161,24 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
         CUtensorMap ta, tb;
         if (int rc = make_map(&ta, a_planes, K, M, lda, a_plane, 64, na)) return rc;
         if (int rc = make_map(&tb, b_planes, K, N, ldb, b_plane, 64, nb)) return rc;
-        if (int rc = allow_max_smem<true, false>(device)) return rc;
-        const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
-        const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
-        umma_gemm_kernel<true, false><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, ta, p);
+        if (p.cluster == 2) {
+            const int items = ((p.tiles_m + 1) / 2) * p.tiles_n * p.k_splits;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2u * (unsigned)(items < pairs ? items : pairs));
+            cfg.blockDim = dim3(UTHREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            AVR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<true, true>, ta, tb, ta, ta, ta, p));
+        } else {
+            if (int rc = allow_max_smem<true, false>(device)) return rc;
+            const int tiles = p.tiles_m * p.tiles_n * p.k_splits;
+            const int grid = tiles < num_sms(device) ? tiles : num_sms(device);
+            umma_gemm_kernel<true, false><<<grid, UTHREADS, smem, st>>>(ta, tb, ta, ta, ta, p);
+        }
         AVR_LAUNCH_CHECK();
     } else {
         p.k_splits = 0;
