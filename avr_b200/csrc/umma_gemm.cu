@@ -159,7 +159,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.stages;
     const uint32_t bar_tfull = bar_empty + 8 * p.stages, bar_tempty = bar_tfull + 16, bar_bres = bar_tempty + 16;
     const uint32_t bar_conv = bar_bres + 8;                  // [stages]: the B tile of a stage has been converted (conv_b)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 5);
+    const uint32_t bar_bload = bar_conv + 8 * p.stages;      // [stages]: pair mode + conv_b: THIS CTA's half of the B tile has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * p.stages + 5);
     const uint32_t bres_base = smem_u32(smem);
     const uint32_t smem_base = bres_base + bres_bytes;
     // epilogue staging: (4 or 8) warps x nc planes x 2 KB, 1024-byte aligned, after the barrier block
@@ -172,7 +173,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, pair ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (pair ? 256 : 128) * p.epi_split); }
         mbar_init(bar_bres, 1);
-        for (int s = 0; s < p.stages; ++s) mbar_init(bar_conv + 8 * s, 4 * p.epi_split);     // one arrival per converting warp
+        // one arrival per converting warp (pair mode: of both CTAs, on the leader's barrier)
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_conv + 8 * s, 4 * p.epi_split * (pair ? 2 : 1)); mbar_init(bar_bload + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -216,15 +218,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_tile_bytes;
+                    // pair mode with the in-kernel conversion: the B halves complete on each CTA's OWN barrier (its converting
+                    // warps wait there); the leader's "full" barrier then counts the A bytes only
+                    const bool b_local = pair && MN_MAJOR && p.conv_b;
                     if constexpr (!pair) mbar_expect_tx(full, stage_bytes);
-                    else if (leader) mbar_expect_tx(full, 2u * stage_bytes);
+                    else if (leader) mbar_expect_tx(full, 2u * (b_local ? a_tile_bytes : stage_bytes));
                     else mbar_arrive_cluster(full, 0u);
                     if constexpr (pair && MN_MAJOR) {
                         // my 128 columns of A (two 64-wide boxes) and my half of the B columns
                         tma_load_3d_2sm(sa, &tmA, full, m0, k0, 0);
                         tma_load_3d_2sm(sa + mn_blk_a, &tmA, full, m0 + 64, k0, 0);
-                        for (int i = 0; i < bn_rows / 64; ++i)
-                            tma_load_3d_2sm(sb + mn_blk_b * i, &tmB, full, n0 + (int)crank * bn_rows + 64 * i, k0, 0);
+                        // (my half starts BN / 2 columns into the tile -- not bn_rows, which is BN / 2 rounded up to whole
+                        // 64-column boxes; the columns a box holds beyond the half are never read by the MMAs)
+                        const int nb0 = n0 + (int)crank * (p.BN >> 1);
+                        if (b_local) mbar_expect_tx(bar_bload + 8 * stage, b_tile_bytes);
+                        for (int i = 0; i < bn_rows / 64; ++i) {
+                            if (b_local) tma_load_3d(sb + mn_blk_b * i, &tmB, bar_bload + 8 * stage, nb0 + 64 * i, k0, 0);
+                            else tma_load_3d_2sm(sb + mn_blk_b * i, &tmB, full, nb0 + 64 * i, k0, 0);
+                        }
                     } else if constexpr (pair) {
                         // my row tile and my half of the rows of the column tile; the bytes count on the leader's barrier
                         tma_load_3d_2sm(sa, &tmA, full, k0, m0, 0);
@@ -365,7 +376,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n_conv = 128 * p.epi_split, t_conv = (warp - 2) * 32 + lane;
                 const uint32_t chunks = (uint32_t)(bn_rows / 64) * 512u;          // 16-byte chunks per plane of the B tile
                 for (int k0 = split * UBK; k0 < p.K; k0 += p.k_splits * UBK) {
-                    mbar_wait(bar_full + 8 * cstage, cphase);
+                    mbar_wait((pair ? bar_bload : bar_full) + 8 * cstage, cphase);
                     const uint32_t sb = smem_base + cstage * stage_bytes + a_tile_bytes;
                     for (uint32_t c = t_conv; c < chunks; c += n_conv) {
                         const uint32_t a0 = sb + (c >> 9) * mn_blk_b + (c & 511u) * 16u, a1 = a0 + 8192u;
@@ -383,7 +394,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     fence_async_smem();                                          // generic-proxy writes -> visible to the MMAs
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_conv + 8 * cstage);
+                    if (lane == 0) {
+                        if constexpr (pair) mbar_arrive_cluster(bar_conv + 8 * cstage, 0u);     // the leader's MMA warp waits for both CTAs
+                        else mbar_arrive(bar_conv + 8 * cstage);
+                    }
                     if (++cstage == p.stages) { cstage = 0; cphase ^= 1u; }
                 }
             }
@@ -1146,7 +1160,7 @@ AVR_API int avr_umma_gemm_tn(int64_t M, int64_t N, int64_t K, const void* a_plan
     // so the partial sums -- and the result -- are bit-identical to it.
     p.cluster = 1;
     int pairs = 0;
-    if (!conv_b && K >= 4096 && p.tiles_m >= 2 && p.BN % 32 == 0 && pair_mode_wanted(0, na)) {
+    if (K >= 4096 && p.tiles_m >= 2 && p.BN % 32 == 0 && pair_mode_wanted(0, na)) {
         pairs = max_resident_pairs_of<true>(device);
         if (pairs > 0) p.cluster = 2;
     }

@@ -25,15 +25,16 @@ SIG_HIDDEN_F16 = True
 # (hi, lo' * 2^11) pairs: 24 bits in two planes, THREE products instead of six.  Range: fp16's -- like tiny-cuda-nn's own
 # activations -- inf / NaN beyond 65504 (loud), absolute error <= 1.5e-11 below 6e-5.  False keeps bf16 triples everywhere
 # (a module constant, not an environment switch: tests set it explicitly).
-SIG_TN_FROM_F16 = False
+SIG_TN_FROM_F16 = True
 # The weight-gradient GEMM of such a layer needs its activation as a bf16 pair (the gradient operand needs bf16's range,
-# and tcgen05.mma faults on a bf16 x f16 mix).  False (default): the producing layer writes each hidden activation twice
-# (ops.UMMA_DUAL_COPY: fp16 pair + bf16 pair).  True: avr_umma_gemm_tn takes the fp16 pair and its epilogue warps, idle
-# during the main loop, convert every tile to bf16 (hi, mid) in shared memory -- bit-identical gradients, 2.1 GB less HBM
-# traffic and activation memory per simu step, the two forward layers 0.82 -> 0.62 and 0.79 -> 0.65 ms, BUT the two
-# 512 x 512 weight-gradient GEMMs 0.61 -> 0.87 ms each: with two 96 KB pipeline stages per CTA the conversion (~1 000 clk
-# after the tile has landed) sits on the stage's critical path.  Net on one box, interleaved: 11.76 vs 11.65 ms per step
-# (profiles/ab_tn_from_f16.py, profiles/r2/ab_tn_from_f16.txt) -- kept as the memory-saving option, not the default.
+# and tcgen05.mma faults on a bf16 x f16 mix).  True (default): avr_umma_gemm_tn takes the fp16 pair and its epilogue warps,
+# idle during the main loop, convert every tile to bf16 (hi, mid) in shared memory -- bit-identical gradients, 2.1 GB less
+# HBM traffic and activation memory per simu step, the two forward layers 0.82 -> 0.62 and 0.79 -> 0.65 ms.  False: the
+# producing layer writes each hidden activation twice (ops.UMMA_DUAL_COPY: fp16 pair + bf16 pair).
+# History (profiles/r2/ab_tn_from_f16*.txt, interleaved runs on one box): on the single-CTA weight-gradient kernel (two
+# 96 KB pipeline stages, the conversion on the stage's critical path: 0.61 -> 0.87 ms per 512 x 512 gradient) it was a net
+# loss, 11.76 vs 11.65 ms per step; as CTA pairs (each CTA converts only its half of the B tile, three 64 KB stages) it
+# is a net gain: 11.28 vs 11.54 ms.
 BWD_PLANES = 2      # gradients enter linearly: 16 bits / three products are enough ...
 DENSITY_BWD_PLANES = 3   # ... except along the sigma decoder: the density gradient of a ray sums to ~0 over its samples
                          # (sum_s w_s = 1), so the decoder's weight-gradient sums cancel to ~1/50 of their terms

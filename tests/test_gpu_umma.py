@@ -242,7 +242,7 @@ def test_umma_near_zero_guard(built_library, M, N, K, mode):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (512, 512, 20000), (16, 128, 5000), (128, 48, 3001), (512, 208, 7777),
-                                   (1600, 512, 4100), (128, 80, 64)])
+                                   (1600, 512, 4100), (128, 80, 64), (512, 464, 9000), (256, 160, 4200)])   # 160-column tiles: halves of 80
 def test_umma_tn_weight_grad(built_library, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     dY, X = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
@@ -258,7 +258,8 @@ def test_umma_tn_weight_grad(built_library, M, N, K):
     assert float(outs[0][:, N:].abs().max()) == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(512, 512, 40000), (512, 208, 9001), (128, 80, 3000), (512, 512, 128 * 148 * 3 + 77)])
+@pytest.mark.parametrize("M,N,K", [(512, 512, 40000), (512, 208, 9001), (128, 80, 3000), (512, 512, 128 * 148 * 3 + 77),
+                                   (512, 464, 8320), (256, 160, 5000)])
 def test_umma_tn_fp16_pair_activation_converted_in_kernel(built_library, M, N, K):
     """Weight gradient whose activation operand is an fp16 (hi, lo') pair: the kernel's epilogue warps turn every tile into a
     bf16 (hi, mid) pair in shared memory (umma_gemm.cu, conv_b).  Bit-identical to handing it the bf16 pair that
