@@ -13,9 +13,12 @@ update is part of the metric ("receivers*steps / time for forward+bac
 What the JSON line holds, and how each number was taken:
 
 * ``value``       K steps, inputs resident in HBM, NO per-kernel events, one CUDA-event pair around the K steps, max over ranks.
-* ``e2e``         the same K steps through ``AVRRender.forward`` with pinned HOST inputs: H2D of the positions (and the
-                  per-step direction table) and an asynchronous D2H of the spectra into a pinned buffer every step; the
-                  steps are not synchronised one by one (throughput, not latency), the region ends with a full sync.
+                  Timed after the W warm-up steps plus ~1.5 s of further untimed steps (``warmup_note``): the power-capped
+                  GPUs run the first tenths of a second after idle 2-3 % faster than the steady state.
+* ``e2e``         the same K steps through ``AVRRender.forward`` with pinned HOST inputs: every step copies its positions
+                  (on a copy stream, one step ahead: two device buffers; the per-step direction table inside forward) and
+                  copies its spectra back to a pinned buffer right after the forward pass; the steps are not synchronised
+                  one by one (throughput, not latency), the region ends with a full device sync.
 * ``kernels`` / ``roofline``   a THIRD pass with CUDA events around every library call (``ops.PROFILE``).
 * ``grid_grad_atomic``         the same workload with fp32-atomic table gradients instead of the deterministic default.
 * ``other_configs``            the other BASELINE shapes (configs[2..4]) measured in this very run, 5 steps each, through the
